@@ -1,0 +1,35 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import torch
+
+    cache = {}
+
+    def load(name):
+        if name not in cache:
+            cache[name] = torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+        return cache[name]
+
+    return load
+
+
+def max_rel_err(a, b):
+    """max|a-b| / max|b|  (SURVEY.md Appendix C block metric)."""
+    a = a.double()
+    b = b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
