@@ -1,0 +1,168 @@
+/* svit_b200 -- C ABI of the B200 (sm_100a) kernels behind the SViT pooled-attention hot path.
+ *
+ * The reference (eladb3/SViT) is pure Python: its "FFI" for this path is the set of torch ops that
+ * slowfast/models/attention.py, stem_helper.py, common.py and video_model_builder.py dispatch.  Each
+ * entry point below replaces one of those op sites (cited per function); the Python host code in
+ * svit_b200/ binds them with ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates; the library allocates
+ *     nothing persistent and keeps no state except cached TMA descriptors, freed by svit_destroy()).
+ *   - `stream` is a cudaStream_t; calls are asynchronous, never synchronise, and are graph-capturable.
+ *   - return value: 0 = ok, < 0 = argument error (SVIT_EINVAL -1, SVIT_ENOTSUP -2), > 0 = cudaError_t.
+ *   - dtype: SVIT_F32 (0) or SVIT_BF16 (1) = storage type of activations; arithmetic is fp32 (SIMT path)
+ *     or bf16 x bf16 -> fp32 (tcgen05 path).  Parameters (LN affine, conv taps, biases) are fp32.
+ *   - token layout of every sequence: [cls | T*H*W patch tokens (t, h, w row-major) | O object tokens].
+ *   - no CPU fallback exists.
+ */
+#ifndef SVIT_B200_H
+#define SVIT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVIT_DTYPE_F32 0
+#define SVIT_DTYPE_BF16 1
+
+/* Library / build identification: returns the compiled arch (100 for sm_100a). */
+int svit_abi_version(void);
+int svit_destroy(void);
+
+/* ---- LayerNorm(C, eps) over tokens: attention.py:558,566 (norm1/norm2), video_model_builder.py:375 (norm).
+ * mean/rstd ([rows], fp32) may be NULL in inference. */
+int svit_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       int64_t rows, int C, float eps, int dtype, void* stream);
+/* dgamma/dbeta are accumulated into (+=). */
+int svit_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                       void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int dtype, void* stream);
+
+/* ---- attention_pool with a Conv3d pool + LayerNorm: attention.py:13-65 (called at :368-388).
+ * in: token (b, n) of head hd starts at in + b*in_batch_stride + n*in_tok_stride + hd*in_head_stride
+ *     (element strides; lets the kernel read q/k/v slices of the packed qkv GEMM output in place).
+ * conv_w [96*27] = pool.weight.reshape(96, 27); tap_frac [27] = fraction of the conv outputs of a 3x3x3
+ * constant cube for which each tap is in bounds (host-computed geometry constant; w_eff = conv_w . tap_frac).
+ * out [B, h, 1 + T*Ho*Wo + O, 96], Ho = (H-1)/stride_hw + 1. */
+int svit_pool_ln_fwd(const void* in, int64_t in_batch_stride, int64_t in_tok_stride, int64_t in_head_stride,
+                     const float* conv_w, const float* tap_frac, const float* gamma, const float* beta, void* out,
+                     int B, int h, int T, int H, int W, int O, int stride_hw, float eps, int dtype, void* stream);
+/* dpre: scratch shaped like `out`; dz written with the strides of `in`; dw[96*27], dgamma, dbeta += . */
+int svit_pool_ln_bwd(const void* in, int64_t in_batch_stride, int64_t in_tok_stride, int64_t in_head_stride,
+                     const float* conv_w, const float* tap_frac, const float* gamma, const void* dout, void* dpre,
+                     void* dz, float* dw, float* dgamma, float* dbeta, int B, int h, int T, int H, int W, int O,
+                     int stride_hw, float eps, int dtype, void* stream);
+
+/* ---- skip-path attention_pool with MaxPool3d k(1,3,3) s(1,s,s) p(0,1,1): attention.py:503-505,549-555,562-564.
+ * x [B, 1+T*H*W+O, C] -> y [B, 1+T*Ho*Wo+O, C]; cls and object rows are copied. stride_hw must be >= 2. */
+int svit_skip_maxpool_fwd(const void* x, void* y, int B, int C, int T, int H, int W, int O, int stride_hw, int dtype,
+                          void* stream);
+int svit_skip_maxpool_bwd(const void* x, const void* dy, void* dx, int B, int C, int T, int H, int W, int O,
+                          int stride_hw, int dtype, void* stream);
+
+/* ---- GEMM with fused epilogue: nn.Linear sites attention.py:345 (qkv), :462 (proj), :561 (skip proj),
+ * common.py:27-34 (fc1+GELU, fc2), stem_helper.py:317 (patch embed as im2col GEMM), and their gradients.
+ *   C[M,N] = residual + sample_scale[row / rows_per_sample] * ( act(op(A).op(B) + bias) * gelu'(gelu_pre) )
+ * Row-major storage.  transA=0: A is [M,K] (lda); 1: A is [K,M].  transB=1: B is [N,K] (nn.Linear weight); 0: [K,N].
+ * Output row remap (rows_in > 0): row m -> (m / rows_in) * rows_out + row_off + m % rows_in (writes patch tokens
+ * straight into rows 1..L of the [B, 1+L+O, C] sequence; residual uses the remapped row). */
+typedef struct svit_gemm_args {
+  const void* A;
+  const void* B;
+  void* C;
+  int64_t M, N, K, lda, ldb, ldc;
+  int32_t transA, transB;
+  const float* bias;         /* [N] or NULL */
+  const void* residual;      /* [*, N] (ldr), activation dtype, or NULL */
+  int64_t ldr;
+  const float* sample_scale; /* DropPath mask / keep_prob per sample, or NULL (common.py:46-59) */
+  int64_t rows_per_sample;
+  const void* gelu_pre;      /* multiply by gelu'(gelu_pre[m,n]) (ldg): backward through common.py:31 */
+  int64_t ldg;
+  void* pre_out;             /* store the pre-activation (after bias) for that backward (ldp), or NULL */
+  int64_t ldp;
+  int32_t act;               /* 0 none, 1 exact-erf GELU */
+  int64_t rows_in, rows_out, row_off;
+  int32_t dtype;             /* dtype of A, B, residual, gelu_pre, pre_out */
+  int32_t out_dtype;         /* dtype of C */
+  int32_t impl;              /* 0 auto (tcgen05 when bf16 and the shape qualifies), 1 CUDA cores, 2 tcgen05 */
+} svit_gemm_args;
+int svit_gemm(const svit_gemm_args* args, void* stream);
+/* out[n] += sum_m x[m,n]  (bias gradients) */
+int svit_colsum(const void* x, float* out, int64_t M, int N, int64_t ld, int dtype, void* stream);
+
+/* ---- pooled attention core: attention.py:429-459 with cal_rel_pos_spatial (:84-137) and
+ * cal_rel_pos_temporal (:140-183) fused into the score tile and the residual-pooling add (:455-459).
+ *   S = scale * q k^T ; S[patch q, patch k] += q . (Rh[i,i'] + Rw[j,j'] + Rt[t,t']) (un-scaled q)
+ *   out = softmax(S) v ; out[rows >= 1] += q
+ * q [B,h,Nq,96], k/v [B,h,Nk,96]; rel_* are the GATHERED tables R[a, b, :] (activation dtype), built on the host
+ * side with the reference's exact fp32 index expression; out [B, Nq, h, 96] (heads merged). lse [B,h,Nq] or NULL. */
+typedef struct svit_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* rel_h; /* [qh, kh, 96] */
+  const void* rel_w; /* [qw, kw, 96] */
+  const void* rel_t; /* [qt, kt, 96] */
+  void* out;
+  float* lse;
+  int32_t B, h, qt, qh, qw, kt, kh, kw, O;
+  float scale;
+  int32_t dtype;
+  int32_t impl; /* 0 auto, 1 CUDA cores, 2 tcgen05 */
+  /* backward only */
+  const void* dout; /* [B, Nq, h, 96] */
+  void* dq;         /* [B,h,Nq,96] */
+  void* dk;         /* [B,h,Nk,96] */
+  void* dv;
+  float* d_rel_h;   /* fp32, same shapes as rel_*, accumulated into (+=) */
+  float* d_rel_w;
+  float* d_rel_t;
+  float* ws_e;      /* scratch [B,h,Nq,kh+kw+kt] fp32: bias terms E */
+  float* ws_de;     /* scratch [B,h,Nq,kh+kw+kt] fp32: dE */
+  float* ws_delta;  /* scratch [B,h,Nq] fp32 */
+} svit_attn_args;
+int svit_attn_fwd(const svit_attn_args* args, void* stream);
+int svit_attn_bwd(const svit_attn_args* args, void* stream);
+
+/* y[m,:] = x[m,:] * scale[m / rows_per_sample]: DropPath backward (common.py:46-59). */
+int svit_scale_rows(const void* x, const float* scale, void* y, int64_t rows, int C, int64_t rows_per_sample, int dtype,
+                    void* stream);
+
+/* ---- token assembly: video_model_builder.py:326-330 (cls) and :354-363 (object tokens).
+ * x [B, 1+L+Tx*O, C]: row 0 = cls; row 1+L+t*O+o = queries[o] + (Tx > 1 ? pos_t[t] : 0). Patch rows untouched. */
+int svit_assemble_tokens_fwd(void* x, const float* cls, const float* queries, const float* pos_t, int B, int64_t L,
+                             int Tx, int O, int C, int dtype, void* stream);
+int svit_assemble_tokens_bwd(const void* dx, float* dcls, float* dqueries, float* dpos_t, int B, int64_t L, int Tx,
+                             int O, int C, int dtype, void* stream);
+
+/* ---- PatchEmbed im2col: stem_helper.py:309-320 (Conv3d k(3,7,7) s(2,4,4) p(1,3,3)) lowered to a GEMM.
+ * cols [B*To*Ho*Wo, Kpad], column order (c, kt, kh, kw), zero padded to Kpad. */
+int svit_im2col3d(const void* x, void* cols, int B, int Cin, int T, int H, int W, int kt, int kh, int kw, int st, int sh,
+                  int sw, int pt, int ph, int pw, int Kpad, int in_dtype, int out_dtype, void* stream);
+
+/* ---- token split: video_model_builder.py:377-384. out [B, 1+O, C] = rows {0} U {N-O .. N-1} of x [B, N, C]. */
+int svit_gather_cls_obj_fwd(const void* x, void* out, int B, int64_t N, int O, int C, int dtype, void* stream);
+int svit_gather_cls_obj_bwd(const void* dout, void* dx, int B, int64_t N, int O, int C, int dtype, void* stream);
+
+/* ---- box-conditioned object tokens: call site video_model_builder.py:385-392, 472-491 (RoIAlign 7x7,
+ * spatial_scale 1/16, aligned, sampling_ratio 0 -> adaptive) applied per frame.
+ * feat: token-major features; patch token (b, s, y, x) at feat + b*feat_batch_stride + (1 + (s*Hf + y)*Wf + x)*C.
+ * boxes [B, Tx, K, 4] xyxy input pixels (fp32). tokens [B, Tx*K, C] = max over the P x P RoIAlign bins;
+ * frame t reads temporal slice t / patch_stride_t (t when Tf == 1). assign [B, Tx*K, 2] int32 = (b, slice). */
+int svit_roi_tokens_fwd(const void* feat, int64_t feat_batch_stride, const float* boxes, void* tokens, int32_t* assign,
+                        int B, int C, int Tf, int Hf, int Wf, int Tx, int K, int patch_stride_t, float spatial_scale,
+                        int P, int dtype, void* stream);
+/* plain RoIAlign (torchvision semantics, aligned flag) on a channels-last map [N, H, W, C]; rois [R,5]; out [R,P,P,C] */
+int svit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, int P,
+                       float spatial_scale, int sampling_ratio, int aligned, int dtype, void* stream);
+
+/* ---- box -> slot integer logic on device (utils/box_ops.py:140-194 match_haog; :116-130 zero_empty_boxes).
+ * boxes [n, 4, 4] fp32 in/out; contact [n, 2] int64 out. */
+int svit_match_haog(float* boxes, int64_t* contact, int64_t n, void* stream);
+int svit_zero_empty_boxes(float* boxes_cxcywh, int64_t n, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,171 @@
+// fp32-accumulate CUDA-core GEMM with the fused epilogue of the hot path.  This is the fp32 parity
+// mode (TF32 off; <=1e-4 per block against the reference) and the fallback shape handler; the bf16
+// production path is the tcgen05 kernel in gemm_tc.cu, which shares the argument struct.
+//
+//   C[M,N] = epi( op(A)[M,K] . op(B)[K,N] )       row-major storage, op = optional transpose
+//   epi(v) = residual + sample_scale[row / rows_per_sample] * ( act(v + bias) * gelu'(gelu_pre) )
+//
+// Used for: qkv / proj / skip-proj / fc1(+GELU) / fc2(+residual) (attention.py:345,462,561; common.py:27-34),
+// the patch-embed GEMM (stem_helper.py:317) and every dgrad / wgrad of those.
+#include "common.cuh"
+#include "../../include/svit_b200.h"
+
+#define BM 64
+#define BN 64
+#define BK 16
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(svit_gemm_args a) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const TI* __restrict__ A = (const TI*)a.A;
+  const TI* __restrict__ Bm = (const TI*)a.B;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = 0; k0 < a.K; k0 += BK) {
+    // ---- A tile -> As[k][m]
+    if (!a.transA) {
+      int m = tid >> 2, kk = (tid & 3) * 4;
+      int64_t gm = m0 + m;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int64_t gk = k0 + kk + i;
+        As[kk + i][m] = (gm < a.M && gk < a.K) ? to_f(A[gm * a.lda + gk]) : 0.f;
+      }
+    } else {
+      int kk = tid >> 4, m = (tid & 15) * 4;
+      int64_t gk = k0 + kk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int64_t gm = m0 + m + i;
+        As[kk][m + i] = (gm < a.M && gk < a.K) ? to_f(A[gk * a.lda + gm]) : 0.f;
+      }
+    }
+    // ---- B tile -> Bs[k][n]
+    if (a.transB) {  // stored [N, K]
+      int n = tid >> 2, kk = (tid & 3) * 4;
+      int64_t gn = n0 + n;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int64_t gk = k0 + kk + i;
+        Bs[kk + i][n] = (gn < a.N && gk < a.K) ? to_f(Bm[gn * a.ldb + gk]) : 0.f;
+      }
+    } else {  // stored [K, N]
+      int kk = tid >> 4, n = (tid & 15) * 4;
+      int64_t gk = k0 + kk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int64_t gn = n0 + n + i;
+        Bs[kk][n + i] = (gn < a.N && gk < a.K) ? to_f(Bm[gk * a.ldb + gn]) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- fused epilogue
+  TO* __restrict__ C = (TO*)a.C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t m = m0 + ty * 4 + i;
+    if (m >= a.M) continue;
+    float sc = a.sample_scale ? a.sample_scale[m / a.rows_per_sample] : 1.f;
+    int64_t orow = a.rows_in > 0 ? (m / a.rows_in) * a.rows_out + a.row_off + (m % a.rows_in) : m;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t n = n0 + tx * 4 + j;
+      if (n >= a.N) continue;
+      float v = acc[i][j];
+      if (a.bias) v += a.bias[n];
+      if (a.pre_out) ((TI*)a.pre_out)[m * a.ldp + n] = from_f<TI>(v);
+      if (a.act == 1) v = gelu_erf(v);
+      if (a.gelu_pre) v *= gelu_erf_grad(to_f(((const TI*)a.gelu_pre)[m * a.ldg + n]));
+      v *= sc;
+      if (a.residual) v += to_f(((const TI*)a.residual)[orow * a.ldr + n]);
+      C[orow * a.ldc + n] = from_f<TO>(v);
+    }
+  }
+}
+
+// column sums of a [M, N] matrix (bias gradients): out[n] += sum_m x[m, n]
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t M, int N, int64_t ld,
+                              int64_t rows_per_cta) {
+  int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) s += to_f(x[r * ld + n]);
+    atomicAdd(&out[n], s);
+  }
+}
+
+int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st);  // gemm_tc.cu
+int svit_gemm_tc_supported(const svit_gemm_args* a);
+
+static int gemm_simt(const svit_gemm_args* a, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div64(a->N, BN), (unsigned)ceil_div64(a->M, BM));
+  if (a->dtype == SVIT_F32 && a->out_dtype == SVIT_F32)
+    gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>(*a);
+  else if (a->dtype == SVIT_BF16 && a->out_dtype == SVIT_BF16)
+    gemm_simt_kernel<bf16, bf16><<<grid, 256, 0, st>>>(*a);
+  else if (a->dtype == SVIT_BF16 && a->out_dtype == SVIT_F32)
+    gemm_simt_kernel<bf16, float><<<grid, 256, 0, st>>>(*a);
+  else
+    return SVIT_EINVAL;
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" {
+
+int svit_gemm(const svit_gemm_args* a, void* stream) {
+  if (!a || !a->A || !a->B || !a->C) return SVIT_EINVAL;
+  if (a->M < 0 || a->N < 0 || a->K < 0) return SVIT_EINVAL;
+  if (a->sample_scale && a->rows_per_sample <= 0) return SVIT_EINVAL;
+  if (a->M == 0 || a->N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->impl == 2) {
+    if (!svit_gemm_tc_supported(a)) return SVIT_ENOTSUP;
+    return svit_gemm_tc(a, st);
+  }
+  if (a->impl == 0 && svit_gemm_tc_supported(a)) return svit_gemm_tc(a, st);
+  return gemm_simt(a, st);
+}
+
+int svit_colsum(const void* x, float* out, int64_t M, int N, int64_t ld, int dtype, void* stream) {
+  if (M < 0 || N < 0) return SVIT_EINVAL;
+  if (M == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t rows_per_cta = 512;
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)ceil_div64(M, rows_per_cta));
+  if (dtype == SVIT_F32)
+    colsum_kernel<float><<<grid, 128, 0, st>>>((const float*)x, out, M, N, ld, rows_per_cta);
+  else if (dtype == SVIT_BF16)
+    colsum_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)x, out, M, N, ld, rows_per_cta);
+  else
+    return SVIT_EINVAL;
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+"""Drop-in replacements for the reference's pooled-attention modules, running on the sm_100a kernels.
+
+  MultiScaleAttention  <->  slowfast/models/attention.py:186-466
+  MultiScaleBlock      <->  slowfast/models/attention.py:469-571
+  attention_pool       <->  slowfast/models/attention.py:13-65
+
+Constructor signatures, parameter names/shapes (state_dict keys) and forward signatures are the
+reference's, so reference checkpoints load unchanged and `VitHooks` (visualization/vis_utils.py:29,69)
+still sees `(x, q_shape)` from `blocks.{i}.attn`.  The supported configuration is the subset
+configs/ssv2.yaml exercises (mode="conv", pool_first=False, separate_qkv=False, cls token on,
+decomposed rel-pos on, residual pooling on, 3x3x3 pooling kernels with temporal stride 1, head_dim 96);
+anything else raises NotImplementedError, as the reference itself does for unknown modes (:306).
+
+nn.Linear / nn.Conv3d / nn.LayerNorm sub-modules are kept purely as parameter containers (same names,
+same default initialisation); their forward() is never called.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+from torch.nn.init import trunc_normal_
+
+from . import ops
+
+HEAD_DIM = ops.HEAD_DIM
+
+
+def rel_pos_index_table(q_n: int, k_n: int) -> torch.Tensor:
+    """Integer table dist[i, j] of the decomposed rel-pos bias, computed with the reference's exact fp32
+    torch expression (attention.py:100-106, 156-163) on the host so that .long() truncates identically."""
+    q_ratio = max(k_n / q_n, 1.0)
+    k_ratio = max(q_n / k_n, 1.0)
+    dist = torch.arange(q_n)[:, None] * q_ratio - torch.arange(k_n)[None, :] * k_ratio
+    dist += (k_n - 1) * k_ratio
+    return dist.long()
+
+
+_idx_cache = {}
+
+
+def _index_on(device, q_n, k_n):
+    key = (str(device), q_n, k_n)
+    if key not in _idx_cache:
+        _idx_cache[key] = rel_pos_index_table(q_n, k_n).to(device)
+    return _idx_cache[key]
+
+
+def gathered_rel_pos(rel_pos: torch.Tensor, q_n: int, k_n: int) -> torch.Tensor:
+    """R[a, b, :] = get_rel_pos(rel_pos, 2*max(q,k)-1)[dist[a, b]]  (attention.py:68-81, 116-119).
+    Small torch glue (tables are <= 111 x 96) that keeps autograd to the parameter."""
+    d = int(2 * max(q_n, k_n) - 1)
+    tab = rel_pos
+    if tab.shape[0] != d:
+        tab = torch.nn.functional.interpolate(tab.reshape(1, tab.shape[0], -1).permute(0, 2, 1), size=d, mode="linear")
+        tab = tab.reshape(-1, d).permute(1, 0)
+    return tab[_index_on(rel_pos.device, q_n, k_n)]
+
+
+def _stride_hw(stride: Sequence[int]) -> int:
+    if len(stride) == 0:
+        return 1
+    if stride[0] != 1 or stride[1] != stride[2]:
+        raise NotImplementedError(f"pool stride {tuple(stride)}: only (1, s, s) is supported")
+    return int(stride[1])
+
+
+def attention_pool(tensor, pool, thw_shape, has_cls_embed=True, norm=None):
+    """Functional form kept for API parity (attention.py:13-65).  `pool` is an nn.Conv3d container
+    (3x3x3 depthwise, stride (1,s,s)) with `norm` an nn.LayerNorm(96), or an nn.MaxPool3d skip pool."""
+    if pool is None:
+        return tensor, thw_shape
+    if not has_cls_embed:
+        raise NotImplementedError("has_cls_embed=False")
+    T, H, W = thw_shape
+    if isinstance(pool, nn.MaxPool3d):
+        if tensor.ndim != 3:
+            raise NotImplementedError("max-pool skip path expects [B, N, C]")
+        s = _stride_hw(pool.stride)
+        O = tensor.shape[1] - 1 - T * H * W
+        assert O > 0
+        return ops.skip_pool(tensor, thw_shape, O, s), [T, ops.pooled_hw(H, s), ops.pooled_hw(W, s)]
+    if isinstance(pool, nn.Conv3d):
+        if tensor.ndim != 4 or norm is None or tensor.shape[-1] != HEAD_DIM:
+            raise NotImplementedError("conv pool expects [B, h, N, 96] and a LayerNorm")
+        s = _stride_hw(pool.stride)
+        B, h, N, d = tensor.shape
+        O = N - 1 - T * H * W
+        assert O > 0
+        # single-tensor call: present it as a degenerate packed tensor (q = k = v slot 0)
+        packed = tensor.permute(0, 2, 1, 3).reshape(B, N, h * d)
+        packed = torch.cat([packed, packed, packed], dim=-1)
+        q, _, _ = ops.qkv_pool(packed, thw_shape, O, s, s, pool.weight, (norm.weight, norm.bias), pool.weight,
+                               (norm.weight, norm.bias), pool.weight, (norm.weight, norm.bias))
+        return q, [T, ops.pooled_hw(H, s), ops.pooled_hw(W, s)]
+    raise NotImplementedError(type(pool))
+
+
+class MultiScaleAttention(nn.Module):
+    def __init__(self, dim, dim_out, input_size, num_heads=8, qkv_bias=False, drop_rate=0.0, kernel_q=(1, 1, 1),
+                 kernel_kv=(1, 1, 1), stride_q=(1, 1, 1), stride_kv=(1, 1, 1), norm_layer=nn.LayerNorm,
+                 has_cls_embed=True, mode="conv", pool_first=False, rel_pos_spatial=False, rel_pos_temporal=False,
+                 rel_pos_zero_init=False, residual_pooling=False, separate_qkv=False):
+        super().__init__()
+        if mode != "conv":
+            raise NotImplementedError(f"Unsupported model {mode}")
+        if pool_first or separate_qkv or not has_cls_embed or drop_rate > 0.0:
+            raise NotImplementedError("svit_b200 supports pool_first=False, separate_qkv=False, cls token, drop_rate=0")
+        if not (rel_pos_spatial and rel_pos_temporal and residual_pooling):
+            raise NotImplementedError("svit_b200 fuses rel_pos_spatial/temporal and residual pooling; all must be on")
+        if tuple(kernel_q) != (3, 3, 3) or tuple(kernel_kv) != (3, 3, 3):
+            raise NotImplementedError("pooling kernels must be (3, 3, 3) (MVIT.POOL_KVQ_KERNEL)")
+        if dim_out // num_heads != HEAD_DIM:
+            raise NotImplementedError("head_dim must be 96")
+        self.pool_first = pool_first
+        self.separate_qkv = separate_qkv
+        self.drop_rate = drop_rate
+        self.num_heads = num_heads
+        self.dim_out = dim_out
+        head_dim = dim_out // num_heads
+        self.scale = head_dim ** -0.5
+        self.has_cls_embed = has_cls_embed
+        self.mode = mode
+        self._sq, self._skv = _stride_hw(stride_q), _stride_hw(stride_kv)
+
+        self.qkv = nn.Linear(dim, dim_out * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim_out, dim_out)
+        mk = lambda st: nn.Conv3d(head_dim, head_dim, tuple(kernel_q), stride=tuple(st), padding=(1, 1, 1),
+                                  groups=head_dim, bias=False)
+        self.pool_q = mk(stride_q)
+        self.norm_q = norm_layer(head_dim)
+        self.pool_k = mk(stride_kv)
+        self.norm_k = norm_layer(head_dim)
+        self.pool_v = mk(stride_kv)
+        self.norm_v = norm_layer(head_dim)
+
+        self.rel_pos_spatial = rel_pos_spatial
+        self.rel_pos_temporal = rel_pos_temporal
+        assert input_size[1] == input_size[2]
+        size = input_size[1]
+        q_size = size // stride_q[1] if len(stride_q) > 0 else size
+        kv_size = size // stride_kv[1] if len(stride_kv) > 0 else size
+        rel_sp_dim = 2 * max(q_size, kv_size) - 1
+        self.rel_pos_h = nn.Parameter(torch.zeros(rel_sp_dim, head_dim))
+        self.rel_pos_w = nn.Parameter(torch.zeros(rel_sp_dim, head_dim))
+        self.rel_pos_t = nn.Parameter(torch.zeros(2 * input_size[0] - 1, head_dim))
+        if not rel_pos_zero_init:
+            trunc_normal_(self.rel_pos_h, std=0.02)
+            trunc_normal_(self.rel_pos_w, std=0.02)
+            trunc_normal_(self.rel_pos_t, std=0.02)
+        self.residual_pooling = residual_pooling
+
+    def forward(self, x, thw_shape, residual: Optional[torch.Tensor] = None,
+                sample_scale: Optional[torch.Tensor] = None):
+        """x [B, N, C] -> (y [B, Nq, dim_out], q_shape).  `residual` / `sample_scale` are optional fusion
+        hooks used by MultiScaleBlock: y = residual + sample_scale[b] * proj(attn)."""
+        B, N, _ = x.shape
+        T, H, W = thw_shape
+        O = N - 1 - T * H * W
+        assert O > 0
+        qkv = ops.linear(x, self.qkv.weight, self.qkv.bias)
+        q, k, v = ops.qkv_pool(qkv, thw_shape, O, self._sq, self._skv,
+                               self.pool_q.weight, (self.norm_q.weight, self.norm_q.bias),
+                               self.pool_k.weight, (self.norm_k.weight, self.norm_k.bias),
+                               self.pool_v.weight, (self.norm_v.weight, self.norm_v.bias))
+        q_shape = [T, ops.pooled_hw(H, self._sq), ops.pooled_hw(W, self._sq)]
+        k_shape = [T, ops.pooled_hw(H, self._skv), ops.pooled_hw(W, self._skv)]
+        Rh = gathered_rel_pos(self.rel_pos_h, q_shape[1], k_shape[1])
+        Rw = gathered_rel_pos(self.rel_pos_w, q_shape[2], k_shape[2])
+        Rt = gathered_rel_pos(self.rel_pos_t, q_shape[0], k_shape[0])
+        o = ops.attention(q, k, v, Rh, Rw, Rt, q_shape, k_shape, O, self.scale)
+        y = ops.linear(o, self.proj.weight, self.proj.bias, residual=residual, sample_scale=sample_scale)
+        return y, q_shape
+
+
+class Mlp(nn.Module):
+    """fc1 -> exact-erf GELU -> fc2 (common.py:7-34), one fused call."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop_rate=0.0):
+        super().__init__()
+        if drop_rate > 0.0 or act_layer is not nn.GELU:
+            raise NotImplementedError("Mlp: drop_rate must be 0 and act_layer nn.GELU")
+        self.drop_rate = drop_rate
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+
+    def forward(self, x, residual=None, sample_scale=None):
+        return ops.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual, sample_scale)
+
+
+class DropPath(nn.Module):
+    """Stochastic depth (common.py:46-70).  Produces the per-sample scale (mask / keep_prob) that the GEMM
+    epilogues apply; the random draw is torch's so the stream matches the reference's draw order."""
+
+    def __init__(self, drop_prob=None):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def sample_scale(self, x: torch.Tensor) -> Optional[torch.Tensor]:
+        if not self.drop_prob or not self.training:
+            return None
+        keep = 1 - self.drop_prob
+        mask = keep + torch.rand((x.shape[0],) + (1,) * (x.ndim - 1), dtype=x.dtype, device=x.device)
+        mask.floor_()
+        return (mask.reshape(-1).float() / keep).contiguous()
+
+    def forward(self, x):
+        s = self.sample_scale(x)
+        return x if s is None else ops._scale_rows(x.contiguous(), s, x[0].numel() // x.shape[-1])
+
+
+class MultiScaleBlock(nn.Module):
+    def __init__(self, dim, dim_out, num_heads, input_size, mlp_ratio=4.0, qkv_bias=False, qk_scale=None,
+                 drop_rate=0.0, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, up_rate=None,
+                 kernel_q=(1, 1, 1), kernel_kv=(1, 1, 1), stride_q=(1, 1, 1), stride_kv=(1, 1, 1), mode="conv",
+                 has_cls_embed=True, pool_first=False, rel_pos_spatial=False, rel_pos_temporal=False,
+                 rel_pos_zero_init=False, residual_pooling=False, dim_mul_in_att=False, separate_qkv=False):
+        super().__init__()
+        if not dim_mul_in_att:
+            raise NotImplementedError("dim_mul_in_att=False")
+        if up_rate is not None and up_rate > 1:
+            raise NotImplementedError("up_rate")
+        self.dim = dim
+        self.dim_out = dim_out
+        self.norm1 = norm_layer(dim)
+        self.dim_mul_in_att = dim_mul_in_att
+        att_dim = dim_out
+        self.attn = MultiScaleAttention(dim, att_dim, num_heads=num_heads, input_size=input_size, qkv_bias=qkv_bias,
+                                        drop_rate=drop_rate, kernel_q=kernel_q, kernel_kv=kernel_kv, stride_q=stride_q,
+                                        stride_kv=stride_kv, norm_layer=norm_layer, has_cls_embed=has_cls_embed,
+                                        mode=mode, pool_first=pool_first, rel_pos_spatial=rel_pos_spatial,
+                                        rel_pos_temporal=rel_pos_temporal, rel_pos_zero_init=rel_pos_zero_init,
+                                        residual_pooling=residual_pooling, separate_qkv=separate_qkv)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(att_dim)
+        self.has_cls_embed = has_cls_embed
+        self.mlp = Mlp(in_features=att_dim, hidden_features=int(att_dim * mlp_ratio), out_features=dim_out,
+                       act_layer=act_layer, drop_rate=drop_rate)
+        if dim != dim_out:
+            self.proj = nn.Linear(dim, dim_out)
+        kernel_skip = [s + 1 if s > 1 else s for s in stride_q]
+        self.pool_skip = (nn.MaxPool3d(kernel_skip, list(stride_q), [int(k // 2) for k in kernel_skip], ceil_mode=False)
+                          if len(kernel_skip) > 0 else None)
+        self._sq = _stride_hw(stride_q)
+
+    def _scale(self, x):
+        return self.drop_path.sample_scale(x) if isinstance(self.drop_path, DropPath) else None
+
+    def forward(self, x, thw_shape):
+        T, H, W = thw_shape
+        O = x.shape[1] - 1 - T * H * W
+        x_norm = ops.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        if self.dim != self.dim_out:
+            x = ops.linear(x_norm, self.proj.weight, self.proj.bias)  # skip path uses the normalised input (:560-561)
+        x_res = ops.skip_pool(x, thw_shape, O, self._sq)
+        x, thw_new = self.attn(x_norm, thw_shape, residual=x_res, sample_scale=self._scale(x))
+        x_norm2 = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        x = self.mlp(x_norm2, residual=x, sample_scale=self._scale(x))
+        return x, thw_new

