@@ -1,6 +1,365 @@
-// tcgen05 GEMM (bf16) -- placeholder until the TMEM kernel lands.
-#include "common.cuh"
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands fed by TMA),
+// with the fused epilogue of the SViT hot path.  Same contract as gemm_simt.cu (svit_gemm_args):
+//   C[M,N] = residual + sample_scale[row/rps] * ( act(op(A).op(B) + bias) * gelu'(gelu_pre) )
+//
+// Persistent, warp-specialised, one CTA per SM (192 threads):
+//   warp 0    TMA producer: 4-stage ring of {A 128x64, B BNx64} bf16 tiles, 128-byte swizzle
+//   warp 1    MMA issuer (one elected lane): tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM,
+//             two accumulator buffers so the MMAs of tile i+1 overlap the epilogue of tile i
+//   warps 2-5 epilogue: tcgen05.ld -> bias / GELU in registers -> fp32 staging in smem -> coalesced
+//             16-byte row segments: gelu' multiply, DropPath scale, residual add, store (bf16 or fp32)
+// Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) -- the latter is what the
+// dgrad / wgrad GEMMs need -- selected through the UMMA descriptors; no transposed copies are made.
+#include <mutex>
+
+#include "tc_common.cuh"
 #include "../../include/svit_b200.h"
-int svit_gemm_tc_supported(const svit_gemm_args* a) { (void)a; return 0; }
-int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st) { (void)a; (void)st; return SVIT_ENOTSUP; }
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192;
+constexpr int STG_PITCH = 64 * 4 + 16;  // fp32 staging row of 64 columns, padded: conflict-free 16-byte accesses
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = 4 * 32 * STG_PITCH;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + alignment slack
+};
+
+struct EpiArgs {
+  const float* bias;
+  const bf16* residual;
+  int64_t ldr;
+  const float* sample_scale;
+  int64_t rps;
+  const bf16* gelu_pre;
+  int64_t ldg;
+  bf16* pre_out;
+  int64_t ldp;
+  int act;
+  int64_t rows_in, rows_out, row_off;
+  void* C;
+  int64_t ldc;
+  int out_f32;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// coalesced write-out of one staged chunk (32 rows x `width` fp32 columns) owned by this warp
+template <bool PLAIN>
+__device__ __forceinline__ void store_chunk(const EpiArgs& e, const unsigned char* stg, int lane, int64_t m_base,
+                                            int64_t n_base, int width, int64_t M, int64_t N, bf16* plain_dst,
+                                            int64_t plain_ld) {
+  const int upr = width >> 3;  // 8-column units per row
+  const int units = 32 * upr;
+  for (int u = lane; u < units; u += 32) {
+    const int r = u / upr, c8 = (u % upr) * 8;
+    const int64_t m = m_base + r, n = n_base + c8;
+    if (m >= M || n >= N) continue;
+    const float4 lo = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c8 * 4);
+    const float4 hi = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c8 * 4 + 16);
+    float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    if (PLAIN) {
+      uint4 o = {pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])};
+      *reinterpret_cast<uint4*>(plain_dst + m * plain_ld + n) = o;
+      continue;
+    }
+    if (e.gelu_pre) {
+      const uint4 g = *reinterpret_cast<const uint4*>(e.gelu_pre + m * e.ldg + n);
+      const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(gp[i]);
+        v[2 * i] *= gelu_erf_grad(f.x);
+        v[2 * i + 1] *= gelu_erf_grad(f.y);
+      }
+    }
+    if (e.sample_scale) {
+      const float sc = e.sample_scale[m / e.rps];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= sc;
+    }
+    const int64_t orow = e.rows_in > 0 ? (m / e.rows_in) * e.rows_out + e.row_off + (m % e.rows_in) : m;
+    if (e.residual) {
+      const uint4 g = *reinterpret_cast<const uint4*>(e.residual + orow * e.ldr + n);
+      const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(gp[i]);
+        v[2 * i] += f.x;
+        v[2 * i + 1] += f.y;
+      }
+    }
+    if (e.out_f32) {
+      float* dst = reinterpret_cast<float*>(e.C) + orow * e.ldc + n;
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 o = {pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])};
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.C) + orow * e.ldc + n) = o;
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int64_t M,
+               int64_t N, int64_t K, EpiArgs e) {
+  using L = SmemLayout<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stg_base = smem + STAGES * L::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int64_t num_tiles = m_tiles * n_tiles;
+  const int num_kb = (int)((K + BK - 1) / BK);
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      tc::mbar_init(&full_bar[i], 1);
+      tc::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&tmem_full[i], 1);
+      tc::mbar_init(&tmem_empty[i], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (int)((t / n_tiles) * BM), n0 = (int)((t % n_tiles) * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * L::STAGE_BYTES;
+          unsigned char* sb = sa + L::A_BYTES;
+          tc::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if (!A_MN) {
+            tc::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tc::tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * BK);
+          }
+          if (!B_MN) {
+            tc::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tc::tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&tmem_empty[as], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? tc::smem_desc_sw128(sa + k * 2048, 8192, 1024) : tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? tc::smem_desc_sw128(sb + k * 2048, 8192, 1024) : tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+            tc::umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+          if (kb == num_kb - 1) tc::umma_commit(&tmem_full[as]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    unsigned char* stg = stg_base + q * 32 * STG_PITCH;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      tc::mbar_wait(&tmem_full[as], acc_phase);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        const int width = (BN - c0) < 64 ? (BN - c0) : 64;
+        float v[64];
+        tc::tmem_ld32(taddr + c0, v);
+        if (width > 32) tc::tmem_ld32(taddr + c0 + 32, v + 32);
+        tc::tmem_ld_wait();
+        if (c0 + 64 >= BN) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
+        }
+        if (e.bias) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (j < width) {
+              int64_t n = n0 + c0 + j;
+              v[j] += (n < N) ? __ldg(e.bias + n) : 0.f;
+            }
+        }
+        if (e.pre_out) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4)
+            if (j < width) *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          store_chunk<true>(e, stg, lane, m0 + q * 32, n0 + c0, width, M, N, e.pre_out, e.ldp);
+          __syncwarp();
+        }
+        if (e.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (j < width) v[j] = gelu_erf(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 64; j += 4)
+          if (j < width) *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        store_chunk<false>(e, stg, lane, m0 + q * 32, n0 + c0, width, M, N, nullptr, 0);
+        __syncwarp();
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const svit_gemm_args* a, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = svit_make_tmap_2d(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM);
+  else rc = svit_make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK);
+  if (rc) return rc;
+  if (!B_MN) rc = svit_make_tmap_2d(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, BN);
+  else rc = svit_make_tmap_2d(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK);
+  if (rc) return rc;
+  EpiArgs e;
+  e.bias = a->bias;
+  e.residual = (const bf16*)a->residual; e.ldr = a->ldr;
+  e.sample_scale = a->sample_scale; e.rps = a->rows_per_sample;
+  e.gelu_pre = (const bf16*)a->gelu_pre; e.ldg = a->ldg;
+  e.pre_out = (bf16*)a->pre_out; e.ldp = a->ldp;
+  e.act = a->act;
+  e.rows_in = a->rows_in; e.rows_out = a->rows_out; e.row_off = a->row_off;
+  e.C = a->C; e.ldc = a->ldc;
+  e.out_f32 = a->out_dtype == SVIT_F32;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int64_t tiles = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN);
+  const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
+  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ta, tb, a->M, a->N, a->K, e);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+template <bool A_MN, bool B_MN>
+int dispatch_bn(const svit_gemm_args* a, cudaStream_t st) {
+  const int64_t N = a->N;
+  if (!B_MN) {
+    if (N % 192 == 0 || N > 384) return launch<192, A_MN, B_MN>(a, st);
+    if (N % 96 == 0) return launch<96, A_MN, B_MN>(a, st);
+    if (N > 128) return launch<192, A_MN, B_MN>(a, st);
+    return N > 64 ? launch<128, A_MN, B_MN>(a, st) : launch<64, A_MN, B_MN>(a, st);
+  }
+  // MN-major B tiles are built from 64-wide swizzle atoms
+  if (N % 192 == 0 || N > 256) return launch<192, A_MN, B_MN>(a, st);
+  if (N > 64) return launch<128, A_MN, B_MN>(a, st);
+  return launch<64, A_MN, B_MN>(a, st);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+svit_tmap_encode_fn svit_get_tmap_encode() {
+  static svit_tmap_encode_fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<svit_tmap_encode_fn>(p);
+  });
+  return fn;
+}
+
+int svit_gemm_tc_supported(const svit_gemm_args* a) {
+  if (a->dtype != SVIT_BF16) return 0;
+  if (a->out_dtype != SVIT_BF16 && a->out_dtype != SVIT_F32) return 0;
+  if (a->K < 8 || a->N < 8 || a->M < 1) return 0;
+  if (a->N % 8 || a->lda % 8 || a->ldb % 8) return 0;
+  if (a->out_dtype == SVIT_BF16 ? (a->ldc % 8) : (a->ldc % 4)) return 0;
+  if (!aligned16(a->A) || !aligned16(a->B) || !aligned16(a->C)) return 0;
+  if (a->residual && (!aligned16(a->residual) || a->ldr % 8)) return 0;
+  if (a->gelu_pre && (!aligned16(a->gelu_pre) || a->ldg % 8)) return 0;
+  if (a->pre_out && (!aligned16(a->pre_out) || a->ldp % 8)) return 0;
+  if (a->M >= (1ll << 31) || a->N >= (1ll << 31) || a->K >= (1ll << 31)) return 0;
+  // operand extents along the contiguous dim must cover whole 16-byte units for TMA
+  if (a->transA ? (a->M % 8) : (a->K % 8)) return 0;
+  if (a->transB ? (a->K % 8) : (a->N % 8)) return 0;
+  return 1;
+}
+
+int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st) {
+  const bool a_mn = a->transA != 0;  // A stored [K, M]
+  const bool b_mn = a->transB == 0;  // B stored [K, N]
+  if (!a_mn && !b_mn) return dispatch_bn<false, false>(a, st);
+  if (!a_mn && b_mn) return dispatch_bn<false, true>(a, st);
+  if (a_mn && b_mn) return dispatch_bn<true, true>(a, st);
+  return dispatch_bn<true, false>(a, st);
+}
+
 extern "C" int svit_destroy(void) { return 0; }

@@ -63,22 +63,70 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 _wcache = {}
 
 
+def _cache_get(w, tag):
+    ent = _wcache.get((id(w), tag))
+    if ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == w.data_ptr():
+        return ent[3]
+    return None
+
+
+def _cache_put(w, tag, value):
+    import weakref
+
+    key = (id(w), tag)
+    _wcache[key] = (weakref.ref(w, lambda _r, k=key: _wcache.pop(k, None)), w._version, w.data_ptr(), value)
+    return value
+
+
 def cast_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """Compute-dtype copy of a GEMM weight, cached until the parameter is modified (param._version)."""
-    wd = w.detach()
-    if wd.dtype == dtype and wd.is_contiguous():
-        return wd
-    key = (wd.data_ptr(), dtype, tuple(wd.shape))
-    ent = _wcache.get(key)
-    if ent is not None and ent[0] == w._version:
-        return ent[1]
-    c = wd.to(dtype).contiguous()
-    _wcache[key] = (w._version, c)
+    """Compute-dtype copy of a GEMM weight, cached per parameter object until it is modified
+    (checked through param._version and data_ptr)."""
+    if w.dtype == dtype and w.is_contiguous():
+        return w.detach()
+    c = _cache_get(w, dtype)
+    if c is None:
+        c = _cache_put(w, dtype, w.detach().to(dtype).contiguous())
     return c
 
 
-def _call(name, *args):
+_FAMILY = {"svit_gemm": "gemm", "svit_attn_fwd": "attention", "svit_attn_bwd": "attention_bwd",
+           "svit_pool_ln_fwd": "pool_ln", "svit_pool_ln_bwd": "pool_ln_bwd", "svit_layernorm_fwd": "layernorm",
+           "svit_layernorm_bwd": "layernorm_bwd", "svit_skip_maxpool_fwd": "skip_pool", "svit_im2col3d": "im2col"}
+_prof = None
+
+
+def profile_start():
+    """Record a CUDA-event pair around every C-ABI call (bench.py's per-kernel breakdown; adds launch gaps,
+    so it is only used in a separate instrumented pass, never in the timed region)."""
+    global _prof
+    _prof = []
+
+
+def profile_stop(steps: int = 1):
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    fam, detail = {}, {}
+    for name, tag, e0, e1 in rec:
+        ms = e0.elapsed_time(e1)
+        f = fam.setdefault(_FAMILY.get(name, "misc"), {"ms_per_step": 0.0, "calls_per_step": 0.0})
+        f["ms_per_step"] += ms / steps
+        f["calls_per_step"] += 1.0 / steps
+        d = detail.setdefault(f"{name}{tag or ''}", {"ms_per_step": 0.0, "calls_per_step": 0.0})
+        d["ms_per_step"] += ms / steps
+        d["calls_per_step"] += 1.0 / steps
+    return {"families": fam, "detail": detail}
+
+
+def _call(name, *args, tag=None):
     _state["launches"] += 1
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(_lib.lib(), name)(*args), name)
+        e1.record()
+        _prof.append((name, tag, e0, e1))
+        return
     check(getattr(_lib.lib(), name)(*args), name)
 
 
@@ -98,7 +146,7 @@ def gemm(A, B, out, M, N, K, lda, ldb, ldc, transA=0, transB=1, bias=None, resid
     a.rows_in, a.rows_out, a.row_off = remap
     a.dtype, a.out_dtype = _dt(A), _dt(out)
     a.impl = _state["gemm_impl"] if impl is None else impl
-    _call("svit_gemm", C.byref(a), _stream())
+    _call("svit_gemm", C.byref(a), _stream(), tag=f"[{M}x{N}x{K}]" if _prof is not None else None)
     return out
 
 
@@ -402,7 +450,8 @@ class _Attention(torch.autograd.Function):
         out = torch.empty(B, Nq, h * d, dtype=q.dtype, device=q.device)
         lse = torch.empty(B, h, Nq, dtype=torch.float32, device=q.device) if need else None
         a = _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale)
-        _call("svit_attn_fwd", C.byref(a), _stream())
+        _call("svit_attn_fwd", C.byref(a), _stream(),
+              tag=f"[B{B} h{h} Nq{Nq} Nk{k.shape[2]}]" if _prof is not None else None)
         if need:
             ctx.save_for_backward(q, k, v, Rh, Rw, Rt, out, lse)
         ctx.geom = (q_thw, k_thw, O, scale)
@@ -493,14 +542,12 @@ class _PatchEmbedTokens(torch.autograd.Function):
 
 
 def _padded_weight(w, K, Kpad, dtype):
-    wd = w.detach()
-    key = (wd.data_ptr(), dtype, "pad", Kpad)
-    ent = _wcache.get(key)
-    if ent is not None and ent[0] == w._version:
-        return ent[1]
-    w2 = torch.zeros(wd.shape[0], Kpad, dtype=dtype, device=wd.device)
-    w2[:, :K] = wd.reshape(wd.shape[0], K).to(dtype)
-    _wcache[key] = (w._version, w2)
+    tag = ("pad", Kpad, dtype)
+    w2 = _cache_get(w, tag)
+    if w2 is None:
+        w2 = torch.zeros(w.shape[0], Kpad, dtype=dtype, device=w.device)
+        w2[:, :K] = w.detach().reshape(w.shape[0], K).to(dtype)
+        _cache_put(w, tag, w2)
     return w2
 
 

@@ -43,7 +43,7 @@ def test_layernorm_fwd_bwd(dtype):
         g = 1 + 0.3 * synth_input(f"lng{C}", (C,), 1)
         b = 0.3 * synth_input(f"lnb{C}", (C,), 1)
         gy = synth_input(f"lngy{C}", (rows, C), 1)
-        xr = x.to(dtype).float().requires_grad_(True)
+        xr = x.to(dtype).float().clone().requires_grad_(True)
         gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
         yr = torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-6)
         yr.backward(gy.to(dtype).float())
