@@ -272,7 +272,10 @@ def test_svit_tiny_fp32_training_gradients(golden):
             bad.append((k, got, n.item()))
     assert not bad, bad[:10]
     for k, w in g["grads"].items():
-        assert max_rel_err(cpu(named[k].grad), w) < 2e-3, k
+        if w.abs().max() < 1e-6:  # mathematically zero (norm_k.bias: a constant key shift cancels in softmax)
+            assert cpu(named[k].grad).abs().max() < 1e-5, k
+        else:
+            assert max_rel_err(cpu(named[k].grad), w) < 2e-3, k
     ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
 
 
