@@ -121,6 +121,18 @@ typedef struct svit_attn_args {
   float* ws_e;      /* scratch [B,h,Nq,kh+kw+kt] fp32: bias terms E */
   float* ws_de;     /* scratch [B,h,Nq,kh+kw+kt] fp32: dE */
   float* ws_delta;  /* scratch [B,h,Nq] fp32 */
+  /* tcgen05 path only (may be NULL for impl 1): the un-gathered, interpolated tables and the integer
+   * index tables of attention.py:100-119,156-163 so that q.R is one tensor-core product per query tile:
+   * rel_tab [ntab_h + ntab_w + ntab_t, 96] = rows of get_rel_pos(rel_pos_h | rel_pos_w | rel_pos_t);
+   * idx_h [qh,kh], idx_w [qw,kw], idx_t [qt,kt] int32 = dist.long(); key_cols [Nk rounded up to 64 (+64)] int32:
+   * per key the packed E columns (i' | (kh+j')<<8 | (kh+kw+t')<<16), 0x00ffffff-style "zero slot" codes for
+   * cls/object keys and bit 31 set for padding keys. */
+  const void* rel_tab;
+  const int32_t* idx_h;
+  const int32_t* idx_w;
+  const int32_t* idx_t;
+  const int32_t* key_cols;
+  int32_t ntab_h, ntab_w, ntab_t;
 } svit_attn_args;
 int svit_attn_fwd(const svit_attn_args* args, void* stream);
 int svit_attn_bwd(const svit_attn_args* args, void* stream);

@@ -40,6 +40,8 @@ class AttnArgs(C.Structure):
         ("O", i32), ("scale", f32), ("dtype", i32), ("impl", i32),
         ("dout", vp), ("dq", vp), ("dk", vp), ("dv", vp), ("d_rel_h", vp), ("d_rel_w", vp), ("d_rel_t", vp),
         ("ws_e", vp), ("ws_de", vp), ("ws_delta", vp),
+        ("rel_tab", vp), ("idx_h", vp), ("idx_w", vp), ("idx_t", vp), ("key_cols", vp),
+        ("ntab_h", i32), ("ntab_w", i32), ("ntab_t", i32),
     ]
 
 

@@ -47,15 +47,56 @@ def _index_on(device, q_n, k_n):
     return _idx_cache[key]
 
 
-def gathered_rel_pos(rel_pos: torch.Tensor, q_n: int, k_n: int) -> torch.Tensor:
-    """R[a, b, :] = get_rel_pos(rel_pos, 2*max(q,k)-1)[dist[a, b]]  (attention.py:68-81, 116-119).
-    Small torch glue (tables are <= 111 x 96) that keeps autograd to the parameter."""
+def interpolated_rel_pos(rel_pos: torch.Tensor, q_n: int, k_n: int) -> torch.Tensor:
+    """get_rel_pos(rel_pos, 2*max(q,k)-1)  (attention.py:68-81): linear interpolation when the table length
+    differs from what the run-time grid needs (frame mode, 312^2 clips)."""
     d = int(2 * max(q_n, k_n) - 1)
     tab = rel_pos
     if tab.shape[0] != d:
         tab = torch.nn.functional.interpolate(tab.reshape(1, tab.shape[0], -1).permute(0, 2, 1), size=d, mode="linear")
         tab = tab.reshape(-1, d).permute(1, 0)
-    return tab[_index_on(rel_pos.device, q_n, k_n)]
+    return tab
+
+
+def gathered_rel_pos(rel_pos: torch.Tensor, q_n: int, k_n: int) -> torch.Tensor:
+    """R[a, b, :] = get_rel_pos(rel_pos, 2*max(q,k)-1)[dist[a, b]]  (attention.py:116-119).
+    Small torch glue (tables are <= 111 x 96) that keeps autograd to the parameter."""
+    return interpolated_rel_pos(rel_pos, q_n, k_n)[_index_on(rel_pos.device, q_n, k_n)]
+
+
+_keycol_cache = {}
+
+
+def key_column_codes(k_shape, O, device) -> torch.Tensor:
+    """int32 [Nk rounded up to a multiple of 64, + 64]: for key n the packed columns of the per-row bias vector
+    E = [E_h (kh) | E_w (kw) | E_t (kt) | 0] it adds: i' | (kh + j') << 8 | (kh + kw + t') << 16.  cls / object keys
+    point at the zero slot; padding keys additionally carry bit 31 (masked)."""
+    kt, kh, kw = k_shape
+    key = (kt, kh, kw, O, str(device))
+    if key not in _keycol_cache:
+        import numpy as np
+
+        ne = kh + kw + kt
+        Lk = kt * kh * kw
+        Nk = 1 + Lk + O
+        n_pad = (Nk + 63) // 64 * 64 + 64
+        zero = ne | (ne << 8) | (ne << 16)
+        codes = np.full(n_pad, zero, dtype=np.uint32)
+        pidx = np.arange(Lk)
+        codes[1:1 + Lk] = (pidx // kw % kh) | ((kh + pidx % kw) << 8) | ((kh + kw + pidx // (kw * kh)) << 16)
+        codes[Nk:] |= np.uint32(0x80000000)
+        _keycol_cache[key] = torch.from_numpy(codes.view(np.int32).copy()).to(device)
+    return _keycol_cache[key]
+
+
+_idx32_cache = {}
+
+
+def _index32_on(device, q_n, k_n):
+    key = (str(device), q_n, k_n)
+    if key not in _idx32_cache:
+        _idx32_cache[key] = rel_pos_index_table(q_n, k_n).to(torch.int32).contiguous().to(device)
+    return _idx32_cache[key]
 
 
 def _stride_hw(stride: Sequence[int]) -> int:
@@ -169,7 +210,16 @@ class MultiScaleAttention(nn.Module):
         Rh = gathered_rel_pos(self.rel_pos_h, q_shape[1], k_shape[1])
         Rw = gathered_rel_pos(self.rel_pos_w, q_shape[2], k_shape[2])
         Rt = gathered_rel_pos(self.rel_pos_t, q_shape[0], k_shape[0])
-        o = ops.attention(q, k, v, Rh, Rw, Rt, q_shape, k_shape, O, self.scale)
+        tc_tables = None
+        if q.dtype == torch.bfloat16:
+            # tensor-core path: un-gathered tables + integer index tables (q.R becomes one MMA per query tile)
+            tabs = [interpolated_rel_pos(t.detach(), a, b) for t, a, b in
+                    ((self.rel_pos_h, q_shape[1], k_shape[1]), (self.rel_pos_w, q_shape[2], k_shape[2]),
+                     (self.rel_pos_t, q_shape[0], k_shape[0]))]
+            tc_tables = (torch.cat(tabs).to(torch.bfloat16).contiguous(), [t.shape[0] for t in tabs],
+                         _index32_on(x.device, q_shape[1], k_shape[1]), _index32_on(x.device, q_shape[2], k_shape[2]),
+                         _index32_on(x.device, q_shape[0], k_shape[0]), key_column_codes(k_shape, O, x.device))
+        o = ops.attention(q, k, v, Rh, Rw, Rt, q_shape, k_shape, O, self.scale, tc_tables)
         y = ops.linear(o, self.proj.weight, self.proj.bias, residual=residual, sample_scale=sample_scale)
         return y, q_shape
 

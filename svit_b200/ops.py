@@ -440,7 +440,7 @@ def _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale):
 
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale):
+    def forward(ctx, q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables):
         _chk(q, "attention")
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         Rh, Rw, Rt = (r.to(q.dtype).contiguous() for r in (Rh, Rw, Rt))
@@ -450,6 +450,11 @@ class _Attention(torch.autograd.Function):
         out = torch.empty(B, Nq, h * d, dtype=q.dtype, device=q.device)
         lse = torch.empty(B, h, Nq, dtype=torch.float32, device=q.device) if need else None
         a = _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale)
+        if tc_tables is not None:
+            tab, ntabs, ih, iw, it, kc = tc_tables
+            a.rel_tab, a.idx_h, a.idx_w, a.idx_t, a.key_cols = (tab.data_ptr(), ih.data_ptr(), iw.data_ptr(),
+                                                                it.data_ptr(), kc.data_ptr())
+            a.ntab_h, a.ntab_w, a.ntab_t = ntabs
         _call("svit_attn_fwd", C.byref(a), _stream(),
               tag=f"[B{B} h{h} Nq{Nq} Nk{k.shape[2]}]" if _prof is not None else None)
         if need:
@@ -476,12 +481,14 @@ class _Attention(torch.autograd.Function):
         a.d_rel_h, a.d_rel_w, a.d_rel_t = dRh.data_ptr(), dRw.data_ptr(), dRt.data_ptr()
         a.ws_e, a.ws_de, a.ws_delta = ws_e.data_ptr(), ws_de.data_ptr(), ws_delta.data_ptr()
         _call("svit_attn_bwd", C.byref(a), _stream())
-        return dq, dk, dv, dRh, dRw, dRt, None, None, None, None
+        return dq, dk, dv, dRh, dRw, dRt, None, None, None, None, None
 
 
-def attention(q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale):
-    """softmax(scale q k^T + rel-pos bias) v + residual pooling -> [B, Nq, h*96] (attention.py:429-461)."""
-    return _Attention.apply(q, k, v, Rh, Rw, Rt, tuple(q_thw), tuple(k_thw), O, float(scale))
+def attention(q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables=None):
+    """softmax(scale q k^T + rel-pos bias) v + residual pooling -> [B, Nq, h*96] (attention.py:429-461).
+    Rh/Rw/Rt: gathered tables (differentiable); tc_tables: (cat table bf16, [rows], idx_h, idx_w, idx_t, key codes)
+    for the tcgen05 kernel, or None."""
+    return _Attention.apply(q, k, v, Rh, Rw, Rt, tuple(q_thw), tuple(k_thw), O, float(scale), tc_tables)
 
 
 # --------------------------------------------------------------------------------------------

@@ -76,3 +76,51 @@ def test_gemm_tc_matches_simt_on_model_shapes():
         ops.gemm(A, W, o1, M, N, K, K, K, N, 0, 1, bias=bias, impl=TC)
         ops.gemm(A, W, o2, M, N, K, K, K, N, 0, 1, bias=bias, impl=ops.IMPL_SIMT)
         assert max_rel_err(cpu(o1), cpu(o2)) < 1e-2, (M, N, K)
+
+
+def _attn_inputs(B, h, q_thw, k_thw, O, seed, rel_std=0.2):
+    from svit_b200 import msa
+    gen = torch.Generator().manual_seed(seed)
+    Nq = 1 + q_thw[0] * q_thw[1] * q_thw[2] + O
+    Nk = 1 + k_thw[0] * k_thw[1] * k_thw[2] + O
+    q = torch.randn(B, h, Nq, 96, generator=gen).to(torch.bfloat16).to(DEV)
+    k = torch.randn(B, h, Nk, 96, generator=gen).to(torch.bfloat16).to(DEV)
+    v = torch.randn(B, h, Nk, 96, generator=gen).to(torch.bfloat16).to(DEV)
+    rels = [(rel_std * torch.randn(2 * max(a, b) - 1, 96, generator=gen)).to(DEV)
+            for a, b in ((q_thw[1], k_thw[1]), (q_thw[2], k_thw[2]), (q_thw[0], k_thw[0]))]
+    R = [msa.gathered_rel_pos(r, a, b) for r, (a, b) in
+         zip(rels, ((q_thw[1], k_thw[1]), (q_thw[2], k_thw[2]), (q_thw[0], k_thw[0])))]
+    tabs = [r.to(torch.bfloat16) for r in rels]
+    tc_tables = (torch.cat(tabs).contiguous(), [t.shape[0] for t in tabs],
+                 msa._index32_on(q.device, q_thw[1], k_thw[1]), msa._index32_on(q.device, q_thw[2], k_thw[2]),
+                 msa._index32_on(q.device, q_thw[0], k_thw[0]), msa.key_column_codes(k_thw, O, q.device))
+    return q, k, v, R, tc_tables
+
+
+ATTN_SHAPES = [
+    # B, h, q_thw, k_thw, O      (tiny / ragged, then every ssv2.yaml stage shape at B=1)
+    (2, 2, (2, 8, 8), (2, 2, 2), 8), (1, 1, (2, 4, 4), (2, 4, 4), 8), (1, 3, (3, 7, 7), (3, 4, 4), 12),
+    (1, 1, (1, 9, 9), (1, 3, 3), 4), (2, 1, (2, 9, 9), (2, 5, 5), 8),
+    (1, 1, (8, 56, 56), (8, 7, 7), 64), (1, 2, (8, 28, 28), (8, 14, 14), 64), (1, 2, (8, 28, 28), (8, 7, 7), 64),
+    (1, 4, (8, 14, 14), (8, 14, 14), 64), (2, 4, (8, 14, 14), (8, 7, 7), 64), (1, 8, (8, 7, 7), (8, 14, 14), 64),
+    (2, 8, (8, 7, 7), (8, 7, 7), 64),
+]
+
+
+@pytest.mark.parametrize("shape", ATTN_SHAPES)
+def test_attention_tc_matches_simt(shape):
+    B, h, q_thw, k_thw, O = shape
+    q, k, v, R, tc_tables = _attn_inputs(B, h, q_thw, k_thw, O, seed=31)
+    scale = 96 ** -0.5
+    ops.set_impl(attn=ops.IMPL_SIMT)
+    with torch.no_grad():
+        ref = ops.attention(q.float(), k.float(), v.float(), R[0], R[1], R[2], q_thw, k_thw, O, scale)
+    ops.set_impl(attn=TC)
+    try:
+        with torch.no_grad():
+            got = ops.attention(q, k, v, R[0], R[1], R[2], q_thw, k_thw, O, scale, tc_tables)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_impl(attn=ops.IMPL_AUTO)
+    err = max_rel_err(cpu(got), cpu(ref))
+    assert err < 1.5e-2, (shape, err)
