@@ -233,10 +233,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
       const float m_new = fmaxf(m_ref, mx);
       const bool grow = m_new > m_ref + 8.f;  // lazy rescale: stale reference max is fine while p <= 2^8
-      if (__any_sync(0xffffffffu, grow) && j > 0) {
-        const float alpha = grow ? exp2f(m_ref - m_new) : 1.f;
+      // Observe every O_DONE phase in order (PV_{j-1} has normally finished long before this point): the parity
+      // wait only distinguishes "current" from "previous" phase, so no phase may be skipped.
+      if (j > 0) {
         tc::mbar_wait(&bars[BAR_O_DONE], (j - 1) & 1);
         tc::fence_after_sync();
+      }
+      if (__any_sync(0xffffffffu, grow) && j > 0) {
+        const float alpha = grow ? exp2f(m_ref - m_new) : 1.f;
 #pragma unroll
         for (int c0 = 0; c0 < HD; c0 += 32) {
           float o[32];
