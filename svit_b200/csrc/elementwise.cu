@@ -319,6 +319,12 @@ static inline int grid_for(int64_t total, int threads) {
   return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
+// bf16 fast paths (stream_bf16.cu): return 1 when they handled the call, 0 when the shape is not covered
+int svit_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                            int64_t rows, int C, float eps, cudaStream_t st);
+int svit_im2col_rows(const void* x, void* cols, int B, int Cin, int T, int H, int W, int To, int Ho, int Wo, int kt, int kh,
+                     int kw, int st_, int sh, int sw, int pt, int ph, int pw, int Kpad, int in_dtype, cudaStream_t st);
+
 extern "C" {
 
 int svit_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
@@ -326,6 +332,11 @@ int svit_layernorm_fwd(const void* x, const float* gamma, const float* beta, voi
   if (C % 32 != 0 || C > 32 * LN_MAXV || rows < 0) return SVIT_EINVAL;
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SVIT_BF16) {
+    int rc = svit_layernorm_fwd_bf16(x, gamma, beta, y, mean, rstd, rows, C, eps, st);
+    if (rc == 1) return 0;
+    if (rc >= 1000) return rc - 1000;
+  }
   int grid = (int)(ceil_div64(rows, 8) < (int64_t)svit_num_sms() * 8 ? ceil_div64(rows, 8) : (int64_t)svit_num_sms() * 8);
   if (dtype == SVIT_F32)
     layernorm_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, rows, C, eps);
@@ -428,6 +439,11 @@ int svit_im2col3d(const void* x, void* cols, int B, int Cin, int T, int H, int W
   int64_t total = (int64_t)B * To * Ho * Wo * Kpad;
   if (total == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == SVIT_BF16) {
+    int rc = svit_im2col_rows(x, cols, B, Cin, T, H, W, To, Ho, Wo, kt, kh, kw, st_, sh, sw, pt, ph, pw, Kpad, in_dtype, st);
+    if (rc == 1) return 0;
+    if (rc >= 1000) return rc - 1000;
+  }
   int g = grid_for(total, 256);
 #define IM2COL(TI, TO) im2col3d_kernel<TI, TO><<<g, 256, 0, st>>>((const TI*)x, (TO*)cols, B, Cin, T, H, W, To, Ho, Wo, kt, kh, kw, st_, sh, sw, pt, ph, pw, Kpad)
   if (in_dtype == SVIT_F32 && out_dtype == SVIT_F32) IM2COL(float, float);

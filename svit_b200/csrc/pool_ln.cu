@@ -275,6 +275,10 @@ __global__ void __launch_bounds__(256) pool_ln_bwd_in_kernel(const T* __restrict
   }
 }
 
+int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const float* conv_w,
+                          const float* tap_frac, const float* gamma, const float* beta, void* out, int B, int h, int T,
+                          int H, int W, int O, int s, float eps, cudaStream_t st);  // pool_ln_tiled.cu
+
 static int make_geom(PoolGeom& g, int B, int h, int T, int H, int W, int O, int s, int64_t in_bs, int64_t in_ts,
                      int64_t in_hs) {
   if (B < 0 || h < 1 || T < 1 || H < 1 || W < 1 || O < 1 || s < 1) return SVIT_EINVAL;
@@ -302,6 +306,10 @@ int svit_pool_ln_fwd(const void* in, int64_t in_batch_stride, int64_t in_tok_str
   int64_t tokens = (int64_t)B * h * (1 + (int64_t)T * g.Ho * g.Wo + O);
   if (tokens == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SVIT_BF16 && in_batch_stride % 2 == 0 && in_tok_stride % 2 == 0 && in_head_stride % 2 == 0 &&
+      (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0)
+    return svit_pool_ln_fwd_bf16(in, in_batch_stride, in_tok_stride, in_head_stride, conv_w, tap_frac, gamma, beta, out,
+                                 B, h, T, H, W, O, stride_hw, eps, st);
   if (dtype == SVIT_F32)
     pool_ln_fwd_kernel<float><<<pool_grid(tokens), 256, 0, st>>>((const float*)in, g, conv_w, tap_frac, gamma, beta, (float*)out, eps);
   else if (dtype == SVIT_BF16)

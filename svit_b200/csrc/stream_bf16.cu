@@ -1,0 +1,178 @@
+// bf16 production variants of the HBM-bound streaming kernels (generic dtype versions live in elementwise.cu):
+//   layernorm_bf16_kernel   8-byte (bf16x4) accesses; a group of C/12 lanes owns one token row
+//   im2col_rows_kernel      PatchEmbed lowering (stem_helper.py:309-320): one CTA per (b, t', h') output row stages
+//                           the Cin*kt*kh input rows it needs in shared memory once, then emits 16-byte column
+//                           chunks of the [tokens, Kpad] matrix fully coalesced
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void unpack4(uint2 v, float f[4]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// G lanes per row, NQ bf16x4 quads per lane: C = 4 * G * NQ  (C = 96: G 8; 192: 16; 384: 32; 768: 32 with NQ 6)
+template <int G, int NQ>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, bf16* __restrict__ y,
+                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                             int64_t rows, float eps) {
+  constexpr int C = 4 * G * NQ;
+  const int lg = threadIdx.x % G;
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
+  float gm[NQ][4], bt[NQ][4];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const float4 g4 = *reinterpret_cast<const float4*>(gamma + 4 * (lg + G * q));
+    const float4 b4 = *reinterpret_cast<const float4*>(beta + 4 * (lg + G * q));
+    gm[q][0] = g4.x; gm[q][1] = g4.y; gm[q][2] = g4.z; gm[q][3] = g4.w;
+    bt[q][0] = b4.x; bt[q][1] = b4.y; bt[q][2] = b4.z; bt[q][3] = b4.w;
+  }
+  // all lanes of a warp iterate the same number of times (shuffles need the full mask)
+  const int64_t iters = (rows + ngroups - 1) / ngroups;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t row = group + it * ngroups;
+    const bool ok = row < rows;
+    float v[NQ][4];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      uint2 raw = make_uint2(0u, 0u);
+      if (ok) raw = *reinterpret_cast<const uint2*>(x + row * C + 4 * (lg + G * q));
+      unpack4(raw, v[q]);
+      s += v[q][0] + v[q][1] + v[q][2] + v[q][3];
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
+    float qq = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[q][i] -= mean;
+        qq += v[q][i] * v[q][i];
+      }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    const float rstd = rsqrtf(qq * (1.f / C) + eps);
+    if (ok) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        uint2 o2;
+        o2.x = pack2(v[q][0] * rstd * gm[q][0] + bt[q][0], v[q][1] * rstd * gm[q][1] + bt[q][1]);
+        o2.y = pack2(v[q][2] * rstd * gm[q][2] + bt[q][2], v[q][3] * rstd * gm[q][3] + bt[q][3]);
+        *reinterpret_cast<uint2*>(y + row * C + 4 * (lg + G * q)) = o2;
+      }
+      if (lg == 0 && mean_out) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+      }
+    }
+  }
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const TI* __restrict__ x, bf16* __restrict__ cols, int Cin, int T,
+                                                          int H, int W, int To, int Ho, int Wo, int kt, int kh, int kw,
+                                                          int st, int sh, int sw, int pt, int ph, int pw, int Kpad, int RW) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int R = Cin * kt * kh;
+  bf16* rows = reinterpret_cast<bf16*>(smem_raw);                    // [R][RW], halo of pw zeros on both sides
+  int* koff = reinterpret_cast<int*>(smem_raw + (((size_t)R * RW * 2 + 15) & ~size_t(15)));  // [Kpad]
+  const int ho = blockIdx.x % Ho, to = (blockIdx.x / Ho) % To, b = blockIdx.x / (Ho * To);
+  const int K = R * kw;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) koff[k] = k < K ? (k / kw) * RW + (k % kw) : -1;
+  for (int i = threadIdx.x; i < R * RW; i += blockDim.x) {
+    const int r = i / RW, col = i % RW;
+    const int dh = r % kh, dt = (r / kh) % kt, c = r / (kh * kt);
+    const int t = to * st - pt + dt, hh = ho * sh - ph + dh, ww = col - pw;
+    float v = 0.f;
+    if (t >= 0 && t < T && hh >= 0 && hh < H && ww >= 0 && ww < W)
+      v = to_f(x[((((int64_t)b * Cin + c) * T + t) * H + hh) * W + ww]);
+    rows[i] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int cpr = Kpad >> 3;  // 16-byte chunks per output row
+  bf16* obase = cols + ((((int64_t)b * To + to) * Ho + ho) * Wo) * Kpad;
+  const unsigned short* rs = reinterpret_cast<const unsigned short*>(rows);
+  for (int i = threadIdx.x; i < Wo * cpr; i += blockDim.x) {
+    const int wo = i / cpr, q = i % cpr;
+    const int base = wo * sw;
+    unsigned short e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int off = koff[q * 8 + u];
+      e[u] = off < 0 ? (unsigned short)0 : rs[off + base];
+    }
+    uint4 o;
+    o.x = e[0] | ((uint32_t)e[1] << 16); o.y = e[2] | ((uint32_t)e[3] << 16);
+    o.z = e[4] | ((uint32_t)e[5] << 16); o.w = e[6] | ((uint32_t)e[7] << 16);
+    *reinterpret_cast<uint4*>(obase + (int64_t)wo * Kpad + q * 8) = o;
+  }
+}
+
+}  // namespace
+
+// returns 1 if handled (launched), 0 if the shape is not covered by the fast path, > 1 on CUDA error (offset by 1000)
+int svit_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                            int64_t rows, int C, float eps, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(x) & 7) || (reinterpret_cast<uintptr_t>(y) & 7) ||
+      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15))
+    return 0;
+  const int sms = svit_num_sms();
+#define LN_LAUNCH(G, NQ)                                                                                           \
+  {                                                                                                                \
+    int64_t blocks = (rows * G + 255) / 256;                                                                       \
+    if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;                                                    \
+    layernorm_bf16_kernel<G, NQ><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, \
+                                                                  rows, eps);                                      \
+  }
+  if (C == 96) LN_LAUNCH(8, 3)
+  else if (C == 192) LN_LAUNCH(16, 3)
+  else if (C == 384) LN_LAUNCH(32, 3)
+  else if (C == 768) LN_LAUNCH(32, 6)
+  else return 0;
+#undef LN_LAUNCH
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : 1000 + (int)e;
+}
+
+int svit_im2col_rows(const void* x, void* cols, int B, int Cin, int T, int H, int W, int To, int Ho, int Wo, int kt, int kh,
+                     int kw, int st_, int sh, int sw, int pt, int ph, int pw, int Kpad, int in_dtype, cudaStream_t st) {
+  if (Kpad % 8 || (reinterpret_cast<uintptr_t>(cols) & 15)) return 0;
+  const int R = Cin * kt * kh;
+  const int RW = (W + 2 * pw + 1) & ~1;
+  if ((Wo - 1) * sw + kw > RW) return 0;
+  const size_t smem = (((size_t)R * RW * 2 + 15) & ~size_t(15)) + (size_t)Kpad * 4;
+  if (smem > 200 * 1024) return 0;
+  const unsigned grid = (unsigned)((int64_t)B * To * Ho);
+  cudaError_t e;
+  if (in_dtype == SVIT_BF16) {
+    static size_t conf = 0;
+    if (smem > conf) {
+      if ((e = cudaFuncSetAttribute(im2col_rows_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+        return 1000 + (int)e;
+      conf = smem;
+    }
+    im2col_rows_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)x, (bf16*)cols, Cin, T, H, W, To, Ho, Wo, kt, kh, kw, st_,
+                                                      sh, sw, pt, ph, pw, Kpad, RW);
+  } else {
+    static size_t conf = 0;
+    if (smem > conf) {
+      if ((e = cudaFuncSetAttribute(im2col_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+        return 1000 + (int)e;
+      conf = smem;
+    }
+    im2col_rows_kernel<float><<<grid, 256, smem, st>>>((const float*)x, (bf16*)cols, Cin, T, H, W, To, Ho, Wo, kt, kh, kw,
+                                                       st_, sh, sw, pt, ph, pw, Kpad, RW);
+  }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : 1000 + (int)e;
+}

@@ -1,0 +1,140 @@
+"""Data-parallel plumbing for the SViT hot path: one process per GPU, clips sharded across ranks, no
+communication in the forward pass, one bucketed gradient all-reduce per training step.
+
+Replaces the reference's DistributedDataParallel wrap (slowfast/models/build.py:69-74) for this path.
+The collective itself is NCCL over NVLink 5 / NVSwitch through torch.distributed (34.37 M fp32 gradients =
+137.5 MB per step): buckets are filled in reverse parameter order -- head and late blocks
+first, the order in which backward produces them -- and each bucket's all-reduce is launched
+asynchronously as soon as its last gradient has been accumulated, so the transfers hide under the
+remaining backward work (blocks 1 and 0 are both the heaviest and the last to finish).
+
+On CPU the same class runs over gloo (tests/test_dist_gloo.py, world_size 2).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None):
+    """Reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun). Returns (rank, world, device)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    use_cuda = torch.cuda.is_available() and backend != "gloo"
+    dev = torch.device("cuda", local) if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if use_cuda:
+            dist.init_process_group(backend or "nccl", device_id=dev)
+        else:
+            dist.init_process_group(backend or "gloo")
+    return rank, world, dev
+
+
+def shard_batch(n_items: int, rank: int, world: int) -> range:
+    """Contiguous, even split of the clip batch (the reference requires divisibility: defaults.py:1141-1149)."""
+    if n_items % world != 0:
+        raise ValueError(f"batch of {n_items} clips is not divisible by world size {world}")
+    per = n_items // world
+    return range(rank * per, (rank + 1) * per)
+
+
+class GradAllReducer:
+    """Bucketed, overlapped gradient averaging (sum all-reduce / world size, as DDP does).
+
+    Usage per step:   reducer.prepare(); loss.backward(); reducer.finish()
+    Parameters that received no gradient are reduced as zeros, which mirrors find_unused_parameters=False
+    plus the reference's `+ sum(p) * 0` tricks (video_model_builder.py:359, 514)."""
+
+    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        order = list(reversed(self.params))  # backward completion order ~ reverse registration order
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        cur, size = [], 0
+        for p in order:
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device)
+                     for b in self.buckets]
+        self._where = {}
+        for bi, b in enumerate(self.buckets):
+            off = 0
+            for p in b:
+                self._where[p] = (bi, off)
+                off += p.numel()
+        self._pending = [0] * len(self.buckets)
+        self._works = [None] * len(self.buckets)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.bytes_per_step = sum(f.numel() * 4 for f in self.flat)
+
+    def prepare(self):
+        for i, b in enumerate(self.buckets):
+            self._pending[i] = len(b)
+            self._works[i] = None
+            self.flat[i].zero_()
+
+    def _launch(self, bi: int):
+        if self.world > 1:
+            self._works[bi] = dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _on_grad(self, p: torch.nn.Parameter):
+        bi, off = self._where[p]
+        self.flat[bi][off:off + p.numel()].copy_(p.grad.reshape(-1))
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def finish(self):
+        """Launch the buckets whose parameters got no gradient, wait, average, write back into .grad."""
+        for bi in range(len(self.buckets)):
+            if self._pending[bi] > 0:
+                self._pending[bi] = 0
+                self._launch(bi)
+        for bi, b in enumerate(self.buckets):
+            if self._works[bi] is not None:
+                self._works[bi].wait()
+            if self.world > 1:
+                self.flat[bi].div_(self.world)
+            off = 0
+            for p in b:
+                g = self.flat[bi][off:off + p.numel()].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += p.numel()
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+
+
+def train_step(model, reducer: Optional[GradAllReducer], clip, labels, optimizer=None, max_norm: Optional[float] = 1.0):
+    """One data-parallel training step on this rank's shard: forward, CE loss (losses.py:156-168, video rank),
+    backward with overlapped gradient all-reduce, optional clip (tools/train_net.py:144-147) and optimizer step."""
+    if reducer is not None:
+        reducer.prepare()
+    logits, extra = model([clip])
+    loss = torch.nn.functional.cross_entropy(logits.float(), labels)
+    loss.backward()
+    if reducer is not None:
+        reducer.finish()
+    if max_norm is not None:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
+    if optimizer is not None:
+        optimizer.step()
+        optimizer.zero_grad(set_to_none=False)
+    return loss.detach()
