@@ -34,9 +34,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// reduction inside one half-warp; the mask names only this half so the two halves of a warp may diverge
 __device__ __forceinline__ float half_sum(float v) {
+  const unsigned mask = 0xffffu << (threadIdx.x & 16);
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
 
