@@ -41,6 +41,7 @@ struct Params {
   int h, qh, qw, kh, kw, kt, O;
   int Nq, Nk, Lq, ne, epitch;
   int ntab, off_w, off_t, n_pass, n_tiles;
+  int n_patch_tiles, kthkh, Lk;  // fast path: key tiles aligned to rows of the key grid
   float c1;  // scale * log2(e)
   const int32_t* idx_h;
   const int32_t* idx_w;
@@ -61,6 +62,18 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// First key row of tile j.  Generic path (KW == 0): 64 consecutive keys.  Fast path (KW == kw known at compile
+// time): patch tile j = [one extra leading key | RPT rows of the key grid]; the leading key is cls for j == 0 and
+// masked otherwise; the object keys follow in tiles of 64.  Column c of a patch tile is then (row (c-1)/KW,
+// col (c-1)%KW) with COMPILE-TIME row/col, so the bias costs one FADD per score instead of index decoding.
+template <int KW>
+__device__ __forceinline__ int key_start(const Params& p, int j) {
+  if (KW == 0) return j * BN;
+  constexpr int RPT = KW > 0 ? 63 / (KW > 0 ? KW : 1) : 1;
+  return j < p.n_patch_tiles ? j * RPT * KW : 1 + p.Lk + (j - p.n_patch_tiles) * BN;
+}
+
+template <int KW>
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_t, Params p) {
@@ -103,7 +116,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc::mbar_wait(&bars[BAR_E_EMPTY], (p.n_pass - 1) & 1);  // tables + staging alias the K/V buffers
       for (int j = 0; j < p.n_tiles; ++j) {
         const int ks = j & 1;
-        const int n0 = j * BN;
+        const int n0 = key_start<KW>(p, j);
         tc::mbar_wait(&bars[BAR_K_EMPTY0 + ks], ((j >> 1) & 1) ^ 1);
         unsigned char* kd = smem + OFF_K + ks * 16384;
         tc::mbar_arrive_expect_tx(&bars[BAR_K_FULL0 + ks], 16384);
@@ -211,10 +224,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       if (lane == 0) tc::mbar_arrive(&bars[BAR_E_EMPTY]);
     }
     // ---- phase S: online softmax over the key tiles
+    float ew[KW > 0 ? KW : 1];
+    if (KW > 0) {
+#pragma unroll
+      for (int k = 0; k < (KW > 0 ? KW : 1); ++k) ew[k] = Er[p.kh + k];
+    }
+    (void)ew;
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < p.n_tiles; ++j) {
       const int sb = j & 1;
-      const int n0 = j * BN;
+      const int n0 = key_start<KW>(p, j);
+      (void)n0;
       tc::mbar_wait(&bars[BAR_S_FULL0 + sb], (j >> 1) & 1);
       tc::fence_after_sync();
       float y[BN];
@@ -222,14 +242,47 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc::tmem_ld32(lane_addr + COL_S0 + sb * BN + 32, y + 32);
       tc::tmem_ld_wait();
       float mx = -INFINITY;
+      if (KW == 0) {
 #pragma unroll
-      for (int c = 0; c < BN; ++c) {
-        const int code = __ldg(p.key_cols + n0 + c);
-        const float bias = Er[code & 0xff] + Er[(code >> 8) & 0xff] + Er[(code >> 16) & 0xff];
-        float v = fmaf(y[c], p.c1, bias);
-        v = code < 0 ? -INFINITY : v;
-        y[c] = v;
-        mx = fmaxf(mx, v);
+        for (int c = 0; c < BN; ++c) {
+          const int code = __ldg(p.key_cols + n0 + c);
+          const float bias = Er[code & 0xff] + Er[(code >> 8) & 0xff] + Er[(code >> 16) & 0xff];
+          float v = fmaf(y[c], p.c1, bias);
+          v = code < 0 ? -INFINITY : v;
+          y[c] = v;
+          mx = fmaxf(mx, v);
+        }
+      } else {
+        constexpr int KWc = KW > 0 ? KW : 1;
+        constexpr int RPT = 63 / KWc;
+        if (j < p.n_patch_tiles) {
+          int gr = j * RPT;
+          int tq = gr / p.kh, iq = gr - tq * p.kh;
+          float brow[RPT];
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) {
+            brow[r] = (gr + r < p.kthkh) ? Er[p.kh + KWc + tq] + Er[iq] : -INFINITY;
+            if (++iq == p.kh) { iq = 0; ++tq; }
+          }
+          y[0] = j == 0 ? y[0] * p.c1 : -INFINITY;  // cls key (no bias) / duplicated key of the previous tile
+          mx = y[0];
+#pragma unroll
+          for (int c = 1; c < BN; ++c) {
+            if (c <= RPT * KWc) {
+              y[c] = fmaf(y[c], p.c1, brow[(c - 1) / KWc] + ew[(c - 1) % KWc]);
+              mx = fmaxf(mx, y[c]);
+            } else {
+              y[c] = -INFINITY;
+            }
+          }
+        } else {
+          const int nvalid = p.O - (j - p.n_patch_tiles) * BN;
+#pragma unroll
+          for (int c = 0; c < BN; ++c) {
+            y[c] = c < nvalid ? y[c] * p.c1 : -INFINITY;
+            mx = fmaxf(mx, y[c]);
+          }
+        }
       }
       const float m_new = fmaxf(m_ref, mx);
       const bool grow = m_new > m_ref + 8.f;  // lazy rescale: stale reference max is fine while p <= 2^8
@@ -339,6 +392,15 @@ int svit_attn_fwd_tc(const svit_attn_args* a, cudaStream_t st) {
   p.off_t = a->ntab_h + a->ntab_w;
   p.n_pass = (p.ntab + TP - 1) / TP;
   p.n_tiles = (p.Nk + BN - 1) / BN;
+  p.Lk = a->kt * a->kh * a->kw;
+  p.kthkh = a->kt * a->kh;
+  p.n_patch_tiles = 0;
+  const int KWs = (a->kw == 7 || a->kw == 14 || a->kw == 10 || a->kw == 20) ? a->kw : 0;
+  if (KWs) {
+    const int rpt = 63 / KWs;
+    p.n_patch_tiles = (p.kthkh + rpt - 1) / rpt;
+    p.n_tiles = p.n_patch_tiles + (a->O + BN - 1) / BN;
+  }
   p.c1 = a->scale * 1.4426950408889634f;
   p.idx_h = a->idx_h; p.idx_w = a->idx_w; p.idx_t = a->idx_t; p.key_cols = a->key_cols;
   p.q = (const bf16*)a->q; p.out = (bf16*)a->out; p.lse = a->lse;
@@ -351,13 +413,24 @@ int svit_attn_fwd_tc(const svit_attn_args* a, cudaStream_t st) {
   if ((rc = svit_make_tmap_2d(&tt, a->rel_tab, p.ntab, HD, HD, TP))) return rc;
   const int smem = OFF_E + BM * p.epitch * 4 + NUM_BARS * 8 + 16 + 1024;
   if (smem > 200 * 1024) return SVIT_ENOTSUP;
-  static bool configured = false;
-  if (!configured) {
-    SVIT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
   dim3 grid((unsigned)((p.Nq + BM - 1) / BM), (unsigned)BH);
-  attn_fwd_tc_kernel<<<grid, NTHREADS, smem, st>>>(tq, tk, tv, tt, p);
+#define ATTN_LAUNCH(KWV)                                                                                              \
+  {                                                                                                                   \
+    static bool configured = false;                                                                                   \
+    if (!configured) {                                                                                                \
+      SVIT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<KWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      configured = true;                                                                                              \
+    }                                                                                                                 \
+    attn_fwd_tc_kernel<KWV><<<grid, NTHREADS, smem, st>>>(tq, tk, tv, tt, p);                                         \
+  }
+  switch (KWs) {
+    case 7: ATTN_LAUNCH(7) break;
+    case 14: ATTN_LAUNCH(14) break;
+    case 10: ATTN_LAUNCH(10) break;
+    case 20: ATTN_LAUNCH(20) break;
+    default: ATTN_LAUNCH(0) break;
+  }
+#undef ATTN_LAUNCH
   SVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -324,6 +324,8 @@ int svit_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta
                             int64_t rows, int C, float eps, cudaStream_t st);
 int svit_im2col_rows(const void* x, void* cols, int B, int Cin, int T, int H, int W, int To, int Ho, int Wo, int kt, int kh,
                      int kw, int st_, int sh, int sw, int pt, int ph, int pw, int Kpad, int in_dtype, cudaStream_t st);
+int svit_skip_maxpool_fwd_bf16(const void* x, void* y, int B, int C, int T, int H, int W, int Ho, int Wo, int O, int s,
+                               cudaStream_t st);
 
 extern "C" {
 
@@ -374,6 +376,11 @@ int svit_skip_maxpool_fwd(const void* x, void* y, int B, int C, int T, int H, in
   int64_t total = (int64_t)B * (1 + (int64_t)T * Ho * Wo + O) * C;
   if (total == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SVIT_BF16) {
+    int rc = svit_skip_maxpool_fwd_bf16(x, y, B, C, T, H, W, Ho, Wo, O, stride_hw, st);
+    if (rc == 1) return 0;
+    if (rc >= 1000) return rc - 1000;
+  }
   if (dtype == SVIT_F32)
     skip_maxpool_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, B, C, T, H, W, Ho, Wo, O, stride_hw);
   else if (dtype == SVIT_BF16)

@@ -217,28 +217,34 @@ pool_ln_direct_kernel(const bf16* __restrict__ in, Geom g, const float* __restri
     } else {
       const int64_t pp = tok - 1;
       const int wo = (int)(pp % g.Wo), ho = (int)((pp / g.Wo) % g.Ho), to = (int)(pp / ((int64_t)g.Wo * g.Ho));
+      // all 27 x 3 words of the window are requested before the first FMA (zero for padding taps), so the
+      // DRAM / L2 latency is paid once per token, not once per tap
+      uint32_t xw[TAPS][3];
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
         const int t = to - 1 + kt;
-        if (t < 0 || t >= g.T) continue;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
           const int hh = ho * g.s - 1 + kh;
-          if (hh < 0 || hh >= g.H) continue;
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const int ww = wo * g.s - 1 + kw;
-            if (ww < 0 || ww >= g.W) continue;
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(zin + (1 + ((int64_t)t * g.H + hh) * g.W + ww) * g.in_ts);
-            const float* wr = sw + ((kt * 3 + kh) * 3 + kw) * PD;
+            const bool ok = t >= 0 && t < g.T && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(
+                zin + (ok ? (1 + ((int64_t)t * g.H + hh) * g.W + ww) * g.in_ts : 0));
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const uint32_t wd = __ldg(q + l16 + 16 * j);
-              const float2 f = *reinterpret_cast<const float2*>(wr + 2 * (l16 + 16 * j));
-              v[2 * j] = fmaf(lo_f(wd), f.x, v[2 * j]);
-              v[2 * j + 1] = fmaf(hi_f(wd), f.y, v[2 * j + 1]);
-            }
+            for (int j = 0; j < 3; ++j) xw[(kt * 3 + kh) * 3 + kw][j] = ok ? __ldg(q + l16 + 16 * j) : 0u;
           }
+        }
+      }
+#pragma unroll
+      for (int tap = 0; tap < TAPS; ++tap) {
+        const float* wr = sw + tap * PD;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float2 f = *reinterpret_cast<const float2*>(wr + 2 * (l16 + 16 * j));
+          v[2 * j] = fmaf(lo_f(xw[tap][j]), f.x, v[2 * j]);
+          v[2 * j + 1] = fmaf(hi_f(xw[tap][j]), f.y, v[2 * j + 1]);
         }
       }
     }

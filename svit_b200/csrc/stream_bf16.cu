@@ -118,7 +118,70 @@ __global__ void __launch_bounds__(256) im2col_rows_kernel(const TI* __restrict__
   }
 }
 
+// skip-path MaxPool3d k(1,3,3) s(1,s,s) p(0,1,1) on [B, N, C] (attention.py:562-564): one thread per 8 channels
+__global__ void __launch_bounds__(256) skip_maxpool_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int C,
+                                                                int T_, int H, int W, int Ho, int Wo, int O, int s) {
+  const int C8 = C >> 3;
+  const int64_t Lin = (int64_t)T_ * H * W, Lout = (int64_t)T_ * Ho * Wo;
+  const int64_t Nin = 1 + Lin + O, Nout = 1 + Lout + O;
+  const int64_t total = (int64_t)B * Nout * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const int64_t r = i / C8;
+    const int64_t tok = r % Nout;
+    const int b = (int)(r / Nout);
+    const bf16* xb = x + (int64_t)b * Nin * C + c8 * 8;
+    uint4 o;
+    if (tok == 0) {
+      o = *reinterpret_cast<const uint4*>(xb);
+    } else if (tok > Lout) {
+      o = *reinterpret_cast<const uint4*>(xb + (tok - Lout + Lin) * C);
+    } else {
+      const int64_t p = tok - 1;
+      const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho), t = (int)(p / ((int64_t)Wo * Ho));
+      uint4 taps[9];
+      bool ok[9];
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw) {
+          const int hh = ho * s - 1 + dh, ww = wo * s - 1 + dw;
+          ok[dh * 3 + dw] = hh >= 0 && hh < H && ww >= 0 && ww < W;
+          taps[dh * 3 + dw] = ok[dh * 3 + dw]
+              ? *reinterpret_cast<const uint4*>(xb + (1 + ((int64_t)t * H + hh) * W + ww) * C) : make_uint4(0, 0, 0, 0);
+        }
+      float m[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) m[u] = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (ok[k]) {
+          const uint32_t wv[4] = {taps[k].x, taps[k].y, taps[k].z, taps[k].w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float a = __uint_as_float(wv[u] << 16), c = __uint_as_float(wv[u] & 0xffff0000u);
+            if (a > m[2 * u] || a != a) m[2 * u] = a;
+            if (c > m[2 * u + 1] || c != c) m[2 * u + 1] = c;
+          }
+        }
+      o.x = pack2(m[0], m[1]); o.y = pack2(m[2], m[3]); o.z = pack2(m[4], m[5]); o.w = pack2(m[6], m[7]);
+    }
+    *reinterpret_cast<uint4*>(y + ((int64_t)b * Nout + tok) * C + c8 * 8) = o;
+  }
+}
+
 }  // namespace
+
+int svit_skip_maxpool_fwd_bf16(const void* x, void* y, int B, int C, int T, int H, int W, int Ho, int Wo, int O, int s,
+                               cudaStream_t st) {
+  if (C % 8 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return 0;
+  const int64_t total = (int64_t)B * (1 + (int64_t)T * Ho * Wo + O) * (C / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)svit_num_sms() * 32) blocks = (int64_t)svit_num_sms() * 32;
+  skip_maxpool_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>((const bf16*)x, (bf16*)y, B, C, T, H, W, Ho, Wo, O, s);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : 1000 + (int)e;
+}
 
 // returns 1 if handled (launched), 0 if the shape is not covered by the fast path, > 1 on CUDA error (offset by 1000)
 int svit_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,

@@ -356,7 +356,8 @@ class _QKVPool(torch.autograd.Function):
             frac = tap_fractions(s, qkv.device)
             _call("svit_pool_ln_fwd", qkv.data_ptr() + which * h * HEAD_DIM * qkv.element_size(), N * D3, D3, HEAD_DIM,
                   w32.data_ptr(), frac.data_ptr(), g32.data_ptr(), _f32(b).data_ptr(), out.data_ptr(),
-                  B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream())
+                  B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream(),
+                  tag=f"[{'qkv'[which]} B{B} h{h} {T}x{H}x{W} s{s}]" if _prof is not None else None)
             outs.append(out)
             saved += [w32, g32]
         ctx.save_for_backward(qkv, *saved)

@@ -104,6 +104,9 @@ ATTN_SHAPES = [
     (1, 1, (8, 56, 56), (8, 7, 7), 64), (1, 2, (8, 28, 28), (8, 14, 14), 64), (1, 2, (8, 28, 28), (8, 7, 7), 64),
     (1, 4, (8, 14, 14), (8, 14, 14), 64), (2, 4, (8, 14, 14), (8, 7, 7), 64), (1, 8, (8, 7, 7), (8, 14, 14), 64),
     (2, 8, (8, 7, 7), (8, 7, 7), 64),
+    # 312^2-style key grids (kw 10 / 20 fast paths), 32-frame object tail (two object-key tiles), frame mode (kt 1)
+    (1, 2, (4, 20, 20), (4, 10, 10), 128), (1, 1, (3, 10, 10), (3, 20, 20), 12), (2, 2, (1, 14, 14), (1, 7, 7), 4),
+    (1, 1, (16, 14, 14), (16, 14, 14), 128),
 ]
 
 
