@@ -6,22 +6,19 @@
 // {2w, 2w+1 : w = l16, l16+16, l16+32} as three bf16x2 words, so a token slice (192 B) is three conflict-free
 // 64-byte half-warp accesses and LayerNorm(96) is a 4-step xor-shuffle inside the half-warp.
 //
-//   pool_ln_s1_tiled_kernel   stride (1,1,1): CTA = 8 x 14 output tile marched over T with a 3-plane rolling
-//                             window of (8+2) x (14+2) token slices in shared memory (cp.async, zero fill);
-//                             each half-warp produces a strip of 7 outputs with a sliding 3x9 register window,
-//                             so one shared-memory word feeds up to 3 x 6 FMAs.
-//   pool_ln_direct_kernel     stride (1,s,s), s >= 2 (windows barely overlap): taps straight from global / L2;
-//                             also emits the cls and object-token rows for both kernels.
+//   pool_ln_tiled_kernel<S>   stride (1,S,S), S = 1 or 2: CTA = one output tile marched over T through a 5-slot
+//                             ring of input planes in shared memory (cp.async two planes ahead, zero fill for the
+//                             spatial padding); each half-warp produces a strip of outputs with a 3x9 register
+//                             window and FFMA2, so one shared-memory word feeds up to 3 x 6 FMAs; tile 0 of each
+//                             (batch, head) also emits the cls and object-token rows.
+//   pool_ln_direct_kernel     stride >= 4 (windows do not overlap) or unaligned input: taps straight from
+//                             global / L2.
 #include "common.cuh"
 
 namespace {
 
 constexpr int PD = 96;
 constexpr int TAPS = 27;
-constexpr int TW = 14, TH = 8, STRIP = 7;
-constexpr int PW = TW + 2, PH = TH + 2;            // plane with halo
-constexpr int PLANE_WORDS = PH * PW * (PD / 2);    // bf16x2 words
-constexpr int SMEM_TILED = 3 * PLANE_WORDS * 4 + TAPS * PD * 4;
 
 struct Geom {
   int B, h, T, H, W, Ho, Wo, O, s;
@@ -75,100 +72,170 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// ------------------------------------------------------------------------------------------------ stride 1
-__global__ void __launch_bounds__(256, 2)
-pool_ln_s1_tiled_kernel(const bf16* __restrict__ in, Geom g, const float* __restrict__ w, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, bf16* __restrict__ out, float eps) {
+// ------------------------------------------------------------------------------------------------ tiled
+// Geometry per pooling stride S (kernel 3x3x3, pad 1, temporal stride 1):
+//   S = 1: CTA tile 8 x 14 outputs, input tile 10 x 16 tokens; warp w = output row w, its half-warps take the
+//          7-output strips at columns 0 and 7 (token positions of opposite parity -> disjoint bank halves).
+//   S = 2: CTA tile 7 x 7 outputs, input tile 15 x 15 tokens; a warp's half-warps take the same 4-output strip on
+//          two consecutive output rows; input rows r with (r >> 1) odd are stored rotated by 16 words so the two
+//          half-warps again hit disjoint bank halves.
+// A strip needs XN = (STRIP-1)*S + 3 = 9 input positions per (kt, kh): 27 LDS.32 feed 3 x STRIP x 6 FMAs.
+// The CTA marches over T through a ring of NS = 5 input planes filled by cp.async two planes ahead of the
+// plane being computed; temporal padding planes are skipped (uniform branch), spatial padding is zero-filled.
+template <int S> struct TileCfg;
+template <> struct TileCfg<1> { static constexpr int THO = 8, TWO = 14, STRIP = 7; };
+template <> struct TileCfg<2> { static constexpr int THO = 7, TWO = 7, STRIP = 4; };
+constexpr int NS = 5;
+
+template <int S>
+struct TileDims {
+  using C = TileCfg<S>;
+  static constexpr int IH = (C::THO - 1) * S + 3, IW = (C::TWO - 1) * S + 3;
+  static constexpr int XN = (C::STRIP - 1) * S + 3;
+  static constexpr int SLOT_WORDS = IH * IW * (PD / 2);
+  // the last strip of a row may read up to XN positions from a start that leaves fewer in the row: the reads run
+  // into the next row / the weight block (values only reach masked outputs), so the weights sit behind the ring
+  static constexpr int SMEM = NS * SLOT_WORDS * 4 + TAPS * PD * 4 + PD * 4;
+};
+
+// two fp32 FMAs per instruction (sm_100 FFMA2): acc = x * w + acc on both halves of a 64-bit register pair
+__device__ __forceinline__ void fma2(float2& acc, const float2 x, const float2 w) {
+  unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
+  const unsigned long long xx = *reinterpret_cast<const unsigned long long*>(&x);
+  const unsigned long long ww = *reinterpret_cast<const unsigned long long*>(&w);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(xx), "l"(ww));
+  acc = *reinterpret_cast<float2*>(&a);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 1)
+pool_ln_tiled_kernel(const bf16* __restrict__ in, Geom g, const float* __restrict__ w, const float* __restrict__ frac,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ out, float eps) {
+  using C = TileCfg<S>;
+  using D = TileDims<S>;
+  constexpr int IH = D::IH, IW = D::IW, XN = D::XN, STRIP = C::STRIP;
   extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t* planes = reinterpret_cast<uint32_t*>(smem);                       // [3][PH][PW][48]
-  float* sw = reinterpret_cast<float*>(smem + 3 * PLANE_WORDS * 4);           // [27][96]
-  const int tiles_w = (g.W + TW - 1) / TW;
-  const int w0 = (blockIdx.x % tiles_w) * TW, h0 = (blockIdx.x / tiles_w) * TH;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem);                          // [NS][IH][IW][48]
+  float* sw = reinterpret_cast<float*>(smem + NS * D::SLOT_WORDS * 4);         // [27][96]
+  float* sweff = sw + TAPS * PD;                                               // [96]
+  const int tiles_w = (g.Wo + C::TWO - 1) / C::TWO;
+  const int tile = blockIdx.x;
+  const int wo0 = (tile % tiles_w) * C::TWO, ho0 = (tile / tiles_w) * C::THO;
+  const int iw0 = wo0 * S - 1, ih0 = ho0 * S - 1;
   const int head = blockIdx.y, b = blockIdx.z;
   const bf16* zin = in + (int64_t)b * g.in_bs + (int64_t)head * g.in_hs;
-  const int64_t Nout = 1 + (int64_t)g.T * g.H * g.W + g.O;
+  const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
+  const int64_t Nout = 1 + Lo + g.O;
   bf16* obase = out + ((int64_t)b * g.h + head) * Nout * PD;
 
-  for (int i = threadIdx.x; i < PD * TAPS; i += blockDim.x) sw[(i % TAPS) * PD + i / TAPS] = w[i];
-
-  auto load_plane = [&](int t) {  // plane t -> slot (t + 3) % 3; planes -1 and T are the conv's zero padding
-    uint32_t* dst = planes + ((t + 3) % 3) * PLANE_WORDS;
-    const bool tv = t >= 0 && t < g.T;
-    for (int i = threadIdx.x; i < PH * PW * 12; i += blockDim.x) {
+  auto load_plane = [&](int t) {
+    uint32_t* dst = ring + (t % NS) * D::SLOT_WORDS;
+    const bf16* src_t = zin + (1 + (int64_t)t * g.H * g.W) * g.in_ts;
+    for (int i = threadIdx.x; i < IH * IW * 12; i += 256) {
       const int chunk = i % 12, pos = i / 12;
-      const int pw = pos % PW, ph = pos / PW;
-      const int hh = h0 - 1 + ph, ww = w0 - 1 + pw;
-      const bool ok = tv && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W;
-      const bf16* src = ok ? zin + (1 + ((int64_t)t * g.H + hh) * g.W + ww) * g.in_ts + chunk * 8 : zin;
-      cp_async16(dst + pos * 48 + chunk * 4, src, ok);
+      const int pw = pos % IW, ph = pos / IW;
+      const int hh = ih0 + ph, ww = iw0 + pw;
+      const bool ok = hh >= 0 && hh < g.H && ww >= 0 && ww < g.W;
+      const bf16* src = ok ? src_t + ((int64_t)hh * g.W + ww) * g.in_ts + chunk * 8 : zin;
+      const int pchunk = (S == 2 && ((ph >> 1) & 1)) ? (chunk + 4 >= 12 ? chunk - 8 : chunk + 4) : chunk;
+      cp_async16(dst + pos * 48 + pchunk * 4, src, ok);
     }
   };
-  load_plane(-1);
-  load_plane(0);
-  cp_async_commit();
+  // prologue: planes 0..2 in flight while the weights are staged
+  for (int t = 0; t < 3; ++t) {
+    if (t < g.T) load_plane(t);
+    cp_async_commit();
+  }
+  for (int i = threadIdx.x; i < PD * TAPS; i += 256) sw[(i % TAPS) * PD + i / TAPS] = w[i];
 
   const int lane = threadIdx.x & 31, l16 = lane & 15;
-  const int strip = (threadIdx.x >> 4);                 // 0..15 half-warps
-  const int srow = strip >> 1, scol = (strip & 1) * STRIP;  // output row in tile, first output col in tile
+  const int warp = threadIdx.x >> 5, hb = (threadIdx.x >> 4) & 1;
+  const int srow = S == 1 ? warp : (warp >> 1) * 2 + hb;       // output row inside the tile
+  const int scol = S == 1 ? hb * STRIP : (warp & 1) * STRIP;   // first output column inside the tile
+  const int ho = ho0 + srow;
+  const bool row_ok = srow < C::THO && ho < g.Ho;
   float gm[6], bt[6];
   load_affine(gamma, beta, l16, gm, bt);
-  const int ho = h0 + srow;
-  const bool row_ok = ho < g.H;
 
   for (int t = 0; t < g.T; ++t) {
-    // plane t+1 -> slot (t+1)%3 (holds plane t-2, no longer needed)
-    __syncthreads();  // everyone finished computing step t-1 (which read slot (t-2)%3 == (t+1)%3)
-    load_plane(t + 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // planes <= t+1 have landed (t+2 may be in flight)
+    __syncthreads();                                      // ... for every thread; compute(t-1) is finished
+    if (t + 3 < g.T) load_plane(t + 3);                   // slot of plane t-2
     cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
     if (row_ok) {
-      float acc[STRIP][6];
+      float2 acc[STRIP][3];
 #pragma unroll
       for (int o = 0; o < STRIP; ++o)
 #pragma unroll
-        for (int c = 0; c < 6; ++c) acc[o][c] = 0.f;
+        for (int j = 0; j < 3; ++j) acc[o][j] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
         const int tp = t - 1 + kt;
-        const uint32_t* pl = planes + ((tp + 3) % 3) * PLANE_WORDS;
+        if (tp < 0 || tp >= g.T) continue;  // temporal zero padding
+        const uint32_t* pl = ring + (tp % NS) * D::SLOT_WORDS;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-          const uint32_t* rowp = pl + ((srow + kh) * PW + scol) * 48;
-          float x[STRIP + 2][6];
+          const int rin = srow * S + kh;
+          const uint32_t* rowp = pl + (rin * IW + scol * S) * 48 + l16;
+          int off[3];
 #pragma unroll
-          for (int p = 0; p < STRIP + 2; ++p)
+          for (int j = 0; j < 3; ++j) {
+            int jj = j;
+            if (S == 2 && ((rin >> 1) & 1)) jj = j + 1 >= 3 ? j - 2 : j + 1;
+            off[j] = jj * 16;
+          }
+          float2 x[XN][3];
+#pragma unroll
+          for (int p = 0; p < XN; ++p)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-              const uint32_t wd = rowp[p * 48 + l16 + 16 * j];
-              x[p][2 * j] = lo_f(wd);
-              x[p][2 * j + 1] = hi_f(wd);
+              const uint32_t wd = rowp[p * 48 + off[j]];
+              x[p][j] = make_float2(lo_f(wd), hi_f(wd));
             }
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const float* wr = sw + ((kt * 3 + kh) * 3 + kw) * PD;
-            float wt[6];
+            float2 wt[3];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const float2 f = *reinterpret_cast<const float2*>(wr + 2 * (l16 + 16 * j));
-              wt[2 * j] = f.x;
-              wt[2 * j + 1] = f.y;
-            }
+            for (int j = 0; j < 3; ++j) wt[j] = *reinterpret_cast<const float2*>(wr + 2 * (l16 + 16 * j));
 #pragma unroll
             for (int o = 0; o < STRIP; ++o)
 #pragma unroll
-              for (int c = 0; c < 6; ++c) acc[o][c] = fmaf(x[o + kw][c], wt[c], acc[o][c]);
+              for (int j = 0; j < 3; ++j) fma2(acc[o][j], x[o * S + kw][j], wt[j]);
           }
         }
       }
 #pragma unroll
       for (int o = 0; o < STRIP; ++o) {
-        const int wo = w0 + scol + o;
-        if (wo < g.W) {  // uniform across the half-warp
-          uint32_t* dst = reinterpret_cast<uint32_t*>(obase + (1 + ((int64_t)t * g.H + ho) * g.W + wo) * PD);
-          ln_store(acc[o], gm, bt, eps, dst, l16);
+        const int wo = wo0 + scol + o;
+        if (scol + o < C::TWO && wo < g.Wo) {  // uniform across the half-warp
+          uint32_t* dst = reinterpret_cast<uint32_t*>(obase + (1 + ((int64_t)t * g.Ho + ho) * g.Wo + wo) * PD);
+          const float v[6] = {acc[o][0].x, acc[o][0].y, acc[o][1].x, acc[o][1].y, acc[o][2].x, acc[o][2].y};
+          ln_store(v, gm, bt, eps, dst, l16);
         }
       }
+    }
+  }
+  // cls + object tokens of this (batch, head): done by the CTA of tile 0
+  if (tile == 0) {
+    for (int c = threadIdx.x; c < PD; c += 256) {
+      float a = 0.f;
+      for (int tp = 0; tp < TAPS; ++tp) a += sw[tp * PD + c] * frac[tp];
+      sweff[c] = a;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x >> 4; r < 1 + g.O; r += 16) {
+      const int64_t tok_in = r == 0 ? 0 : L + r, tok_out = r == 0 ? 0 : Lo + r;
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(zin + tok_in * g.in_ts);
+      float v[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const uint32_t wd = p[l16 + 16 * j];
+        const int c = 2 * (l16 + 16 * j);
+        v[2 * j] = lo_f(wd) * (r == 0 ? 1.f : sweff[c]);
+        v[2 * j + 1] = hi_f(wd) * (r == 0 ? 1.f : sweff[c + 1]);
+      }
+      ln_store(v, gm, bt, eps, reinterpret_cast<uint32_t*>(obase + tok_out * PD), l16);
     }
   }
 }
@@ -264,21 +331,29 @@ int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   g.Ho = (H - 1) / s + 1; g.Wo = (W - 1) / s + 1;
   g.in_bs = in_bs; g.in_ts = in_ts; g.in_hs = in_hs;
   const int sms = svit_num_sms();
-  const bool tiled = (s == 1) && (in_ts % 8 == 0) && (in_hs % 8 == 0) && (in_bs % 8 == 0) &&
-                     ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && H * W >= 49;
-  if (tiled) {
+  const bool tiled = (s == 1 || s == 2) && (in_ts % 8 == 0) && (in_hs % 8 == 0) && (in_bs % 8 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  if (tiled && s == 1) {
+    using C = TileCfg<1>;
     static bool configured = false;
     if (!configured) {
-      SVIT_CUDA(cudaFuncSetAttribute(pool_ln_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILED));
+      SVIT_CUDA(cudaFuncSetAttribute(pool_ln_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileDims<1>::SMEM));
       configured = true;
     }
-    dim3 grid((unsigned)(((W + TW - 1) / TW) * ((H + TH - 1) / TH)), (unsigned)h, (unsigned)B);
-    pool_ln_s1_tiled_kernel<<<grid, 256, SMEM_TILED, st>>>((const bf16*)in, g, conv_w, gamma, beta, (bf16*)out, eps);
+    dim3 grid((unsigned)(((g.Wo + C::TWO - 1) / C::TWO) * ((g.Ho + C::THO - 1) / C::THO)), (unsigned)h, (unsigned)B);
+    pool_ln_tiled_kernel<1><<<grid, 256, TileDims<1>::SMEM, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
     SVIT_CHECK_LAUNCH();
-    const int64_t special = (int64_t)B * h * (1 + O);
-    int blocks = (int)((special + 15) / 16);
-    if (blocks > sms * 8) blocks = sms * 8;
-    pool_ln_direct_kernel<<<blocks, 256, 0, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps, 1);
+    return 0;
+  }
+  if (tiled && s == 2) {
+    using C = TileCfg<2>;
+    static bool configured = false;
+    if (!configured) {
+      SVIT_CUDA(cudaFuncSetAttribute(pool_ln_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileDims<2>::SMEM));
+      configured = true;
+    }
+    dim3 grid((unsigned)(((g.Wo + C::TWO - 1) / C::TWO) * ((g.Ho + C::THO - 1) / C::THO)), (unsigned)h, (unsigned)B);
+    pool_ln_tiled_kernel<2><<<grid, 256, TileDims<2>::SMEM, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
     SVIT_CHECK_LAUNCH();
     return 0;
   }
