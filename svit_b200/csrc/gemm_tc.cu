@@ -393,7 +393,11 @@ int svit_gemm_tc_supported(const svit_gemm_args* a) {
   return 1;
 }
 
+int svit_gemm_tc_tma_supported(const svit_gemm_args* a);  // gemm_tc2.cu
+int svit_gemm_tc_tma(const svit_gemm_args* a, cudaStream_t st);
+
 int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st) {
+  if (svit_gemm_tc_tma_supported(a)) return svit_gemm_tc_tma(a, st);
   const bool a_mn = a->transA != 0;  // A stored [K, M]
   const bool b_mn = a->transB == 0;  // B stored [K, N]
   if (!a_mn && !b_mn) return dispatch_bn<false, false>(a, st);

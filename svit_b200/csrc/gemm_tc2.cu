@@ -1,0 +1,475 @@
+// bf16 GEMM on the 5th-generation tensor cores, TMA-store epilogue (the production path of svit_gemm for bf16
+// outputs; gemm_tc.cu keeps the generic-epilogue kernel for fp32 outputs, pre-activation side outputs and
+// MN-major A).  Same contract (svit_gemm_args):
+//   C[M,N] = residual + sample_scale[row/rps] * ( act(A.op(B) + bias) * gelu'(gelu_pre) )
+//
+// Persistent, warp-specialised, one CTA per SM (320 threads):
+//   warp 0     TMA producer: ring of {A 128x64, B BNx64} bf16 tiles, 128-byte swizzle, OOB zero fill
+//   warp 1     MMA issuer (one lane): tcgen05.mma 128 x BN x 16, fp32 accumulators double-buffered in TMEM
+//   warps 2-9  epilogue, two groups of four warps (one warp per TMEM lane quarter, thread = accumulator row).
+//              A group takes alternate 32-column boxes of the tile: tcgen05.ld (32 columns) -> bias / GELU /
+//              gelu' / DropPath scale / residual in registers -> bf16 -> 64-byte-swizzled staging slot -> one
+//              TMA store per box (cp.async.bulk.tensor, clipped at the tensor edge).  The residual (or gelu_pre)
+//              box is TMA-loaded INTO the staging slot two boxes ahead by the group's leader thread and combined
+//              in place, so every global access of the epilogue is a bulk tensor copy.
+// Ring of 4 staging slots per group: a slot is rewritten only after the store that read it has drained
+// (cp.async.bulk.wait_group.read 2 by the leader, published by the group's named barrier).
+#include "tc_common.cuh"
+#include "../../include/svit_b200.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr int BOX_N = 32;                 // columns per epilogue box
+constexpr int SLOT_BYTES = BM * BOX_N * 2;  // 8 KB
+constexpr int SPG = 4;                    // staging slots per epilogue group
+constexpr int PF_DIST = 2;                // aux boxes requested ahead
+constexpr int SMEM_LIMIT = 232448;        // 227 KB
+
+enum { AUX_NONE = 0, AUX_RESIDUAL = 1, AUX_GELU_PRE = 2 };
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = 2 * SPG * SLOT_BYTES;
+  static constexpr int FIXED = STG_BYTES + 512 + 1024;  // staging + barriers + alignment slack
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+};
+
+struct Epi {
+  const float* bias;
+  const float* sample_scale;
+  int64_t rps;
+  int act;
+  int aux;  // AUX_*
+  int64_t rows_in, rows_out, row_off;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): Phi(x) and x * phi(x) for gelu'(x) = Phi(x) + x phi(x).
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float ex = exp2f(-1.4426950408889634f * z * z);
+  const float erfc_half = 0.5f * poly * t * ex;
+  const float cdf = x >= 0.f ? 1.0f - erfc_half : erfc_half;
+  return fmaf(x * 0.3989422804014327f, ex, cdf);
+}
+
+// x * Phi(x), Phi through a tanh form fitted to the exact erf GELU (max abs deviation 2.5e-5 on [-9, 9]) and
+// MUFU.TANH: one MUFU + 7 FP32 ops; the error is an order of magnitude below the bf16 rounding of the result.
+__device__ __forceinline__ float gelu_fwd_fast(float x) {
+  const float x2 = fminf(x * x, 81.0f);
+  const float u = x * fmaf(x2, fmaf(x2, -3.51516789e-04f, 3.70056460e-02f), 7.97507884e-01f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map),
+               "r"(tc::smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Static schedule of one epilogue group's boxes: tiles blockIdx.x, +gridDim.x, ...; inside a tile the boxes
+// c = g, g+2, ... that start left of N.
+struct BoxIter {
+  int64_t t, num_tiles, n_tiles, N;
+  int c, g, BN;
+  __device__ BoxIter(int64_t t0, int64_t num_tiles_, int64_t n_tiles_, int64_t N_, int g_, int BN_)
+      : t(t0), num_tiles(num_tiles_), n_tiles(n_tiles_), N(N_), c(g_), g(g_), BN(BN_) {
+    settle();
+  }
+  __device__ int nbox() const {
+    const int64_t n0 = (t % n_tiles) * BN;
+    const int64_t rem = N - n0 < BN ? N - n0 : BN;
+    return (int)((rem + BOX_N - 1) / BOX_N);
+  }
+  __device__ void settle() {
+    while (t < num_tiles && c >= nbox()) {
+      t += gridDim.x;
+      c = g;
+    }
+  }
+  __device__ bool valid() const { return t < num_tiles; }
+  __device__ void next() {
+    c += 2;
+    settle();
+  }
+};
+
+__device__ __forceinline__ int64_t remap_row(const Epi& e, int64_t m) {
+  return e.rows_in > 0 ? (m / e.rows_in) * e.rows_out + e.row_off + (m % e.rows_in) : m;
+}
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_x, int64_t M,
+                   int64_t N, int64_t K, Epi e) {
+  using L = Cfg<BN>;
+  constexpr int STAGES = L::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stg_base = smem + L::STG_OFF;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* aux_full = tmem_empty + 2;  // [2 * SPG]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_full + 2 * SPG);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int64_t num_tiles = m_tiles * n_tiles;
+  const int num_kb = (int)((K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_b);
+    tc::prefetch_tmap(&tmap_c);
+    if (e.aux) tc::prefetch_tmap(&tmap_x);
+    for (int i = 0; i < STAGES; ++i) {
+      tc::mbar_init(&full_bar[i], 1);
+      tc::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&tmem_full[i], 1);
+      tc::mbar_init(&tmem_empty[i], EPI_WARPS);
+    }
+    for (int i = 0; i < 2 * SPG; ++i) tc::mbar_init(&aux_full[i], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, L::TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (int)((t / n_tiles) * BM), n0 = (int)((t % n_tiles) * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * L::STAGE_BYTES;
+          unsigned char* sb = sa + L::A_BYTES;
+          tc::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tc::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+          if (!B_MN) {
+            tc::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tc::tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&tmem_empty[as], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? tc::smem_desc_sw128(sb + k * 2048, 8192, 1024) : tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+            tc::umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) tc::umma_commit(&tmem_full[as]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int g = (warp - 2) >> 2;     // epilogue group: boxes c with c % 2 == g
+    const int r = q * 32 + lane;       // accumulator row inside the tile
+    const bool leader = (warp - 2) == g * 4 && lane == 0;
+    unsigned char* my_slots = stg_base + g * SPG * SLOT_BYTES;
+    uint64_t* my_aux = aux_full + g * SPG;
+    const uint32_t sw = (uint32_t)((r >> 1) & 3);
+    const int aux = e.aux;
+
+    // leader: request the first PF_DIST aux boxes
+    BoxIter pf(blockIdx.x, num_tiles, n_tiles, N, g, BN);
+    uint32_t pf_cnt = 0;
+    auto request_aux = [&]() {
+      if (!pf.valid()) return;
+      const int64_t m0 = (pf.t / n_tiles) * BM, n0 = (pf.t % n_tiles) * BN;
+      const int64_t row0 = aux == AUX_RESIDUAL ? remap_row(e, m0) : m0;
+      const int slot = pf_cnt % SPG;
+      tc::mbar_arrive_expect_tx(&my_aux[slot], SLOT_BYTES);
+      tc::tma_load_2d(my_slots + slot * SLOT_BYTES, &tmap_x, &my_aux[slot], (int)(n0 + pf.c * BOX_N), (int)row0);
+      ++pf_cnt;
+      pf.next();
+    };
+    if (leader && aux) {
+      for (int i = 0; i < PF_DIST; ++i) request_aux();
+    }
+
+    uint32_t cnt = 0;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      const int64_t rem = N - n0 < BN ? N - n0 : BN;
+      const int nbox = (int)((rem + BOX_N - 1) / BOX_N);
+      const int64_t orow0 = remap_row(e, m0);
+      float sc = 1.f;
+      if (e.sample_scale) {
+        const int64_t m = m0 + r < M ? m0 + r : M - 1;
+        sc = e.sample_scale[m / e.rps];
+      }
+      int last_c = -1;
+      for (int c = g; c < nbox; c += 2) last_c = c;
+      tc::mbar_wait(&tmem_full[as], acc_phase);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if (last_c < 0) {  // no box for this group in this tile (narrow tail): keep the arrival count uniform
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
+      }
+#pragma unroll 1
+      for (int c = g; c < nbox; c += 2) {
+        const int slot = cnt % SPG;
+        unsigned char* sbase = my_slots + slot * SLOT_BYTES;
+        float v[BOX_N];
+        tc::tmem_ld32(taddr + c * BOX_N, v);
+        const int64_t ncol = n0 + c * BOX_N;
+        // bias (L1-resident broadcast loads) while the TMEM load is in flight
+        float bv[BOX_N];
+        if (e.bias) {
+#pragma unroll
+          for (int j = 0; j < BOX_N; j += 4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ncol + j < N) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + ncol + j));
+            bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+          }
+        }
+        tc::tmem_ld_wait();
+        if (c == last_c) {  // this warp's rows of the accumulator are in registers: release the TMEM buffer
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
+        }
+        if (e.bias) {
+#pragma unroll
+          for (int j = 0; j < BOX_N; ++j) v[j] += bv[j];
+        }
+        if (e.act == 1) {
+#pragma unroll
+          for (int j = 0; j < BOX_N; ++j) v[j] = gelu_fwd_fast(v[j]);
+        }
+        uint4 ax[4];
+        if (aux) {
+          tc::mbar_wait(&my_aux[slot], (cnt / SPG) & 1);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ax[k] = *reinterpret_cast<const uint4*>(sbase + r * 64 + ((k ^ sw) << 4));
+        }
+        if (aux == AUX_GELU_PRE) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&ax[k]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(gp[i]);
+              v[k * 8 + 2 * i] *= gelu_grad(f.x);
+              v[k * 8 + 2 * i + 1] *= gelu_grad(f.y);
+            }
+          }
+        }
+        if (e.sample_scale) {
+#pragma unroll
+          for (int j = 0; j < BOX_N; ++j) v[j] *= sc;
+        }
+        if (aux == AUX_RESIDUAL) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&ax[k]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(gp[i]);
+              v[k * 8 + 2 * i] += f.x;
+              v[k * 8 + 2 * i + 1] += f.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint4 o = {pack_bf16(v[k * 8], v[k * 8 + 1]), pack_bf16(v[k * 8 + 2], v[k * 8 + 3]),
+                           pack_bf16(v[k * 8 + 4], v[k * 8 + 5]), pack_bf16(v[k * 8 + 6], v[k * 8 + 7])};
+          *reinterpret_cast<uint4*>(sbase + r * 64 + ((k ^ sw) << 4)) = o;
+        }
+        tc::fence_proxy_async();
+        named_bar_sync(1 + g, 128);
+        if (leader) {
+          tma_store_2d(&tmap_c, sbase, (int)ncol, (int)orow0);
+          bulk_commit();
+          bulk_wait_read<2>();  // the stores of boxes <= cnt-2 have drained: their slots may be refilled
+          if (aux) request_aux();
+        }
+        ++cnt;
+      }
+    }
+    if (leader) bulk_wait_all();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
+}
+
+// 2-D bf16 tensor [rows, cols] (row pitch ld), box = [BM rows, 32 cols], 64-byte swizzle (epilogue boxes).
+int make_box_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  svit_tmap_encode_fn enc = svit_get_tmap_encode();
+  if (!enc) return SVIT_ENOTSUP;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {BOX_N, BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : SVIT_EINVAL;
+}
+
+template <int BN, bool B_MN>
+int launch(const svit_gemm_args* a, cudaStream_t st) {
+  using L = Cfg<BN>;
+  static_assert(L::STAGES >= 2, "pipeline too shallow");
+  static_assert(L::TOTAL <= SMEM_LIMIT, "shared memory budget");
+  CUtensorMap ta, tb, tcm, tx;
+  int rc;
+  if ((rc = svit_make_tmap_2d(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM))) return rc;
+  if (!B_MN) rc = svit_make_tmap_2d(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, BN);
+  else rc = svit_make_tmap_2d(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK);
+  if (rc) return rc;
+  const uint64_t out_rows = a->rows_in > 0 ? (uint64_t)((a->M + a->rows_in - 1) / a->rows_in * a->rows_out) : (uint64_t)a->M;
+  if ((rc = make_box_map(&tcm, a->C, out_rows, (uint64_t)a->N, (uint64_t)a->ldc))) return rc;
+  Epi e;
+  e.bias = a->bias;
+  e.sample_scale = a->sample_scale; e.rps = a->rows_per_sample;
+  e.act = a->act;
+  e.aux = a->residual ? AUX_RESIDUAL : (a->gelu_pre ? AUX_GELU_PRE : AUX_NONE);
+  e.rows_in = a->rows_in; e.rows_out = a->rows_out; e.row_off = a->row_off;
+  tx = tcm;
+  if (e.aux == AUX_RESIDUAL) rc = make_box_map(&tx, a->residual, out_rows, (uint64_t)a->N, (uint64_t)a->ldr);
+  else if (e.aux == AUX_GELU_PRE) rc = make_box_map(&tx, a->gelu_pre, (uint64_t)a->M, (uint64_t)a->N, (uint64_t)a->ldg);
+  if (rc) return rc;
+  auto kern = gemm_tc_tma_kernel<BN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int64_t tiles = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN);
+  const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
+  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ta, tb, tcm, tx, a->M, a->N, a->K, e);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+// tile width: the widest of {256, 192, 128, 96, 64} that divides N, else the one wasting the fewest MMA columns
+int pick_bn(int64_t N, bool b_mn) {
+  const int cand[5] = {256, 192, 128, 96, 64};
+  for (int i = 0; i < 5; ++i) {
+    if (b_mn && cand[i] % 64) continue;
+    if (N % cand[i] == 0) return cand[i];
+  }
+  int best = 64;
+  int64_t best_cols = -1;
+  for (int i = 0; i < 5; ++i) {
+    if (b_mn && cand[i] % 64) continue;
+    const int64_t cols = (N + cand[i] - 1) / cand[i] * cand[i];
+    if (best_cols < 0 || cols < best_cols) { best_cols = cols; best = cand[i]; }
+  }
+  return best;
+}
+
+template <bool B_MN>
+int dispatch(const svit_gemm_args* a, cudaStream_t st) {
+  switch (pick_bn(a->N, B_MN)) {
+    case 256: return launch<256, B_MN>(a, st);
+    case 192: return launch<192, B_MN>(a, st);
+    case 128: return launch<128, B_MN>(a, st);
+    case 96: if (!B_MN) return launch<96, false>(a, st); return launch<128, B_MN>(a, st);
+    default: return launch<64, B_MN>(a, st);
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// Preconditions beyond svit_gemm_tc_supported(): bf16 output, K-major A, at most one auxiliary input, no
+// pre-activation side output, output row remap only with whole tiles per segment.
+int svit_gemm_tc_tma_supported(const svit_gemm_args* a) {
+  if (a->out_dtype != SVIT_BF16 || a->transA) return 0;
+  if (a->pre_out) return 0;
+  if (a->residual && a->gelu_pre) return 0;
+  if (a->rows_in > 0 && (a->rows_in % BM || a->gelu_pre)) return 0;
+  if (a->ldc % 8 || !aligned16(a->C)) return 0;
+  if (a->residual && (a->ldr % 8 || !aligned16(a->residual))) return 0;
+  if (a->gelu_pre && (a->ldg % 8 || !aligned16(a->gelu_pre))) return 0;
+  if (a->bias && !aligned16(a->bias)) return 0;
+  if (a->M < BM) return 0;  // tiny problems (heads): the generic kernel is fine
+  return 1;
+}
+
+int svit_gemm_tc_tma(const svit_gemm_args* a, cudaStream_t st) {
+  if (a->transB == 0) return dispatch<true>(a, st);
+  return dispatch<false>(a, st);
+}

@@ -118,6 +118,60 @@ __global__ void __launch_bounds__(256) im2col_rows_kernel(const TI* __restrict__
   }
 }
 
+// Fast variant for bf16 clips: CTA = 4 * (Kpad / 8) threads per (b, t', h') output row.  The R = Cin*kt*kh input
+// rows are staged with 16-byte loads (halo of HALO zero elements on both sides); a thread owns ONE 16-byte column
+// chunk q of the lowered rows, so the eight source offsets of its chunk sit in registers and every output row
+// (Kpad * 2 bytes) is written as contiguous 16-byte stores.
+constexpr int IM_HALO = 4;
+__global__ void __launch_bounds__(256) im2col_rows_vec_kernel(const bf16* __restrict__ x, bf16* __restrict__ cols, int Cin,
+                                                              int T, int H, int W, int To, int Ho, int Wo, int kt, int kh,
+                                                              int kw, int st, int sh, int sw, int pt, int ph, int pw,
+                                                              int Kpad, int RW) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned short* rows = reinterpret_cast<unsigned short*>(smem_raw);  // [R][RW]
+  const int R = Cin * kt * kh, K = R * kw;
+  const int ho = blockIdx.x % Ho, to = (blockIdx.x / Ho) % To, b = blockIdx.x / (Ho * To);
+  const int cpr = Kpad >> 3, wchunks = W >> 3;
+  // stage: row r = (c, dt, dh); 16-byte chunks of the W input pixels land at element HALO + 8*j (8-byte aligned)
+  for (int i = threadIdx.x; i < R * (wchunks + 2); i += blockDim.x) {
+    const int r = i / (wchunks + 2), j = i % (wchunks + 2) - 1;
+    unsigned short* dst = rows + r * RW;
+    if (j < 0) {
+      *reinterpret_cast<uint2*>(dst) = make_uint2(0u, 0u);
+    } else if (j == wchunks) {
+      *reinterpret_cast<uint2*>(dst + IM_HALO + W) = make_uint2(0u, 0u);
+    } else {
+      const int dh = r % kh, dt = (r / kh) % kt, c = r / (kh * kt);
+      const int t = to * st - pt + dt, hh = ho * sh - ph + dh;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (t >= 0 && t < T && hh >= 0 && hh < H)
+        v = __ldg(reinterpret_cast<const uint4*>(x + ((((int64_t)b * Cin + c) * T + t) * H + hh) * W + 8 * j));
+      uint2* d2 = reinterpret_cast<uint2*>(dst + IM_HALO + 8 * j);
+      d2[0] = make_uint2(v.x, v.y);
+      d2[1] = make_uint2(v.z, v.w);
+    }
+  }
+  const int q = threadIdx.x % cpr, w_first = threadIdx.x / cpr, w_step = blockDim.x / cpr;
+  int off[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int k = q * 8 + u;
+    off[u] = k < K ? (k / kw) * RW + (k % kw) + IM_HALO - pw : -1;
+  }
+  __syncthreads();
+  bf16* obase = cols + ((((int64_t)b * To + to) * Ho + ho) * Wo) * Kpad + q * 8;
+  for (int wo = w_first; wo < Wo; wo += w_step) {
+    const int base = wo * sw;
+    unsigned short e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = off[u] < 0 ? (unsigned short)0 : rows[off[u] + base];
+    uint4 o;
+    o.x = e[0] | ((uint32_t)e[1] << 16); o.y = e[2] | ((uint32_t)e[3] << 16);
+    o.z = e[4] | ((uint32_t)e[5] << 16); o.w = e[6] | ((uint32_t)e[7] << 16);
+    *reinterpret_cast<uint4*>(obase + (int64_t)wo * Kpad) = o;
+  }
+}
+
 // skip-path MaxPool3d k(1,3,3) s(1,s,s) p(0,1,1) on [B, N, C] (attention.py:562-564): one thread per 8 channels
 __global__ void __launch_bounds__(256) skip_maxpool_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int C,
                                                                 int T_, int H, int W, int Ho, int Wo, int O, int s) {
@@ -217,6 +271,24 @@ int svit_im2col_rows(const void* x, void* cols, int B, int Cin, int T, int H, in
   if (smem > 200 * 1024) return 0;
   const unsigned grid = (unsigned)((int64_t)B * To * Ho);
   cudaError_t e;
+  const int cpr = Kpad / 8;
+  if (in_dtype == SVIT_BF16 && W % 8 == 0 && pw <= IM_HALO && cpr <= 64 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int RWv = (W + 2 * IM_HALO + 7) & ~7;  // rows 16-byte aligned
+    const int threads = (256 / cpr) * cpr;
+    const size_t smv = (size_t)R * RWv * 2;
+    if ((Wo - 1) * sw + kw - 1 - pw < W + 4 && smv <= 200 * 1024) {
+      static size_t confv = 0;
+      if (smv > confv) {
+        if ((e = cudaFuncSetAttribute(im2col_rows_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv)) != cudaSuccess)
+          return 1000 + (int)e;
+        confv = smv;
+      }
+      im2col_rows_vec_kernel<<<grid, threads, smv, st>>>((const bf16*)x, (bf16*)cols, Cin, T, H, W, To, Ho, Wo, kt, kh, kw, st_,
+                                                         sh, sw, pt, ph, pw, Kpad, RWv);
+      e = cudaGetLastError();
+      return e == cudaSuccess ? 1 : 1000 + (int)e;
+    }
+  }
   if (in_dtype == SVIT_BF16) {
     static size_t conf = 0;
     if (smem > conf) {

@@ -216,14 +216,14 @@ class _Mlp(torch.autograd.Function):
     """y = residual + sample_scale * fc2(gelu(fc1(x)))   (common.py:27-34, attention.py:567-570)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, residual, sample_scale):
+    def forward(ctx, x, w1, b1, w2, b2, residual, sample_scale, grad_mode):
         _chk(x, "mlp")
         x = x.contiguous()
         K = x.shape[-1]
         Hd = w1.shape[0]
         N = w2.shape[0]
         M = x.numel() // K
-        need = any(ctx.needs_input_grad[:5])
+        need = grad_mode and any(ctx.needs_input_grad[:5])
         w1c, w2c = cast_weight(w1, x.dtype), cast_weight(w2, x.dtype)
         hid = torch.empty(*x.shape[:-1], Hd, dtype=x.dtype, device=x.device)
         pre = torch.empty_like(hid) if need else None
@@ -260,11 +260,11 @@ class _Mlp(torch.autograd.Function):
         db1 = _colsum(dpre, M, Hd)
         dx = torch.empty_like(x)
         gemm(dpre, w1c, dx, M, K, Hd, Hd, K, K, 0, 0)
-        return dx, dw1, db1, dw2, db2, dres, None
+        return dx, dw1, db1, dw2, db2, dres, None, None
 
 
 def mlp(x, w1, b1, w2, b2, residual=None, sample_scale=None):
-    return _Mlp.apply(x, w1, b1, w2, b2, residual, sample_scale)
+    return _Mlp.apply(x, w1, b1, w2, b2, residual, sample_scale, torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------------------------
@@ -272,12 +272,12 @@ def mlp(x, w1, b1, w2, b2, residual=None, sample_scale=None):
 # --------------------------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps):
+    def forward(ctx, x, gamma, beta, eps, grad_mode):
         _chk(x, "layer_norm")
         x = x.contiguous()
         Cn = x.shape[-1]
         rows = x.numel() // Cn
-        need = any(ctx.needs_input_grad[:3])
+        need = grad_mode and any(ctx.needs_input_grad[:3])
         y = torch.empty_like(x)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
@@ -299,11 +299,11 @@ class _LayerNorm(torch.autograd.Function):
         db = torch.zeros(Cn, dtype=torch.float32, device=x.device)
         _call("svit_layernorm_bwd", dy.data_ptr(), x.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
               dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, Cn, _dt(x), _stream())
-        return dx, dg, db, None
+        return dx, dg, db, None, None
 
 
 def layer_norm(x, gamma, beta, eps=LN_EPS):
-    return _LayerNorm.apply(x, gamma, beta, eps)
+    return _LayerNorm.apply(x, gamma, beta, eps, torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------------------------
@@ -441,13 +441,13 @@ def _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale):
 
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables):
+    def forward(ctx, q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables, grad_mode):
         _chk(q, "attention")
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         Rh, Rw, Rt = (r.to(q.dtype).contiguous() for r in (Rh, Rw, Rt))
         B, h, Nq, d = q.shape
         assert d == HEAD_DIM, "svit_b200 attention kernels are specialised for head_dim 96"
-        need = any(ctx.needs_input_grad[:6])
+        need = grad_mode and any(ctx.needs_input_grad[:6])
         out = torch.empty(B, Nq, h * d, dtype=q.dtype, device=q.device)
         lse = torch.empty(B, h, Nq, dtype=torch.float32, device=q.device) if need else None
         a = _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale)
@@ -482,14 +482,15 @@ class _Attention(torch.autograd.Function):
         a.d_rel_h, a.d_rel_w, a.d_rel_t = dRh.data_ptr(), dRw.data_ptr(), dRt.data_ptr()
         a.ws_e, a.ws_de, a.ws_delta = ws_e.data_ptr(), ws_de.data_ptr(), ws_delta.data_ptr()
         _call("svit_attn_bwd", C.byref(a), _stream())
-        return dq, dk, dv, dRh, dRw, dRt, None, None, None, None, None
+        return dq, dk, dv, dRh, dRw, dRt, None, None, None, None, None, None
 
 
 def attention(q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables=None):
     """softmax(scale q k^T + rel-pos bias) v + residual pooling -> [B, Nq, h*96] (attention.py:429-461).
     Rh/Rw/Rt: gathered tables (differentiable); tc_tables: (cat table bf16, [rows], idx_h, idx_w, idx_t, key codes)
     for the tcgen05 kernel, or None."""
-    return _Attention.apply(q, k, v, Rh, Rw, Rt, tuple(q_thw), tuple(k_thw), O, float(scale), tc_tables)
+    return _Attention.apply(q, k, v, Rh, Rw, Rt, tuple(q_thw), tuple(k_thw), O, float(scale), tc_tables,
+                            torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------------------------

@@ -60,6 +60,59 @@ def test_gemm_tc_fused_epilogue():
     assert max_rel_err(cpu(gout), (A.float() @ W.float().t()).double() * zz.grad) < 6e-3
 
 
+@pytest.mark.parametrize("M,N,K,mode", [
+    (768, 288, 96, "gelu"), (768, 384, 192, "res_remap"), (1000, 1536, 384, "gelu_pre"), (50000, 1152, 384, "res"),
+    (33000, 96, 384, "res_scale"), (4100, 200, 72, "bias"), (20000, 3072, 768, "gelu"), (3000, 768, 3072, "res_scale"),
+    (130, 40, 40, "res"),
+])
+def test_gemm_tc_tma_epilogues(M, N, K, mode):
+    """The TMA-store epilogue kernel (bf16 out): every fused epilogue, ragged M / N / K, many tiles per CTA so the
+    staging-slot ring, the aux prefetch and both TMEM accumulator phases wrap several times."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=gen).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(N, K, generator=gen) * K ** -0.5).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(N, generator=gen).to(DEV)
+    z = A.float() @ W.float().t() + bias
+    if mode == "gelu":
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.gemm(A, W, out, M, N, K, K, K, N, 0, 1, bias=bias, act=1, impl=TC)
+        ref = torch.nn.functional.gelu(z)
+    elif mode == "bias":
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.gemm(A, W, out, M, N, K, K, K, N, 0, 1, bias=bias, impl=TC)
+        ref = z
+    elif mode == "res":
+        res = torch.randn(M, N, generator=gen).to(torch.bfloat16).to(DEV)
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.gemm(A, W, out, M, N, K, K, K, N, 0, 1, bias=bias, residual=res, ldr=N, impl=TC)
+        ref = z + res.float()
+    elif mode == "res_scale":
+        nb = 4 if M % 4 == 0 else 1
+        res = torch.randn(M, N, generator=gen).to(torch.bfloat16).to(DEV)
+        scale = torch.tensor([0.0, 1.25, 1.0, 2.0][:nb]).to(DEV)
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.gemm(A, W, out, M, N, K, K, K, N, 0, 1, bias=bias, residual=res, ldr=N, sample_scale=scale,
+                 rows_per_sample=M // nb, impl=TC)
+        ref = z * scale.repeat_interleave(M // nb)[:, None] + res.float()
+    elif mode == "res_remap":
+        nb, rin, rout, off = M // 384, 384, 400, 9
+        res = torch.randn(nb, rout, N, generator=gen).to(torch.bfloat16).to(DEV)
+        out = res.clone()
+        ops.gemm(A, W, out, M, N, K, K, K, N, 0, 1, bias=bias, residual=res, ldr=N, remap=(rin, rout, off), impl=TC)
+        ref = res.float().clone()
+        ref[:, off:off + rin] += z.reshape(nb, rin, N)
+        assert torch.equal(out[:, :off], res[:, :off]) and torch.equal(out[:, off + rin:], res[:, off + rin:])
+    elif mode == "gelu_pre":
+        pre = torch.randn(M, N, generator=gen).to(torch.bfloat16).to(DEV)
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.gemm(A, W, out, M, N, K, K, K, N, 0, 1, gelu_pre=pre, ldg=N, impl=TC)
+        zz = pre.float().double().requires_grad_(True)
+        torch.nn.functional.gelu(zz).sum().backward()
+        ref = ((z - bias).double() * zz.grad).float()
+    assert not torch.isnan(out.float()).any()
+    assert max_rel_err(cpu(out), cpu(ref)) < 6e-3, (M, N, K, mode)
+
+
 def test_gemm_tc_matches_simt_on_model_shapes():
     """Every forward GEMM shape of configs/ssv2.yaml (M = tokens of one clip)."""
     gen = torch.Generator().manual_seed(29)
