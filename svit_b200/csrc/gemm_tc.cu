@@ -172,7 +172,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                int64_t N, int64_t K, EpiArgs e) {
   using L = SmemLayout<BN>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer offset (not an integer round trip) so accesses stay in the shared state space
+  unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stg_base = smem + STAGES * L::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -243,11 +244,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        tc::mbar_wait(&tmem_empty[as], acc_phase ^ 1);
+        tc::mbar_wait_hot(&tmem_empty[as], acc_phase ^ 1);
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          tc::mbar_wait(&full_bar[stage], phase);
+          tc::mbar_wait_hot(&full_bar[stage], phase);
           tc::fence_after_sync();
           const uint32_t sa = tc::smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
@@ -276,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int as = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-      tc::mbar_wait(&tmem_full[as], acc_phase);
+      tc::mbar_wait_hot(&tmem_full[as], acc_phase);
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       const int last = half ? LAST_CH1 : LAST_CH0;

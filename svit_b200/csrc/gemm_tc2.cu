@@ -53,6 +53,7 @@ struct Epi {
   int act;
   int aux;  // AUX_*
   int64_t rows_in, rows_out, row_off;
+  unsigned long long* dbg;  // optional timeline buffer (CTA 0 only): [role][event] = (tag, clock64)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -74,15 +75,25 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return fmaf(x * 0.3989422804014327f, ex, cdf);
 }
 
-// x * Phi(x), Phi through a tanh form fitted to the exact erf GELU (max abs deviation 2.5e-5 on [-9, 9]) and
-// MUFU.TANH: one MUFU + 7 FP32 ops; the error is an order of magnitude below the bf16 rounding of the result.
-__device__ __forceinline__ float gelu_fwd_fast(float x) {
-  const float x2 = fminf(x * x, 81.0f);
-  const float u = x * fmaf(x2, fmaf(x2, -3.51516789e-04f, 3.70056460e-02f), 7.97507884e-01f);
-  float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
-  const float hx = 0.5f * x;
-  return fmaf(hx, th, hx);
+using tc::add2;
+using tc::fma2;
+using tc::mul2;
+
+// x * Phi(x) on two elements, Phi through a tanh form fitted to the exact erf GELU (max abs deviation 2.5e-5 on
+// [-9, 9], x^2 clamped beyond) and MUFU.TANH; the error is an order of magnitude below the bf16 rounding of the
+// result.  Per pair: 5 packed FP32 ops + 2 FMNMX + 2 MUFU.
+__device__ __forceinline__ float2 gelu_fwd_fast2(const float2 x) {
+  float2 x2 = mul2(x, x);
+  x2.x = fminf(x2.x, 81.0f);
+  x2.y = fminf(x2.y, 81.0f);
+  const float2 p = fma2(x2, fma2(x2, make_float2(-3.51516789e-04f, -3.51516789e-04f), make_float2(3.70056460e-02f, 3.70056460e-02f)),
+                        make_float2(7.97507884e-01f, 7.97507884e-01f));
+  const float2 u = mul2(x, p);
+  float2 th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(u.y));
+  const float2 hx = mul2(x, make_float2(0.5f, 0.5f));
+  return fma2(hx, th, hx);
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
@@ -127,6 +138,16 @@ struct BoxIter {
   }
 };
 
+// timeline probe: role 0 producer, 1 MMA, 2 epilogue group-0 leader lane; 4096 events per role
+#define TL(role, tag)                                                            \
+  do {                                                                           \
+    if (e.dbg && blockIdx.x == 0 && tl_n < 4096) {                               \
+      e.dbg[((role) * 4096 + tl_n) * 2] = (unsigned long long)(tag);             \
+      e.dbg[((role) * 4096 + tl_n) * 2 + 1] = (unsigned long long)clock64();     \
+      ++tl_n;                                                                    \
+    }                                                                            \
+  } while (0)
+
 __device__ __forceinline__ int64_t remap_row(const Epi& e, int64_t m) {
   return e.rows_in > 0 ? (m / e.rows_in) * e.rows_out + e.row_off + (m % e.rows_in) : m;
 }
@@ -139,7 +160,8 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   using L = Cfg<BN>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer offset (not an integer round trip) so accesses stay in the shared state space
+  unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stg_base = smem + L::STG_OFF;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -180,10 +202,12 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int tl_n = 0;
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (int)((t / n_tiles) * BM), n0 = (int)((t % n_tiles) * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          TL(0, kb);
           unsigned char* sa = smem + stage * L::STAGE_BYTES;
           unsigned char* sb = sa + L::A_BYTES;
           tc::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
@@ -205,15 +229,18 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      int tl_n = 0;
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        tc::mbar_wait(&tmem_empty[as], acc_phase ^ 1);
+        tc::mbar_wait_hot(&tmem_empty[as], acc_phase ^ 1);
         tc::fence_after_sync();
+        TL(1, 1000);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          tc::mbar_wait(&full_bar[stage], phase);
+          tc::mbar_wait_hot(&full_bar[stage], phase);
           tc::fence_after_sync();
+          TL(1, kb);
           const uint32_t sa = tc::smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
@@ -258,6 +285,8 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
     uint32_t cnt = 0;
     int it = 0;
+    int tl_n = leader ? 0 : 4096;
+    if (g != 0) tl_n = 4096;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -272,8 +301,10 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
       int last_c = -1;
       for (int c = g; c < nbox; c += 2) last_c = c;
-      tc::mbar_wait(&tmem_full[as], acc_phase);
+      TL(2, 2000);
+      tc::mbar_wait_hot(&tmem_full[as], acc_phase);
       tc::fence_after_sync();
+      TL(2, 2001);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       if (last_c < 0) {  // no box for this group in this tile (narrow tail): keep the arrival count uniform
         tc::fence_before_sync();
@@ -298,22 +329,25 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
         tc::tmem_ld_wait();
+        TL(2, 100 + c);
         if (c == last_c) {  // this warp's rows of the accumulator are in registers: release the TMEM buffer
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
         }
+        float2* v2 = reinterpret_cast<float2*>(v);
         if (e.bias) {
+          const float2* b2 = reinterpret_cast<const float2*>(bv);
 #pragma unroll
-          for (int j = 0; j < BOX_N; ++j) v[j] += bv[j];
+          for (int j = 0; j < BOX_N / 2; ++j) v2[j] = add2(v2[j], b2[j]);
         }
         if (e.act == 1) {
 #pragma unroll
-          for (int j = 0; j < BOX_N; ++j) v[j] = gelu_fwd_fast(v[j]);
+          for (int j = 0; j < BOX_N / 2; ++j) v2[j] = gelu_fwd_fast2(v2[j]);
         }
         uint4 ax[4];
         if (aux) {
-          tc::mbar_wait(&my_aux[slot], (cnt / SPG) & 1);
+          tc::mbar_wait_hot(&my_aux[slot], (cnt / SPG) & 1);
 #pragma unroll
           for (int k = 0; k < 4; ++k) ax[k] = *reinterpret_cast<const uint4*>(sbase + r * 64 + ((k ^ sw) << 4));
         }
@@ -330,19 +364,16 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
         if (e.sample_scale) {
+          const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
-          for (int j = 0; j < BOX_N; ++j) v[j] *= sc;
+          for (int j = 0; j < BOX_N / 2; ++j) v2[j] = mul2(v2[j], sc2);
         }
         if (aux == AUX_RESIDUAL) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&ax[k]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f = __bfloat1622float2(gp[i]);
-              v[k * 8 + 2 * i] += f.x;
-              v[k * 8 + 2 * i + 1] += f.y;
-            }
+            for (int i = 0; i < 4; ++i) v2[k * 4 + i] = add2(v2[k * 4 + i], __bfloat1622float2(gp[i]));
           }
         }
 #pragma unroll
@@ -351,14 +382,17 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                            pack_bf16(v[k * 8 + 4], v[k * 8 + 5]), pack_bf16(v[k * 8 + 6], v[k * 8 + 7])};
           *reinterpret_cast<uint4*>(sbase + r * 64 + ((k ^ sw) << 4)) = o;
         }
+        TL(2, 200 + c);
         tc::fence_proxy_async();
         named_bar_sync(1 + g, 128);
+        TL(2, 300 + c);
         if (leader) {
           tma_store_2d(&tmap_c, sbase, (int)ncol, (int)orow0);
           bulk_commit();
           bulk_wait_read<2>();  // the stores of boxes <= cnt-2 have drained: their slots may be refilled
           if (aux) request_aux();
         }
+        TL(2, 400 + c);
         ++cnt;
       }
     }
@@ -386,6 +420,9 @@ int make_box_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
   return r == CUDA_SUCCESS ? 0 : SVIT_EINVAL;
 }
 
+unsigned long long* g_timeline = nullptr;
+unsigned long long* svit_gemm_timeline_buffer() { return g_timeline; }
+
 template <int BN, bool B_MN>
 int launch(const svit_gemm_args* a, cudaStream_t st) {
   using L = Cfg<BN>;
@@ -405,6 +442,7 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
   e.act = a->act;
   e.aux = a->residual ? AUX_RESIDUAL : (a->gelu_pre ? AUX_GELU_PRE : AUX_NONE);
   e.rows_in = a->rows_in; e.rows_out = a->rows_out; e.row_off = a->row_off;
+  e.dbg = svit_gemm_timeline_buffer();
   tx = tcm;
   if (e.aux == AUX_RESIDUAL) rc = make_box_map(&tx, a->residual, out_rows, (uint64_t)a->N, (uint64_t)a->ldr);
   else if (e.aux == AUX_GELU_PRE) rc = make_box_map(&tx, a->gelu_pre, (uint64_t)a->M, (uint64_t)a->N, (uint64_t)a->ldg);
@@ -467,6 +505,13 @@ int svit_gemm_tc_tma_supported(const svit_gemm_args* a) {
   if (a->bias && !aligned16(a->bias)) return 0;
   if (a->M < BM) return 0;  // tiny problems (heads): the generic kernel is fine
   return 1;
+}
+
+// Diagnostic hook (not part of the public header): device buffer of 3 * 4096 * 2 uint64 that CTA 0 of the next
+// launches fills with (tag, clock64) events; pass NULL to switch the probe off.
+extern "C" int svit_debug_gemm_timeline(void* device_buffer) {
+  g_timeline = (unsigned long long*)device_buffer;
+  return 0;
 }
 
 int svit_gemm_tc_tma(const svit_gemm_args* a, cudaStream_t st) {
