@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libsvit_sm100.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("SVIT_NVCC_EXTRA", "").split()
 
 
 def _sources():

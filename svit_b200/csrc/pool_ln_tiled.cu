@@ -13,7 +13,9 @@
 //                             (batch, head) also emits the cls and object-token rows.
 //   pool_ln_direct_kernel     stride >= 4 (windows do not overlap) or unaligned input: taps straight from
 //                             global / L2.
-#include "common.cuh"
+#include <type_traits>
+
+#include "tc_common.cuh"
 
 namespace {
 
@@ -100,6 +102,11 @@ struct TileDims {
 
 // two fp32 FMAs per instruction (sm_100 FFMA2): acc = x * w + acc on both halves of a 64-bit register pair
 __device__ __forceinline__ void fma2(float2& acc, const float2 x, const float2 w) {
+#ifdef POOL_SCALAR_FMA
+  acc.x = fmaf(x.x, w.x, acc.x);
+  acc.y = fmaf(x.y, w.y, acc.y);
+  return;
+#endif
   unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
   const unsigned long long xx = *reinterpret_cast<const unsigned long long*>(&x);
   const unsigned long long ww = *reinterpret_cast<const unsigned long long*>(&w);
@@ -240,6 +247,240 @@ pool_ln_tiled_kernel(const bf16* __restrict__ in, Geom g, const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------ channel-pair
+// pool_ln_cp_kernel<S>: thread = (strip of SW consecutive outputs along W, one bf16x2 channel pair).  The 27 tap
+// weights of the pair live in registers for the whole CTA lifetime; the CTA marches over the T input planes and
+// every plane is read from shared memory exactly once per strip: its three input rows feed the accumulators of the
+// three output planes t-1, t, t+1 (three rotating register sets), so one LDS.32 + 2 conversions feed up to 27 FFMA2.
+// A finished output plane goes through an fp32 staging tile to the LayerNorm lanes (4 lanes per token, 24 channels
+// each).  384 threads = 8 strips x 48 pairs; input planes arrive through a 3-slot cp.async ring, two planes ahead.
+template <int S> struct CpCfg;
+template <> struct CpCfg<1> { static constexpr int ROWS = 4, TW = 14, SW = 7, IW = 16; };
+template <> struct CpCfg<2> { static constexpr int ROWS = 4, TW = 7, SW = 4, IW = 15; };  // strip 2 over-reads 2 tokens (masked output)
+constexpr int CP_THREADS = 384, CP_STRIPS = 8, CP_SLOTS = 3;
+constexpr int CP_PITCH = 50;  // staging token pitch in float2: conflict-free 16-byte reads by the LN lanes
+
+template <int S>
+struct CpDims {
+  using C = CpCfg<S>;
+  static constexpr int IH = (C::ROWS - 1) * S + 3, IW = C::IW;
+  static constexpr int XN = (C::SW - 1) * S + 3;
+  static constexpr int PLANE_BYTES = IH * IW * PD * 2;                  // one TMA box
+  static constexpr int SLOT_WORDS = ((PLANE_BYTES + 127) / 128) * 32;   // ring slots stay 128-byte aligned
+  static constexpr int NTOK = CP_STRIPS * C::SW;
+  static constexpr int OFF_STG = CP_SLOTS * SLOT_WORDS * 4;
+  static constexpr int OFF_TOK = OFF_STG + NTOK * CP_PITCH * 8;
+  static constexpr int OFF_AFF = OFF_TOK + ((NTOK * 8 + 15) & ~15);   // int64 token index per staged token
+  static constexpr int OFF_W = OFF_AFF + 3 * PD * 4;                   // gamma, beta, w_eff
+  static constexpr int OFF_BAR = OFF_W + TAPS * (PD / 2) * 8;          // tap weights as float2 [27][48]
+  static constexpr int SMEM = OFF_BAR + 64;                            // one mbarrier per ring slot
+};
+
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
+// LayerNorm + store of the first `ntok` staged tokens (pre-LN fp32, CP_PITCH float2 per token); four lanes per token.
+__device__ __forceinline__ void cp_ln_flush(const float2* stg, const long long* stg_tok, const float* aff, int ntok, float eps,
+                                            bf16* __restrict__ obase) {
+  const int tok = threadIdx.x >> 2, q = threadIdx.x & 3;
+  if ((threadIdx.x & ~31) >= ntok * 4) return;  // whole warp idle
+  const bool live = tok < ntok;
+  const float2* src = stg + (live ? tok : 0) * CP_PITCH + q * 12;
+  float2 x[12];
+#pragma unroll
+  for (int i = 0; i < 12; i += 2) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    x[i] = make_float2(v.x, v.y);
+    x[i + 1] = make_float2(v.z, v.w);
+  }
+  float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { s2.x += x[i].x; s2.y += x[i].y; }
+  float sum = s2.x + s2.y;
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  const float mean = sum * (1.f / PD);
+  float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    x[i].x -= mean; x[i].y -= mean;
+    q2.x = fmaf(x[i].x, x[i].x, q2.x);
+    q2.y = fmaf(x[i].y, x[i].y, q2.y);
+  }
+  float var = q2.x + q2.y;
+  var += __shfl_xor_sync(0xffffffffu, var, 1);
+  var += __shfl_xor_sync(0xffffffffu, var, 2);
+  const float rstd = rsqrtf(var * (1.f / PD) + eps);
+  const long long gtok = live ? stg_tok[tok] : -1;
+  if (gtok < 0) return;
+  const float* gm = aff + q * 24;
+  const float* bt = aff + PD + q * 24;
+  uint32_t o[12];
+#pragma unroll
+  for (int i = 0; i < 12; i += 2) {
+    const float4 g4 = *reinterpret_cast<const float4*>(gm + 2 * i);
+    const float4 b4 = *reinterpret_cast<const float4*>(bt + 2 * i);
+    o[i] = pack2(fmaf(x[i].x * rstd, g4.x, b4.x), fmaf(x[i].y * rstd, g4.y, b4.y));
+    o[i + 1] = pack2(fmaf(x[i + 1].x * rstd, g4.z, b4.z), fmaf(x[i + 1].y * rstd, g4.w, b4.w));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(obase + gtok * PD + q * 24);
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+}
+
+template <int S>
+__global__ void __launch_bounds__(CP_THREADS, 2)
+pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ in, Geom g, const float* __restrict__ w, const float* __restrict__ frac,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ out, float eps) {
+  using C = CpCfg<S>;
+  using D = CpDims<S>;
+  constexpr int IH = D::IH, IW = D::IW, XN = D::XN, SW = C::SW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem);
+  float2* stg = reinterpret_cast<float2*>(smem + D::OFF_STG);
+  long long* stg_tok = reinterpret_cast<long long*>(smem + D::OFF_TOK);
+  float* aff = reinterpret_cast<float*>(smem + D::OFF_AFF);  // gamma[96] | beta[96] | w_eff[96]
+  float2* sw2 = reinterpret_cast<float2*>(smem + D::OFF_W);  // [27][48]: tap weights of channel pair wd
+  const int tiles_w = (g.Wo + C::TW - 1) / C::TW;
+  const int tile = blockIdx.x;
+  const int wo0 = (tile % tiles_w) * C::TW, ho0 = (tile / tiles_w) * C::ROWS;
+  const int iw0 = wo0 * S - 1, ih0 = ho0 * S - 1;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const bf16* zin = in + (int64_t)b * g.in_bs + (int64_t)head * g.in_hs;
+  const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
+  const int64_t Nout = 1 + Lo + g.O;
+  bf16* obase = out + ((int64_t)b * g.h + head) * Nout * PD;
+
+  // one TMA box per plane: (96 channels of this head, IW tokens, IH rows) with zero fill outside the H x W grid
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + D::OFF_BAR);
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmap);
+    for (int i = 0; i < CP_SLOTS; ++i) tc::mbar_init(&full[i], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  auto load_plane = [&](int t) {  // thread 0 only
+    const int slot = t % CP_SLOTS;
+    tc::mbar_arrive_expect_tx(&full[slot], D::PLANE_BYTES);
+    tc::tma_load_5d(ring + slot * D::SLOT_WORDS, &tmap, &full[slot], head * PD, iw0, ih0, t, b);
+  };
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < 2 && t < g.T; ++t) load_plane(t);
+  }
+  for (int i = threadIdx.x; i < PD; i += CP_THREADS) {
+    aff[i] = gamma[i];
+    aff[PD + i] = beta[i];
+  }
+
+  const int strip = threadIdx.x / 48, wd = threadIdx.x - strip * 48;   // strip, channel-pair word
+  const int srow = strip >> 1, scol = (strip & 1) * SW;
+  const int ho = ho0 + srow;
+  for (int i = threadIdx.x; i < TAPS * 48; i += CP_THREADS) {
+    const int tp = i / 48, pr = i - tp * 48;
+    sw2[i] = make_float2(__ldg(w + (2 * pr) * TAPS + tp), __ldg(w + (2 * pr + 1) * TAPS + tp));
+  }
+  float2 acc[3][SW];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int o = 0; o < SW; ++o) acc[a][o] = make_float2(0.f, 0.f);
+
+  // stage output plane t (accumulator set a) for the LayerNorm lanes
+  auto stage_out = [&](float2 (&set)[SW], int t) {
+#pragma unroll
+    for (int o = 0; o < SW; ++o) {
+      stg[(strip * SW + o) * CP_PITCH + wd] = set[o];
+      set[o] = make_float2(0.f, 0.f);
+    }
+    if (wd < SW) {
+      const int o = wd, wo = wo0 + scol + o;
+      const bool ok = ho < g.Ho && scol + o < C::TW && wo < g.Wo;
+      stg_tok[strip * SW + o] = ok ? 1 + ((int64_t)t * g.Ho + ho) * g.Wo + wo : -1;
+    }
+  };
+
+  auto step = [&](auto rtag, int tp) {
+    constexpr int R = decltype(rtag)::value;  // tp % 3
+    __syncthreads();                                      // staging tile and ring slot (tp+2)%3 are free
+    if (threadIdx.x == 0 && tp + 2 < g.T) load_plane(tp + 2);
+    tc::mbar_wait_hot(&full[tp % CP_SLOTS], (tp / CP_SLOTS) & 1);  // plane tp has landed
+    const uint32_t* pl = ring + (tp % CP_SLOTS) * D::SLOT_WORDS;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const uint32_t* rowp = pl + ((srow * S + kh) * IW + scol * S) * 48 + wd;
+      float2 x[XN];
+#pragma unroll
+      for (int p = 0; p < XN; ++p) {
+        const uint32_t v = rowp[p * 48];
+        x[p] = make_float2(lo_f(v), hi_f(v));
+      }
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        const int t_out = tp + 1 - kt;
+        if (t_out < 0 || t_out >= g.T) continue;  // temporal zero padding (uniform)
+        constexpr int dummy = 0; (void)dummy;
+        float2 (&set)[SW] = acc[(R + 4 - kt) % 3];
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float2 wt = sw2[((kt * 3 + kh) * 3 + kw) * 48 + wd];
+#pragma unroll
+          for (int o = 0; o < SW; ++o) fma2(set[o], x[o * S + kw], wt);
+        }
+      }
+    }
+    if (tp >= 1) stage_out(acc[(R + 2) % 3], tp - 1);  // output plane tp-1 has now seen planes tp-2, tp-1, tp
+    __syncthreads();
+    if (tp >= 1) cp_ln_flush(stg, stg_tok, aff, D::NTOK, eps, obase);
+  };
+  for (int tp0 = 0; tp0 < g.T; tp0 += 3) {
+    step(std::integral_constant<int, 0>{}, tp0);
+    if (tp0 + 1 < g.T) step(std::integral_constant<int, 1>{}, tp0 + 1);
+    if (tp0 + 2 < g.T) step(std::integral_constant<int, 2>{}, tp0 + 2);
+  }
+  // last output plane T-1 (its t+1 neighbour is zero padding)
+  __syncthreads();
+  {
+    const int a = (g.T - 1) % 3;
+    if (a == 0) stage_out(acc[0], g.T - 1);
+    else if (a == 1) stage_out(acc[1], g.T - 1);
+    else stage_out(acc[2], g.T - 1);
+  }
+  __syncthreads();
+  cp_ln_flush(stg, stg_tok, aff, D::NTOK, eps, obase);
+  // cls + object tokens of this (batch, head): tile 0, through the same staging / LayerNorm path
+  if (tile == 0) {
+    float* sweff = aff + 2 * PD;
+    if (threadIdx.x < 48) {
+      float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int tp = 0; tp < TAPS; ++tp) {
+        const float f = __ldg(frac + tp);
+        a.x = fmaf(sw2[tp * 48 + wd].x, f, a.x);
+        a.y = fmaf(sw2[tp * 48 + wd].y, f, a.y);
+      }
+      sweff[2 * wd] = a.x;
+      sweff[2 * wd + 1] = a.y;
+    }
+    for (int base = 0; base < 1 + g.O; base += D::NTOK) {
+      __syncthreads();  // previous flush finished with the staging tile; w_eff visible
+      const int n = min(D::NTOK, 1 + g.O - base);
+      for (int i = threadIdx.x; i < n * 48; i += CP_THREADS) {
+        const int k = i / 48, ww = i - k * 48;
+        const int r = base + k;  // 0 = cls, r >= 1: object token r-1
+        const int64_t tok_in = r == 0 ? 0 : L + r;
+        const uint32_t v = reinterpret_cast<const uint32_t*>(zin + tok_in * g.in_ts)[ww];
+        const float sx = r == 0 ? 1.f : sweff[2 * ww], sy = r == 0 ? 1.f : sweff[2 * ww + 1];
+        stg[k * CP_PITCH + ww] = make_float2(lo_f(v) * sx, hi_f(v) * sy);
+        if (ww == 0) stg_tok[k] = r == 0 ? 0 : Lo + r;
+      }
+      __syncthreads();
+      cp_ln_flush(stg, stg_tok, aff, n, eps, obase);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ direct
 // One half-warp per output token.  mode 0: all tokens; mode 1: only cls + object tokens (companion of the tiled
 // kernel, which writes the patch tokens).
@@ -331,8 +572,45 @@ int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   g.Ho = (H - 1) / s + 1; g.Wo = (W - 1) / s + 1;
   g.in_bs = in_bs; g.in_ts = in_ts; g.in_hs = in_hs;
   const int sms = svit_num_sms();
-  const bool tiled = (s == 1 || s == 2) && (in_ts % 8 == 0) && (in_hs % 8 == 0) && (in_bs % 8 == 0) &&
-                     ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  const bool tiled = (s == 1 || s == 2) && (T <= 64) && (in_ts % 8 == 0) && (in_hs % 8 == 0) && (in_bs % 8 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (tiled && in_hs == PD && (T * H * W) > 0) {
+    // 5-D view of the patch tokens: (head*96 + c, w, h, t, b); the box of a CTA is (96, IW, IH, 1, 1)
+    svit_tmap_encode_fn enc = svit_get_tmap_encode();
+    if (!enc) return SVIT_ENOTSUP;
+    const int IWb = s == 1 ? CpDims<1>::IW : CpDims<2>::IW, IHb = s == 1 ? CpDims<1>::IH : CpDims<2>::IH;
+    CUtensorMap tm;
+    cuuint64_t dims[5] = {(cuuint64_t)h * PD, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)in_ts * 2, (cuuint64_t)W * in_ts * 2, (cuuint64_t)H * W * in_ts * 2, (cuuint64_t)in_bs * 2};
+    cuuint32_t box[5] = {PD, (cuuint32_t)IWb, (cuuint32_t)IHb, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const bf16* base = (const bf16*)in + in_ts;  // token 0 is the cls token
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return SVIT_EINVAL;
+    if (s == 1) {
+      using C = CpCfg<1>;
+      static bool configured = false;
+      if (!configured) {
+        SVIT_CUDA(cudaFuncSetAttribute(pool_ln_cp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CpDims<1>::SMEM));
+        configured = true;
+      }
+      dim3 grid((unsigned)(((g.Wo + C::TW - 1) / C::TW) * ((g.Ho + C::ROWS - 1) / C::ROWS)), (unsigned)h, (unsigned)B);
+      pool_ln_cp_kernel<1><<<grid, CP_THREADS, CpDims<1>::SMEM, st>>>(tm, (const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
+    } else {
+      using C = CpCfg<2>;
+      static bool configured = false;
+      if (!configured) {
+        SVIT_CUDA(cudaFuncSetAttribute(pool_ln_cp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CpDims<2>::SMEM));
+        configured = true;
+      }
+      dim3 grid((unsigned)(((g.Wo + C::TW - 1) / C::TW) * ((g.Ho + C::ROWS - 1) / C::ROWS)), (unsigned)h, (unsigned)B);
+      pool_ln_cp_kernel<2><<<grid, CP_THREADS, CpDims<2>::SMEM, st>>>(tm, (const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
+    }
+    SVIT_CHECK_LAUNCH();
+    return 0;
+  }
   if (tiled && s == 1) {
     using C = TileCfg<1>;
     static bool configured = false;
