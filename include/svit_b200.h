@@ -133,6 +133,11 @@ typedef struct svit_attn_args {
   const int32_t* idx_t;
   const int32_t* key_cols;
   int32_t ntab_h, ntab_w, ntab_t;
+  /* bias-in-MMA kernel (attn_tc3.cu), optional: sel_tab [ceil(Nk/64)*64, sel_cols] in the activation dtype, row n =
+   * key n: 1 in columns i'(n), kh + j'(n), kh + kw + t'(n) for patch keys, all zero for cls / object keys, and
+   * -1e30 in the last column for padding keys (n >= Nk).  sel_cols must be 32 and kh + kw + kt <= 31. */
+  const void* sel_tab;
+  int32_t sel_cols;
 } svit_attn_args;
 int svit_attn_fwd(const svit_attn_args* args, void* stream);
 int svit_attn_bwd(const svit_attn_args* args, void* stream);

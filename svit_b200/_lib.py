@@ -42,6 +42,7 @@ class AttnArgs(C.Structure):
         ("ws_e", vp), ("ws_de", vp), ("ws_delta", vp),
         ("rel_tab", vp), ("idx_h", vp), ("idx_w", vp), ("idx_t", vp), ("key_cols", vp),
         ("ntab_h", i32), ("ntab_w", i32), ("ntab_t", i32),
+        ("sel_tab", vp), ("sel_cols", i32),
     ]
 
 

@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(256) attn_fwd_simt_kernel(svit_attn_args a) {
 
 int svit_attn_fwd_tc(const svit_attn_args* a, cudaStream_t st);  // attn_tc.cu
 int svit_attn_tc_supported(const svit_attn_args* a);
+int svit_attn_fwd_tc3(const svit_attn_args* a, cudaStream_t st);  // attn_tc3.cu (bias inside the score MMA)
+int svit_attn_tc3_supported(const svit_attn_args* a);
 
 static int attn_check(const svit_attn_args* a) {
   if (!a || !a->q || !a->k || !a->v || !a->out || !a->rel_h || !a->rel_w || !a->rel_t) return SVIT_EINVAL;
@@ -176,9 +178,11 @@ extern "C" int svit_attn_fwd(const svit_attn_args* a, void* stream) {
   if (a->B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (a->impl == 2) {
+    if (svit_attn_tc3_supported(a)) return svit_attn_fwd_tc3(a, st);
     if (!svit_attn_tc_supported(a)) return SVIT_ENOTSUP;
     return svit_attn_fwd_tc(a, st);
   }
+  if (a->impl == 0 && svit_attn_tc3_supported(a)) return svit_attn_fwd_tc3(a, st);
   if (a->impl == 0 && svit_attn_tc_supported(a)) return svit_attn_fwd_tc(a, st);
   if (a->kh + a->kw + a->kt > MAXE) return SVIT_ENOTSUP;
   const int64_t Nq = 1 + (int64_t)a->qt * a->qh * a->qw + a->O;

@@ -89,6 +89,32 @@ def key_column_codes(k_shape, O, device) -> torch.Tensor:
     return _keycol_cache[key]
 
 
+_sel_cache = {}
+
+
+def key_select_table(k_shape, O, device, cols: int = 32) -> Optional[torch.Tensor]:
+    """bf16 [ceil(Nk / 64) * 64, cols] for the bias-in-MMA attention kernel: row n = key n selects the columns
+    i' | kh + j' | kh + kw + t' of the per-query bias vector E (attention.py:100-119, 156-163); cls / object keys
+    select nothing; padding keys carry -1e30 in the last column (E'[last] = 1).  None if the columns do not fit."""
+    kt, kh, kw = k_shape
+    ne = kh + kw + kt
+    if ne > cols - 1:
+        return None
+    key = (kt, kh, kw, O, cols, str(device))
+    if key not in _sel_cache:
+        Lk = kt * kh * kw
+        Nk = 1 + Lk + O
+        rows = (Nk + 63) // 64 * 64
+        sel = torch.zeros(rows, cols, dtype=torch.float32)
+        pidx = torch.arange(Lk)
+        sel[1 + pidx, pidx // kw % kh] = 1.0
+        sel[1 + pidx, kh + pidx % kw] = 1.0
+        sel[1 + pidx, kh + kw + pidx // (kw * kh)] = 1.0
+        sel[Nk:, cols - 1] = -1e30
+        _sel_cache[key] = sel.to(torch.bfloat16).to(device)
+    return _sel_cache[key]
+
+
 _idx32_cache = {}
 
 
@@ -218,7 +244,8 @@ class MultiScaleAttention(nn.Module):
                      (self.rel_pos_t, q_shape[0], k_shape[0]))]
             tc_tables = (torch.cat(tabs).to(torch.bfloat16).contiguous(), [t.shape[0] for t in tabs],
                          _index32_on(x.device, q_shape[1], k_shape[1]), _index32_on(x.device, q_shape[2], k_shape[2]),
-                         _index32_on(x.device, q_shape[0], k_shape[0]), key_column_codes(k_shape, O, x.device))
+                         _index32_on(x.device, q_shape[0], k_shape[0]), key_column_codes(k_shape, O, x.device),
+                         key_select_table(k_shape, O, x.device))
         o = ops.attention(q, k, v, Rh, Rw, Rt, q_shape, k_shape, O, self.scale, tc_tables)
         y = ops.linear(o, self.proj.weight, self.proj.bias, residual=residual, sample_scale=sample_scale)
         return y, q_shape

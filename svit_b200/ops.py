@@ -452,10 +452,13 @@ class _Attention(torch.autograd.Function):
         lse = torch.empty(B, h, Nq, dtype=torch.float32, device=q.device) if need else None
         a = _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale)
         if tc_tables is not None:
-            tab, ntabs, ih, iw, it, kc = tc_tables
+            tab, ntabs, ih, iw, it, kc = tc_tables[:6]
             a.rel_tab, a.idx_h, a.idx_w, a.idx_t, a.key_cols = (tab.data_ptr(), ih.data_ptr(), iw.data_ptr(),
                                                                 it.data_ptr(), kc.data_ptr())
             a.ntab_h, a.ntab_w, a.ntab_t = ntabs
+            sel = tc_tables[6] if len(tc_tables) > 6 else None
+            if sel is not None:  # bias-in-MMA kernel (attn_tc3.cu)
+                a.sel_tab, a.sel_cols = sel.data_ptr(), sel.shape[1]
         _call("svit_attn_fwd", C.byref(a), _stream(),
               tag=f"[B{B} h{h} Nq{Nq} Nk{k.shape[2]}]" if _prof is not None else None)
         if need:

@@ -146,7 +146,8 @@ def _attn_inputs(B, h, q_thw, k_thw, O, seed, rel_std=0.2):
     tabs = [r.to(torch.bfloat16) for r in rels]
     tc_tables = (torch.cat(tabs).contiguous(), [t.shape[0] for t in tabs],
                  msa._index32_on(q.device, q_thw[1], k_thw[1]), msa._index32_on(q.device, q_thw[2], k_thw[2]),
-                 msa._index32_on(q.device, q_thw[0], k_thw[0]), msa.key_column_codes(k_thw, O, q.device))
+                 msa._index32_on(q.device, q_thw[0], k_thw[0]), msa.key_column_codes(k_thw, O, q.device),
+                 msa.key_select_table(k_thw, O, q.device))
     return q, k, v, R, tc_tables
 
 
@@ -163,10 +164,17 @@ ATTN_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("bias_in_mma", [True, False])
 @pytest.mark.parametrize("shape", ATTN_SHAPES)
-def test_attention_tc_matches_simt(shape):
+def test_attention_tc_matches_simt(shape, bias_in_mma):
+    """bias_in_mma: the kernel of attn_tc3.cu (selection table present and kh + kw + kt <= 31), otherwise the
+    kernel of attn_tc.cu (bias added by the softmax warps)."""
     B, h, q_thw, k_thw, O = shape
     q, k, v, R, tc_tables = _attn_inputs(B, h, q_thw, k_thw, O, seed=31)
+    if bias_in_mma and tc_tables[6] is None:
+        pytest.skip("bias columns do not fit the 32-column selection table")
+    if not bias_in_mma:
+        tc_tables = tc_tables[:6]
     scale = 96 ** -0.5
     ops.set_impl(attn=ops.IMPL_SIMT)
     with torch.no_grad():
