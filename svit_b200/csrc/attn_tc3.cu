@@ -29,16 +29,18 @@ constexpr int BM = 128;   // query rows per CTA
 constexpr int BN = 64;    // keys per tile
 constexpr int HB = 32;    // score columns per softmax thread and tile
 constexpr int TP = 80;    // table rows per E pass
-constexpr int EK = 32;    // E' / Sel columns
+constexpr int EK = 32;    // E' / Sel columns of the first chunk (the last one is the mask column)
+constexpr int EK2 = 16;   // optional second chunk
 constexpr int HD = SVIT_HEAD_DIM;
 constexpr int NTHREADS = 320;
 constexpr int STG_PITCH = TP + 1;
 
 constexpr int OFF_Q0 = 0;                 // 128 rows x 128 B (columns 0..63, SW128)
 constexpr int OFF_Q1 = 16384;             // 128 rows x 64 B  (columns 64..95, SW64)
-constexpr int OFF_ET = 24576;             // 128 rows x 64 B  (E', SW64)
-constexpr int OFF_K = 32768;              // 2 stages x { K0 64 x 128 B | K1 64 x 64 B | Sel 64 x 64 B }
-constexpr int K_STAGE = 16384, K1_OFF = 8192, SEL_OFF = 12288;
+constexpr int OFF_ET = 24576;             // 128 rows x 64 B  (E' columns 0..31, SW64)
+constexpr int OFF_ET2 = 32768;            // 128 rows x 32 B  (E' columns 32..47, SW32; only when ne > 31)
+constexpr int OFF_K = 36864;              // 2 stages x { K0 64 x 128 B | K1 64 x 64 B | Sel 64 x 64 B | Sel2 64 x 32 B }
+constexpr int K_STAGE = 18432, K1_OFF = 8192, SEL_OFF = 12288, SEL2_OFF = 16384;
 constexpr int OFF_V = OFF_K + 2 * K_STAGE;  // 2 stages x (2 boxes x 64 rows x 128 B)
 constexpr int V_STAGE = 16384;
 constexpr int OFF_T = OFF_K;              // tables alias K/V: 2 boxes x 80 rows x 128 B
@@ -87,10 +89,24 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t smem_addr) {
   return d;
 }
 
+// K-major, 32-byte swizzle: rows of 32 B, 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(16 >> 4) << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
+
+// X16: the bias vector has more than 31 entries; entries 31.. live in a second 16-column chunk (one more K-step)
+template <bool X16>
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_constant__ CUtensorMap tmap_q1,
                     const __grid_constant__ CUtensorMap tmap_k0, const __grid_constant__ CUtensorMap tmap_k1,
-                    const __grid_constant__ CUtensorMap tmap_sel, const __grid_constant__ CUtensorMap tmap_v,
+                    const __grid_constant__ CUtensorMap tmap_sel, const __grid_constant__ CUtensorMap tmap_sel2,
+                    const __grid_constant__ CUtensorMap tmap_v,
                     const __grid_constant__ CUtensorMap tmap_t, Params p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -105,6 +121,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_q0); tc::prefetch_tmap(&tmap_q1); tc::prefetch_tmap(&tmap_k0); tc::prefetch_tmap(&tmap_k1);
     tc::prefetch_tmap(&tmap_sel); tc::prefetch_tmap(&tmap_v); tc::prefetch_tmap(&tmap_t);
+    if (X16) tc::prefetch_tmap(&tmap_sel2);
     for (int i = 0; i < NUM_BARS; ++i) {
       const bool eight = (i == BAR_E_EMPTY || i == BAR_E_READY || i == BAR_P_FULL0 || i == BAR_P_FULL1);
       tc::mbar_init(&bars[i], eight ? 8 : 1);
@@ -135,10 +152,11 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
         const int n0 = j * BN;
         tc::mbar_wait(&bars[BAR_K_EMPTY0 + ks], ((j >> 1) & 1) ^ 1);
         unsigned char* kd = smem + OFF_K + ks * K_STAGE;
-        tc::mbar_arrive_expect_tx(&bars[BAR_K_FULL0 + ks], K_STAGE);
+        tc::mbar_arrive_expect_tx(&bars[BAR_K_FULL0 + ks], X16 ? K_STAGE : SEL2_OFF);
         tc::tma_load_3d(kd, &tmap_k0, &bars[BAR_K_FULL0 + ks], 0, n0, bh);
         tc::tma_load_3d(kd + K1_OFF, &tmap_k1, &bars[BAR_K_FULL0 + ks], 64, n0, bh);
         tc::tma_load_2d(kd + SEL_OFF, &tmap_sel, &bars[BAR_K_FULL0 + ks], 0, n0);
+        if (X16) tc::tma_load_2d(kd + SEL2_OFF, &tmap_sel2, &bars[BAR_K_FULL0 + ks], EK, n0);
         tc::mbar_wait(&bars[BAR_V_EMPTY0 + ks], ((j >> 1) & 1) ^ 1);
         unsigned char* vd = smem + OFF_V + ks * V_STAGE;
         tc::mbar_arrive_expect_tx(&bars[BAR_V_FULL0 + ks], V_STAGE);
@@ -153,6 +171,8 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       constexpr uint32_t idesc_s = tc::idesc_bf16(BM, BN, 0, 0);
       constexpr uint32_t idesc_o = tc::idesc_bf16(BM, HD, 0, 1);
       const uint32_t sq0 = tc::smem_u32(smem + OFF_Q0), sq1 = tc::smem_u32(smem + OFF_Q1), se = tc::smem_u32(smem + OFF_ET);
+      const uint32_t se2 = tc::smem_u32(smem + OFF_ET2);
+      (void)se2;
       tc::mbar_wait(&bars[BAR_Q_FULL], 0);
       for (int ps = 0; ps < p.n_pass; ++ps) {
         tc::mbar_wait(&bars[BAR_T_FULL], ps & 1);
@@ -187,6 +207,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             tc::umma_bf16_ss(d, smem_desc_sw64(se + k * 32), smem_desc_sw64(sk + SEL_OFF + k * 32), idesc_s, 1u);
+          if (X16) tc::umma_bf16_ss(d, smem_desc_sw32(se2), smem_desc_sw32(sk + SEL2_OFF), idesc_s, 1u);
           tc::umma_commit(&bars[BAR_K_EMPTY0 + ks]);
           tc::umma_commit(&bars[BAR_S_FULL0 + (j & 1)]);
         }
@@ -215,8 +236,10 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
     const int pair_bar = 1 + qd;
     const bool qpatch = row >= 1 && row <= p.Lq;
-    // ---- phase E: this thread owns E' columns [16 half, 16 half + 16) of its row
-    int g[16];
+    // ---- phase E: this thread owns E' columns [16 half, 16 half + 16) of the first chunk (column 31 = mask) and, with
+    // X16, columns [8 half, 8 half + 8) of the second; bias entry e sits in column e (e < 31) or 32 + (e - 31)
+    constexpr int NG = X16 ? 24 : 16;
+    int g[NG];
     {
       int qi = 0, qj = 0, qt_ = 0;
       if (qpatch) {
@@ -224,19 +247,19 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
         qj = pp % p.qw; qi = (pp / p.qw) % p.qh; qt_ = pp / (p.qw * p.qh);
       }
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int c = half * 16 + u;
+      for (int u = 0; u < NG; ++u) {
+        const int c = u < 16 ? half * 16 + u : (EK - 1) + half * 8 + (u - 16);  // bias entry
         g[u] = -1;
-        if (qpatch) {
+        if (qpatch && !(u < 16 && c == EK - 1)) {
           if (c < p.kh) g[u] = __ldg(p.idx_h + qi * p.kh + c);
           else if (c < p.kh + p.kw) g[u] = p.off_w + __ldg(p.idx_w + qj * p.kw + (c - p.kh));
           else if (c < p.ne) g[u] = p.off_t + __ldg(p.idx_t + qt_ * p.kt + (c - p.kh - p.kw));
         }
       }
     }
-    float ev[16];
+    float ev[NG];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) ev[u] = 0.f;
+    for (int u = 0; u < NG; ++u) ev[u] = 0.f;
     float* stg = reinterpret_cast<float*>(smem + OFF_STG) + rl * STG_PITCH;
     for (int ps = 0; ps < p.n_pass; ++ps) {
       tc::mbar_wait_hot(&bars[BAR_E_FULL], ps & 1);
@@ -254,7 +277,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       named_bar_sync(pair_bar, 64);  // the staged row is complete
       const int lo = ps * TP;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+      for (int u = 0; u < NG; ++u) {
         const int gg = g[u] - lo;
         if (g[u] >= 0 && gg >= 0 && gg < TP) ev[u] = stg[gg];
       }
@@ -264,7 +287,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
     }
     {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) ev[u] *= p.inv_scale;
+      for (int u = 0; u < NG; ++u) ev[u] *= p.inv_scale;
       if (half == 1) ev[15] = 1.0f;  // column 31: multiplies the mask row of Sel (every query row, patch or not)
       const uint32_t sw = (uint32_t)((rl >> 1) & 3);
       unsigned char* erow = smem + OFF_ET + rl * 64;
@@ -272,6 +295,11 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       const uint4 hi4 = {pack2(ev[8], ev[9]), pack2(ev[10], ev[11]), pack2(ev[12], ev[13]), pack2(ev[14], ev[15])};
       *reinterpret_cast<uint4*>(erow + (((uint32_t)(half * 2) ^ sw) << 4)) = lo4;
       *reinterpret_cast<uint4*>(erow + (((uint32_t)(half * 2 + 1) ^ sw) << 4)) = hi4;
+      if (X16) {
+        const uint4 x4 = {pack2(ev[NG - 8], ev[NG - 7]), pack2(ev[NG - 6], ev[NG - 5]), pack2(ev[NG - 4], ev[NG - 3]),
+                          pack2(ev[NG - 2], ev[NG - 1])};
+        *reinterpret_cast<uint4*>(smem + OFF_ET2 + rl * 32 + (((uint32_t)half ^ (uint32_t)((rl >> 2) & 1)) << 4)) = x4;
+      }
       tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       tc::fence_before_sync();
       __syncwarp();
@@ -429,13 +457,28 @@ int make_map32(CUtensorMap* m, const void* ptr, int rank, uint64_t d2, uint64_t 
   return r == CUDA_SUCCESS ? 0 : SVIT_EINVAL;
 }
 
+// 16-column box, 32-byte swizzle (second chunk of the Sel table)
+int make_map16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  svit_tmap_encode_fn enc = svit_get_tmap_encode();
+  if (!enc) return SVIT_ENOTSUP;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {16, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : SVIT_EINVAL;
+}
+
 }  // namespace
 
-// Requires the Sel table (a->sel_tab, 32 columns) and all kh + kw + kt bias columns to fit next to the mask column.
+// Requires the Sel table (a->sel_tab): 32 columns for kh + kw + kt <= 31, 48 columns for up to 47 bias entries.
 int svit_attn_tc3_supported(const svit_attn_args* a) {
   if (a->dtype != SVIT_BF16) return 0;
-  if (!a->rel_tab || !a->idx_h || !a->idx_w || !a->idx_t || !a->sel_tab || a->sel_cols != EK) return 0;
-  if (a->kh + a->kw + a->kt > EK - 1) return 0;
+  if (!a->rel_tab || !a->idx_h || !a->idx_w || !a->idx_t || !a->sel_tab) return 0;
+  const int ne = a->kh + a->kw + a->kt;
+  if (!((a->sel_cols == EK && ne <= EK - 1) || (a->sel_cols == EK + EK2 && ne <= EK - 1 + EK2))) return 0;
   if (!aligned16(a->q) || !aligned16(a->k) || !aligned16(a->v) || !aligned16(a->out) || !aligned16(a->rel_tab) ||
       !aligned16(a->sel_tab))
     return 0;
@@ -459,22 +502,27 @@ int svit_attn_fwd_tc3(const svit_attn_args* a, cudaStream_t st) {
   p.idx_h = a->idx_h; p.idx_w = a->idx_w; p.idx_t = a->idx_t;
   p.out = (bf16*)a->out; p.lse = a->lse;
   const uint64_t BH = (uint64_t)a->B * a->h;
-  CUtensorMap tq0, tq1, tk0, tk1, tsel, tv, tt;
+  CUtensorMap tq0, tq1, tk0, tk1, tsel, tsel2, tv, tt;
+  const bool x16 = a->sel_cols == EK + EK2;
   int rc;
   if ((rc = svit_make_tmap_3d(&tq0, a->q, BH, p.Nq, HD, HD, (uint64_t)p.Nq * HD, BM))) return rc;
   if ((rc = make_map32(&tq1, a->q, 3, BH, p.Nq, HD, HD, (uint64_t)p.Nq * HD, BM))) return rc;
   if ((rc = svit_make_tmap_3d(&tk0, a->k, BH, p.Nk, HD, HD, (uint64_t)p.Nk * HD, BN))) return rc;
   if ((rc = make_map32(&tk1, a->k, 3, BH, p.Nk, HD, HD, (uint64_t)p.Nk * HD, BN))) return rc;
-  if ((rc = make_map32(&tsel, a->sel_tab, 2, 1, (uint64_t)p.n_tiles * BN, EK, EK, 0, BN))) return rc;
+  if ((rc = make_map32(&tsel, a->sel_tab, 2, 1, (uint64_t)p.n_tiles * BN, (uint64_t)a->sel_cols, (uint64_t)a->sel_cols, 0, BN))) return rc;
+  tsel2 = tsel;
+  if (x16 && (rc = make_map16(&tsel2, a->sel_tab, (uint64_t)p.n_tiles * BN, (uint64_t)a->sel_cols, BN))) return rc;
   if ((rc = svit_make_tmap_3d(&tv, a->v, BH, p.Nk, HD, HD, (uint64_t)p.Nk * HD, BN))) return rc;
   if ((rc = svit_make_tmap_2d(&tt, a->rel_tab, p.ntab, HD, HD, TP))) return rc;
   dim3 grid((unsigned)((p.Nq + BM - 1) / BM), (unsigned)BH);
   static bool configured = false;
   if (!configured) {
-    SVIT_CUDA(cudaFuncSetAttribute(attn_fwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    SVIT_CUDA(cudaFuncSetAttribute(attn_fwd_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    SVIT_CUDA(cudaFuncSetAttribute(attn_fwd_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     configured = true;
   }
-  attn_fwd_tc3_kernel<<<grid, NTHREADS, SMEM_TOTAL, st>>>(tq0, tq1, tk0, tk1, tsel, tv, tt, p);
+  if (x16) attn_fwd_tc3_kernel<true><<<grid, NTHREADS, SMEM_TOTAL, st>>>(tq0, tq1, tk0, tk1, tsel, tsel2, tv, tt, p);
+  else attn_fwd_tc3_kernel<false><<<grid, NTHREADS, SMEM_TOTAL, st>>>(tq0, tq1, tk0, tk1, tsel, tsel2, tv, tt, p);
   SVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -92,25 +92,28 @@ def key_column_codes(k_shape, O, device) -> torch.Tensor:
 _sel_cache = {}
 
 
-def key_select_table(k_shape, O, device, cols: int = 32) -> Optional[torch.Tensor]:
-    """bf16 [ceil(Nk / 64) * 64, cols] for the bias-in-MMA attention kernel: row n = key n selects the columns
-    i' | kh + j' | kh + kw + t' of the per-query bias vector E (attention.py:100-119, 156-163); cls / object keys
-    select nothing; padding keys carry -1e30 in the last column (E'[last] = 1).  None if the columns do not fit."""
+def key_select_table(k_shape, O, device) -> Optional[torch.Tensor]:
+    """bf16 [ceil(Nk / 64) * 64, 32 or 48] for the bias-in-MMA attention kernel: row n = key n selects the entries
+    i' | kh + j' | kh + kw + t' of the per-query bias vector E (attention.py:100-119, 156-163); entry e lives in
+    column e (e < 31) or 32 + (e - 31); cls / object keys select nothing; padding keys carry -1e30 in column 31
+    (E'[31] = 1).  None if kh + kw + kt > 47."""
     kt, kh, kw = k_shape
     ne = kh + kw + kt
-    if ne > cols - 1:
+    if ne > 47:
         return None
-    key = (kt, kh, kw, O, cols, str(device))
+    cols = 32 if ne <= 31 else 48
+    key = (kt, kh, kw, O, str(device))
     if key not in _sel_cache:
         Lk = kt * kh * kw
         Nk = 1 + Lk + O
         rows = (Nk + 63) // 64 * 64
         sel = torch.zeros(rows, cols, dtype=torch.float32)
         pidx = torch.arange(Lk)
-        sel[1 + pidx, pidx // kw % kh] = 1.0
-        sel[1 + pidx, kh + pidx % kw] = 1.0
-        sel[1 + pidx, kh + kw + pidx // (kw * kh)] = 1.0
-        sel[Nk:, cols - 1] = -1e30
+        col = lambda e: torch.where(e < 31, e, e + 1)
+        sel[1 + pidx, col(pidx // kw % kh)] = 1.0
+        sel[1 + pidx, col(kh + pidx % kw)] = 1.0
+        sel[1 + pidx, col(kh + kw + pidx // (kw * kh))] = 1.0
+        sel[Nk:, 31] = -1e30
         _sel_cache[key] = sel.to(torch.bfloat16).to(device)
     return _sel_cache[key]
 
