@@ -54,6 +54,8 @@ struct Params {
   unsigned long long* dbg;  // optional timeline buffer (CTA (0,0) only)
 };
 
+// timeline probe (build with SVIT_NVCC_EXTRA=-DSVIT_TIMELINE; tools/attn_timeline.py)
+#ifdef SVIT_TIMELINE
 #define TL(role, tag)                                                                 \
   do {                                                                                \
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tl_n < 4096) {                 \
@@ -62,6 +64,9 @@ struct Params {
       ++tl_n;                                                                         \
     }                                                                                 \
   } while (0)
+#else
+#define TL(role, tag) do { (void)tl_n; } while (0)
+#endif
 
 enum {  // barrier slots
   BAR_Q_FULL = 0, BAR_T_FULL, BAR_E_FULL, BAR_E_EMPTY, BAR_K_FULL0, BAR_K_FULL1, BAR_K_EMPTY0, BAR_K_EMPTY1,

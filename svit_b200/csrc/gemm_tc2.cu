@@ -3,17 +3,17 @@
 // MN-major A).  Same contract (svit_gemm_args):
 //   C[M,N] = residual + sample_scale[row/rps] * ( act(A.op(B) + bias) * gelu'(gelu_pre) )
 //
-// Persistent, warp-specialised, one CTA per SM (320 threads):
+// Persistent, warp-specialised, one CTA per SM (320 or 448 threads):
 //   warp 0     TMA producer: ring of {A 128x64, B BNx64} bf16 tiles, 128-byte swizzle, OOB zero fill
 //   warp 1     MMA issuer (one lane): tcgen05.mma 128 x BN x 16, fp32 accumulators double-buffered in TMEM
-//   warps 2-9  epilogue, two groups of four warps (one warp per TMEM lane quarter, thread = accumulator row).
-//              A group takes alternate 32-column boxes of the tile: tcgen05.ld (32 columns) -> bias / GELU /
+//   warps 2..   epilogue, two or three groups of four warps (one warp per TMEM lane quarter, thread = accumulator row).
+//              A group takes every third 32-column box of the tile: tcgen05.ld (32 columns) -> bias / GELU /
 //              gelu' / DropPath scale / residual in registers -> bf16 -> 64-byte-swizzled staging slot -> one
 //              TMA store per box (cp.async.bulk.tensor, clipped at the tensor edge).  The residual (or gelu_pre)
 //              box is TMA-loaded INTO the staging slot two boxes ahead by the group's leader thread and combined
 //              in place, so every global access of the epilogue is a bulk tensor copy.
-// Ring of 4 staging slots per group: a slot is rewritten only after the store that read it has drained
-// (cp.async.bulk.wait_group.read 2 by the leader, published by the group's named barrier).
+// Ring of SPG staging slots per group: a slot is rewritten only after the store that read it has drained
+// (cp.async.bulk.wait_group.read SPG-2 by the leader, published by the group's named barrier).
 #include "tc_common.cuh"
 #include "../../include/svit_b200.h"
 
@@ -21,22 +21,24 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int NUM_THREADS = 320;
-constexpr int EPI_WARPS = 8;
+// Epilogue shape G = groups of four warps (one warp per TMEM lane quarter): G = 3 with 3 staging slots per group
+// for epilogue-heavy problems (GELU, short K), G = 2 with 4 slots (one more operand stage) otherwise.
+constexpr int spg_of(int G) { return G == 3 ? 3 : 4; }
+constexpr int threads_of(int G) { return 64 + 128 * G; }
 constexpr int BOX_N = 32;                 // columns per epilogue box
 constexpr int SLOT_BYTES = BM * BOX_N * 2;  // 8 KB
-constexpr int SPG = 4;                    // staging slots per epilogue group
 constexpr int PF_DIST = 2;                // aux boxes requested ahead
 constexpr int SMEM_LIMIT = 232448;        // 227 KB
 
 enum { AUX_NONE = 0, AUX_RESIDUAL = 1, AUX_GELU_PRE = 2 };
 
-template <int BN>
+template <int BN, int G>
 struct Cfg {
+  static constexpr int SPG = spg_of(G);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = 2 * SPG * SLOT_BYTES;
+  static constexpr int STG_BYTES = G * SPG * SLOT_BYTES;
   static constexpr int FIXED = STG_BYTES + 512 + 1024;  // staging + barriers + alignment slack
   static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -114,16 +116,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // Static schedule of one epilogue group's boxes: tiles blockIdx.x, +gridDim.x, ...; inside a tile the boxes
 // c = g, g+2, ... that start left of N.
 struct BoxIter {
-  int64_t t, num_tiles, n_tiles, N;
-  int c, g, BN;
-  __device__ BoxIter(int64_t t0, int64_t num_tiles_, int64_t n_tiles_, int64_t N_, int g_, int BN_)
-      : t(t0), num_tiles(num_tiles_), n_tiles(n_tiles_), N(N_), c(g_), g(g_), BN(BN_) {
+  int t, num_tiles, n_tiles, N;
+  int c, g, BN, G;
+  __device__ BoxIter(int t0, int num_tiles_, int n_tiles_, int N_, int g_, int BN_, int G_)
+      : t(t0), num_tiles(num_tiles_), n_tiles(n_tiles_), N(N_), c(g_), g(g_), BN(BN_), G(G_) {
     settle();
   }
   __device__ int nbox() const {
-    const int64_t n0 = (t % n_tiles) * BN;
-    const int64_t rem = N - n0 < BN ? N - n0 : BN;
-    return (int)((rem + BOX_N - 1) / BOX_N);
+    const int n0 = (t % n_tiles) * BN;
+    const int rem = N - n0 < BN ? N - n0 : BN;
+    return (rem + BOX_N - 1) / BOX_N;
   }
   __device__ void settle() {
     while (t < num_tiles && c >= nbox()) {
@@ -133,12 +135,14 @@ struct BoxIter {
   }
   __device__ bool valid() const { return t < num_tiles; }
   __device__ void next() {
-    c += 2;
+    c += G;
     settle();
   }
 };
 
-// timeline probe: role 0 producer, 1 MMA, 2 epilogue group-0 leader lane; 4096 events per role
+// timeline probe (build with SVIT_NVCC_EXTRA=-DSVIT_TIMELINE; tools/gemm_timeline.py): role 0 producer, 1 MMA,
+// 2 epilogue group-0 leader lane; 4096 events per role
+#ifdef SVIT_TIMELINE
 #define TL(role, tag)                                                            \
   do {                                                                           \
     if (e.dbg && blockIdx.x == 0 && tl_n < 4096) {                               \
@@ -147,18 +151,25 @@ struct BoxIter {
       ++tl_n;                                                                    \
     }                                                                            \
   } while (0)
+#else
+#define TL(role, tag) do { (void)tl_n; } while (0)
+#endif
 
-__device__ __forceinline__ int64_t remap_row(const Epi& e, int64_t m) {
-  return e.rows_in > 0 ? (m / e.rows_in) * e.rows_out + e.row_off + (m % e.rows_in) : m;
+__device__ __forceinline__ int remap_row(const Epi& e, int m) {  // all row counts are < 2^31 (svit_gemm_tc_supported)
+  if (e.rows_in <= 0) return m;
+  const int ri = (int)e.rows_in, q = m / ri;
+  return q * (int)e.rows_out + (int)e.row_off + (m - q * ri);
 }
 
-template <int BN, bool B_MN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, bool B_MN, int G>
+__global__ void __launch_bounds__(threads_of(G), 1)
 gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_x, int64_t M,
-                   int64_t N, int64_t K, Epi e) {
-  using L = Cfg<BN>;
+                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_x, int M,
+                   int N, int K, Epi e) {
+  using L = Cfg<BN, G>;
   constexpr int STAGES = L::STAGES;
+  constexpr int SPG = L::SPG;
+  constexpr int EPI_WARPS = 4 * G;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment by pointer offset (not an integer round trip) so accesses stay in the shared state space
   unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -167,13 +178,13 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* aux_full = tmem_empty + 2;  // [2 * SPG]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_full + 2 * SPG);
+  uint64_t* aux_full = tmem_empty + 2;  // [G * SPG]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_full + G * SPG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
-  const int64_t num_tiles = m_tiles * n_tiles;
-  const int num_kb = (int)((K + BK - 1) / BK);
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a);
@@ -188,7 +199,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tc::mbar_init(&tmem_full[i], 1);
       tc::mbar_init(&tmem_empty[i], EPI_WARPS);
     }
-    for (int i = 0; i < 2 * SPG; ++i) tc::mbar_init(&aux_full[i], 1);
+    for (int i = 0; i < G * SPG; ++i) tc::mbar_init(&aux_full[i], 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, L::TMEM_COLS);
@@ -203,8 +214,8 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int tl_n = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (int)((t / n_tiles) * BM), n0 = (int)((t % n_tiles) * BN);
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           TL(0, kb);
@@ -230,7 +241,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       uint32_t phase = 0;
       int it = 0;
       int tl_n = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         tc::mbar_wait_hot(&tmem_empty[as], acc_phase ^ 1);
@@ -258,7 +269,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int g = (warp - 2) >> 2;     // epilogue group: boxes c with c % 2 == g
+    const int g = (warp - 2) >> 2;     // epilogue group: boxes c with c % G == g
     const int r = q * 32 + lane;       // accumulator row inside the tile
     const bool leader = (warp - 2) == g * 4 && lane == 0;
     unsigned char* my_slots = stg_base + g * SPG * SLOT_BYTES;
@@ -267,15 +278,15 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int aux = e.aux;
 
     // leader: request the first PF_DIST aux boxes
-    BoxIter pf(blockIdx.x, num_tiles, n_tiles, N, g, BN);
+    BoxIter pf(blockIdx.x, num_tiles, n_tiles, N, g, BN, G);
     uint32_t pf_cnt = 0;
     auto request_aux = [&]() {
       if (!pf.valid()) return;
-      const int64_t m0 = (pf.t / n_tiles) * BM, n0 = (pf.t % n_tiles) * BN;
-      const int64_t row0 = aux == AUX_RESIDUAL ? remap_row(e, m0) : m0;
+      const int m0 = (pf.t / n_tiles) * BM, n0 = (pf.t % n_tiles) * BN;
+      const int row0 = aux == AUX_RESIDUAL ? remap_row(e, m0) : m0;
       const int slot = pf_cnt % SPG;
       tc::mbar_arrive_expect_tx(&my_aux[slot], SLOT_BYTES);
-      tc::tma_load_2d(my_slots + slot * SLOT_BYTES, &tmap_x, &my_aux[slot], (int)(n0 + pf.c * BOX_N), (int)row0);
+      tc::tma_load_2d(my_slots + slot * SLOT_BYTES, &tmap_x, &my_aux[slot], n0 + pf.c * BOX_N, row0);
       ++pf_cnt;
       pf.next();
     };
@@ -287,20 +298,20 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     int it = 0;
     int tl_n = leader ? 0 : 4096;
     if (g != 0) tl_n = 4096;
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-      const int64_t rem = N - n0 < BN ? N - n0 : BN;
-      const int nbox = (int)((rem + BOX_N - 1) / BOX_N);
-      const int64_t orow0 = remap_row(e, m0);
+      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      const int rem = N - n0 < BN ? N - n0 : BN;
+      const int nbox = (rem + BOX_N - 1) / BOX_N;
+      const int orow0 = remap_row(e, m0);
       float sc = 1.f;
       if (e.sample_scale) {
-        const int64_t m = m0 + r < M ? m0 + r : M - 1;
-        sc = e.sample_scale[m / e.rps];
+        const int m = m0 + r < M ? m0 + r : M - 1;
+        sc = e.sample_scale[m / (int)e.rps];
       }
       int last_c = -1;
-      for (int c = g; c < nbox; c += 2) last_c = c;
+      for (int c = g; c < nbox; c += G) last_c = c;
       TL(2, 2000);
       tc::mbar_wait_hot(&tmem_full[as], acc_phase);
       tc::fence_after_sync();
@@ -312,12 +323,12 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
       }
 #pragma unroll 1
-      for (int c = g; c < nbox; c += 2) {
+      for (int c = g; c < nbox; c += G) {
         const int slot = cnt % SPG;
         unsigned char* sbase = my_slots + slot * SLOT_BYTES;
         float v[BOX_N];
         tc::tmem_ld32(taddr + c * BOX_N, v);
-        const int64_t ncol = n0 + c * BOX_N;
+        const int ncol = n0 + c * BOX_N;
         // bias (L1-resident broadcast loads) while the TMEM load is in flight
         float bv[BOX_N];
         if (e.bias) {
@@ -387,9 +398,9 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         named_bar_sync(1 + g, 128);
         TL(2, 300 + c);
         if (leader) {
-          tma_store_2d(&tmap_c, sbase, (int)ncol, (int)orow0);
+          tma_store_2d(&tmap_c, sbase, ncol, orow0);
           bulk_commit();
-          bulk_wait_read<2>();  // the stores of boxes <= cnt-2 have drained: their slots may be refilled
+          bulk_wait_read<SPG - 2>();  // the stores of boxes <= cnt - (SPG - 2) have drained: their slots may be refilled
           if (aux) request_aux();
         }
         TL(2, 400 + c);
@@ -423,9 +434,9 @@ int make_box_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
 unsigned long long* g_timeline = nullptr;
 unsigned long long* svit_gemm_timeline_buffer() { return g_timeline; }
 
-template <int BN, bool B_MN>
-int launch(const svit_gemm_args* a, cudaStream_t st) {
-  using L = Cfg<BN>;
+template <int BN, bool B_MN, int G>
+int launch_g(const svit_gemm_args* a, cudaStream_t st) {
+  using L = Cfg<BN, G>;
   static_assert(L::STAGES >= 2, "pipeline too shallow");
   static_assert(L::TOTAL <= SMEM_LIMIT, "shared memory budget");
   CUtensorMap ta, tb, tcm, tx;
@@ -447,7 +458,7 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
   if (e.aux == AUX_RESIDUAL) rc = make_box_map(&tx, a->residual, out_rows, (uint64_t)a->N, (uint64_t)a->ldr);
   else if (e.aux == AUX_GELU_PRE) rc = make_box_map(&tx, a->gelu_pre, (uint64_t)a->M, (uint64_t)a->N, (uint64_t)a->ldg);
   if (rc) return rc;
-  auto kern = gemm_tc_tma_kernel<BN, B_MN>;
+  auto kern = gemm_tc_tma_kernel<BN, B_MN, G>;
   static bool configured = false;
   if (!configured) {
     SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -455,9 +466,16 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
   }
   const int64_t tiles = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN);
   const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
-  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ta, tb, tcm, tx, a->M, a->N, a->K, e);
+  kern<<<grid, threads_of(G), L::TOTAL, st>>>(ta, tb, tcm, tx, (int)a->M, (int)a->N, (int)a->K, e);
   SVIT_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN, bool B_MN>
+int launch(const svit_gemm_args* a, cudaStream_t st) {
+  // three epilogue groups when the epilogue dominates: GELU / gelu' math, or few K-steps per tile
+  if (a->act == 1 || a->gelu_pre || a->K <= 256) return launch_g<BN, B_MN, 3>(a, st);
+  return launch_g<BN, B_MN, 2>(a, st);
 }
 
 // tile width: the widest of {256, 192, 128, 96, 64} that divides N, else the one wasting the fewest MMA columns
