@@ -178,9 +178,13 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel breakdown here")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: configs[1] (the headline metric); train: configs[2], fwd + bwd + gradient all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "train":
+        return run_train(args)
 
     import torch.distributed as dist
 
@@ -338,6 +342,79 @@ def main():
         with open(args.profile_json, "w") as f:
             json.dump(prof, f, indent=1)
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train(args):
+    """configs[2]: full training step (forward + backward, bf16 activations, fp32 parameter gradients) with batch 8
+    clips per GPU sharded over the ranks and one bucketed NCCL gradient all-reduce per step (no optimizer: the
+    optimizer is outside the hot path)."""
+    import torch.distributed as dist
+
+    import svit_b200
+    from svit_b200 import ops
+    from svit_b200.config import ssv2_cfg
+    from svit_b200.distributed import GradAllReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K = max(3, args.warmup), args.steps
+    B = 8 if args.batch == 64 else args.batch
+    cfg = ssv2_cfg()
+    torch.manual_seed(0)
+    model = svit_b200.SViT(cfg, compute_dtype=torch.bfloat16).to(dev).train()
+    reducer = GradAllReducer(model.parameters()) if world > 1 else None
+    gen = torch.Generator().manual_seed(1234 + rank)
+    clips = [torch.randn(B, 3, 16, 224, 224, generator=gen).to(torch.bfloat16).to(dev) for _ in range(2)]
+    labels = torch.randint(0, cfg.MODEL.NUM_CLASSES, (B,), generator=gen).to(dev)
+
+    def step(i):
+        for p in model.parameters():
+            p.grad = None
+        if reducer is not None:
+            reducer.prepare()
+        preds, extra = model([clips[i & 1]])
+        loss = torch.nn.functional.cross_entropy(extra["logits"].float(), labels)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    barrier()
+    l0 = ops.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        line = {"metric": "clips/sec (16x224^2, bf16) SViT training step (fwd+bwd+grad all-reduce)",
+                "value": world * B * K / (ms / 1e3), "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "gpu_launches": ops.launches() - l0, "loss": float(loss),
+                "config": {"workload": f"SViT (configs/ssv2.yaml) training step, batch {B} clips per GPU, random init, "
+                                       "cross-entropy on the class logits, no optimizer step",
+                           "parallelism": f"dp{world}", "global_batch": B * world}}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

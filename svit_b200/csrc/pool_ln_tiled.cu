@@ -280,7 +280,28 @@ __device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
   return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
-// LayerNorm + store of the first `ntok` staged tokens (pre-LN fp32, CP_PITCH float2 per token); four lanes per token.
+// packed fp32x2 helpers (FADD2 / FMUL2 / FFMA2)
+__device__ __forceinline__ float2 padd2(const float2 a, const float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 pmul2(const float2 a, const float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 pfma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<const unsigned long long*>(&b)), "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+
+// LayerNorm + store of the first `ntok` staged tokens (pre-LN fp32, CP_PITCH float2 per token); four lanes per token,
+// 24 channels per lane, packed fp32x2 arithmetic.
 __device__ __forceinline__ void cp_ln_flush(const float2* stg, const long long* stg_tok, const float* aff, int ntok, float eps,
                                             bf16* __restrict__ obase) {
   const int tok = threadIdx.x >> 2, q = threadIdx.x & 3;
@@ -294,19 +315,19 @@ __device__ __forceinline__ void cp_ln_flush(const float2* stg, const long long* 
     x[i] = make_float2(v.x, v.y);
     x[i + 1] = make_float2(v.z, v.w);
   }
-  float2 s2 = make_float2(0.f, 0.f);
+  float2 s2 = padd2(x[0], x[1]);
 #pragma unroll
-  for (int i = 0; i < 12; ++i) { s2.x += x[i].x; s2.y += x[i].y; }
+  for (int i = 2; i < 12; ++i) s2 = padd2(s2, x[i]);
   float sum = s2.x + s2.y;
   sum += __shfl_xor_sync(0xffffffffu, sum, 1);
   sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-  const float mean = sum * (1.f / PD);
+  const float nmean = sum * (-1.f / PD);
+  const float2 nm2 = make_float2(nmean, nmean);
   float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
-    x[i].x -= mean; x[i].y -= mean;
-    q2.x = fmaf(x[i].x, x[i].x, q2.x);
-    q2.y = fmaf(x[i].y, x[i].y, q2.y);
+    x[i] = padd2(x[i], nm2);
+    q2 = pfma2(x[i], x[i], q2);
   }
   float var = q2.x + q2.y;
   var += __shfl_xor_sync(0xffffffffu, var, 1);
@@ -314,21 +335,37 @@ __device__ __forceinline__ void cp_ln_flush(const float2* stg, const long long* 
   const float rstd = rsqrtf(var * (1.f / PD) + eps);
   const long long gtok = live ? stg_tok[tok] : -1;
   if (gtok < 0) return;
-  const float* gm = aff + q * 24;
-  const float* bt = aff + PD + q * 24;
+  const float2 r2 = make_float2(rstd, rstd);
+  const float4* gm = reinterpret_cast<const float4*>(aff + q * 24);
+  const float4* bt = reinterpret_cast<const float4*>(aff + PD + q * 24);
   uint32_t o[12];
 #pragma unroll
   for (int i = 0; i < 12; i += 2) {
-    const float4 g4 = *reinterpret_cast<const float4*>(gm + 2 * i);
-    const float4 b4 = *reinterpret_cast<const float4*>(bt + 2 * i);
-    o[i] = pack2(fmaf(x[i].x * rstd, g4.x, b4.x), fmaf(x[i].y * rstd, g4.y, b4.y));
-    o[i + 1] = pack2(fmaf(x[i + 1].x * rstd, g4.z, b4.z), fmaf(x[i + 1].y * rstd, g4.w, b4.w));
+    const float4 g4 = gm[i >> 1], b4 = bt[i >> 1];
+    const float2 y0 = pfma2(pmul2(x[i], r2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+    const float2 y1 = pfma2(pmul2(x[i + 1], r2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+    o[i] = pack2(y0.x, y0.y);
+    o[i + 1] = pack2(y1.x, y1.y);
   }
   uint4* dst = reinterpret_cast<uint4*>(obase + gtok * PD + q * 24);
   dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
   dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
   dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
 }
+
+#ifdef SVIT_TIMELINE
+__device__ unsigned long long* g_pool_dbg = nullptr;
+#define PTL(tag)                                                              \
+  do {                                                                        \
+    if (g_pool_dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && tl_n < 1024) { \
+      g_pool_dbg[tl_n * 2] = (unsigned long long)(tag);                       \
+      g_pool_dbg[tl_n * 2 + 1] = (unsigned long long)clock64();               \
+      ++tl_n;                                                                 \
+    }                                                                         \
+  } while (0)
+#else
+#define PTL(tag) do { } while (0)
+#endif
 
 template <int S>
 __global__ void __launch_bounds__(CP_THREADS, 2)
@@ -401,11 +438,16 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
     }
   };
 
+  int tl_n = 0;
+  (void)tl_n;
   auto step = [&](auto rtag, int tp) {
     constexpr int R = decltype(rtag)::value;  // tp % 3
-    __syncthreads();                                      // staging tile and ring slot (tp+2)%3 are free
+    PTL(100 + tp);
+    __syncthreads();
+    PTL(200 + tp);                                      // staging tile and ring slot (tp+2)%3 are free
     if (threadIdx.x == 0 && tp + 2 < g.T) load_plane(tp + 2);
     tc::mbar_wait_hot(&full[tp % CP_SLOTS], (tp / CP_SLOTS) & 1);  // plane tp has landed
+    PTL(300 + tp);
     const uint32_t* pl = ring + (tp % CP_SLOTS) * D::SLOT_WORDS;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
@@ -430,9 +472,12 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
         }
       }
     }
+    PTL(400 + tp);
     if (tp >= 1) stage_out(acc[(R + 2) % 3], tp - 1);  // output plane tp-1 has now seen planes tp-2, tp-1, tp
     __syncthreads();
+    PTL(500 + tp);
     if (tp >= 1) cp_ln_flush(stg, stg_tok, aff, D::NTOK, eps, obase);
+    PTL(600 + tp);
   };
   for (int tp0 = 0; tp0 < g.T; tp0 += 3) {
     step(std::integral_constant<int, 0>{}, tp0);
@@ -562,6 +607,13 @@ pool_ln_direct_kernel(const bf16* __restrict__ in, Geom g, const float* __restri
 }
 
 }  // namespace
+
+#ifdef SVIT_TIMELINE
+extern "C" int svit_debug_pool_timeline(void* device_buffer) {
+  unsigned long long* p = (unsigned long long*)device_buffer;
+  return (int)cudaMemcpyToSymbol(g_pool_dbg, &p, sizeof(p));
+}
+#endif
 
 // bf16 fast path of svit_pool_ln_fwd (pool_ln.cu dispatches here).  Requires 4-byte aligned token slices.
 int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const float* conv_w,
