@@ -119,6 +119,46 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
   }
 }
 
+// bf16, N % 8 == 0: 16-byte loads, thread = 8 columns x a stripe of rows; shared-memory reduce over the row groups,
+// one atomicAdd per column and CTA
+__global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t M,
+                                                            int N, int64_t ld, int64_t rows_per_cta) {
+  __shared__ float red[256 * 8];
+  const int n8 = N >> 3;
+  const int tpr = n8 < 256 ? n8 : 256;          // threads across a row
+  const int rg = 256 / tpr;                      // row groups
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+  for (int c8 = blockIdx.x * tpr + tx; c8 < n8; c8 += gridDim.x * tpr) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ty < rg) {
+#pragma unroll 4
+      for (int64_t r = r0 + ty; r < r1; r += rg) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * ld + c8 * 8));
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[2 * u] += __uint_as_float(wv[u] << 16);
+          acc[2 * u + 1] += __uint_as_float(wv[u] & 0xffff0000u);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) red[threadIdx.x * 8 + u] = acc[u];
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float sum = 0.f;
+        for (int g = 0; g < rg; ++g) sum += red[(g * tpr + tx) * 8 + u];
+        atomicAdd(&out[c8 * 8 + u], sum);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st);  // gemm_tc.cu
 int svit_gemm_tc_supported(const svit_gemm_args* a);
 
@@ -156,6 +196,16 @@ int svit_colsum(const void* x, float* out, int64_t M, int N, int64_t ld, int dty
   if (M < 0 || N < 0) return SVIT_EINVAL;
   if (M == 0 || N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SVIT_BF16 && N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int n8 = N / 8, tpr = n8 < 256 ? n8 : 256;
+    const unsigned gx = (unsigned)((n8 + tpr - 1) / tpr);
+    int64_t rows = ceil_div64(M, ceil_div64((int64_t)svit_num_sms() * 4, gx));  // ~4 CTAs per SM
+    if (rows < 64) rows = 64;
+    dim3 grid8(gx, (unsigned)ceil_div64(M, rows));
+    colsum_bf16x8_kernel<<<grid8, 256, 0, st>>>((const bf16*)x, out, M, N, ld, rows);
+    SVIT_CHECK_LAUNCH();
+    return 0;
+  }
   int64_t rows_per_cta = 512;
   dim3 grid((unsigned)((N + 127) / 128), (unsigned)ceil_div64(M, rows_per_cta));
   if (dtype == SVIT_F32)

@@ -51,6 +51,7 @@ struct EpiArgs {
   void* C;
   int64_t ldc;
   int out_f32;
+  int splits;  // split-K: > 1 -> fp32 partial sums are accumulated with atomics into a zeroed C
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -157,8 +158,13 @@ __device__ __forceinline__ void store_chunk(const EpiArgs& e, const unsigned cha
     }
     if (e.out_f32) {
       float* dst = reinterpret_cast<float*>(e.C) + orow[it] * e.ldc + n;
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      if (e.splits > 1) {
+        atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+        atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
     } else {
       uint4 o = {pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])};
       *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.C) + orow[it] * e.ldc + n) = o;
@@ -183,8 +189,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
-  const int64_t num_tiles = m_tiles * n_tiles;
-  const int num_kb = (int)((K + BK - 1) / BK);
+  const int64_t out_tiles = m_tiles * n_tiles;
+  const int64_t num_tiles = out_tiles * e.splits;           // work item = (K split, output tile)
+  const int num_kb_all = (int)((K + BK - 1) / BK);
+  const int kb_per = (num_kb_all + e.splits - 1) / e.splits;  // K blocks per split
   constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
 
   if (warp == 0 && lane == 0) {
@@ -211,9 +219,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < num_tiles; w += gridDim.x) {
+        const int64_t t = w % out_tiles;
+        const int kb0 = (int)(w / out_tiles) * kb_per;
+        const int kb1 = kb0 + kb_per < num_kb_all ? kb0 + kb_per : num_kb_all;
         const int m0 = (int)((t / n_tiles) * BM), n0 = (int)((t % n_tiles) * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * L::STAGE_BYTES;
           unsigned char* sb = sa + L::A_BYTES;
@@ -241,13 +252,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int64_t w = blockIdx.x; w < num_tiles; w += gridDim.x, ++it) {
+        const int kb0 = (int)(w / out_tiles) * kb_per;
+        const int kb1 = kb0 + kb_per < num_kb_all ? kb0 + kb_per : num_kb_all;
         const int as = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         tc::mbar_wait_hot(&tmem_empty[as], acc_phase ^ 1);
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait_hot(&full_bar[stage], phase);
           tc::fence_after_sync();
           const uint32_t sa = tc::smem_u32(smem + stage * L::STAGE_BYTES);
@@ -256,10 +269,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? tc::smem_desc_sw128(sa + k * 2048, 8192, 1024) : tc::smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? tc::smem_desc_sw128(sb + k * 2048, 8192, 1024) : tc::smem_desc_sw128(sb + k * 32, 16, 1024);
-            tc::umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc::umma_bf16_ss(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           tc::umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
-          if (kb == num_kb - 1) tc::umma_commit(&tmem_full[as]);
+          if (kb == kb1 - 1) tc::umma_commit(&tmem_full[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -273,7 +286,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int LAST_CH0 = ((NCH - 1) & 1) == 0 ? NCH - 1 : NCH - 2;  // last chunk index handled by half 0
     constexpr int LAST_CH1 = ((NCH - 1) & 1) == 1 ? NCH - 1 : NCH - 2;
     int it = 0;
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int64_t w = blockIdx.x; w < num_tiles; w += gridDim.x, ++it) {
+      const int64_t t = w % out_tiles;
       const int as = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
@@ -332,13 +346,30 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
   e.rows_in = a->rows_in; e.rows_out = a->rows_out; e.row_off = a->row_off;
   e.C = a->C; e.ldc = a->ldc;
   e.out_f32 = a->out_dtype == SVIT_F32;
+  // split-K for the weight-gradient shape (few output tiles, very long reduction): fp32 partials via atomics
+  e.splits = 1;
+  {
+    const int64_t tiles0 = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN);
+    const int64_t nkb = (a->K + BK - 1) / BK;
+    const bool plain = e.out_f32 && !a->bias && !a->residual && !a->gelu_pre && !a->pre_out && !a->sample_scale &&
+                       a->act == 0 && a->rows_in == 0 && a->ldc == a->N;
+    if (plain && tiles0 * 2 <= svit_num_sms() && nkb >= 16) {
+      int64_t sp = svit_num_sms() / tiles0;
+      if (sp > nkb / 4) sp = nkb / 4;
+      if (sp > 1) {
+        const int64_t per = (nkb + sp - 1) / sp;
+        e.splits = (int)((nkb + per - 1) / per);  // no empty split
+        SVIT_CUDA(cudaMemsetAsync(a->C, 0, (size_t)a->M * a->N * sizeof(float), st));
+      }
+    }
+  }
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
     SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  const int64_t tiles = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN);
+  const int64_t tiles = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN) * e.splits;
   const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
   kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ta, tb, a->M, a->N, a->K, e);
   SVIT_CHECK_LAUNCH();

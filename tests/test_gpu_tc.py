@@ -113,6 +113,28 @@ def test_gemm_tc_tma_epilogues(M, N, K, mode):
     assert max_rel_err(cpu(out), cpu(ref)) < 6e-3, (M, N, K, mode)
 
 
+@pytest.mark.parametrize("M,N", [(5000, 384), (201224, 96), (13064, 1536), (300, 2304), (77, 8)])
+def test_colsum_bf16(M, N):
+    gen = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, N, generator=gen).to(torch.bfloat16).to(DEV)
+    got = ops._colsum(x, M, N)
+    ref = x.double().sum(0)
+    assert (cpu(got).double() - ref.cpu()).abs().max() / ref.abs().max().clamp_min(1.0) < 1e-4
+
+
+@pytest.mark.parametrize("Mo,No,Kr", [(96, 384, 201224), (384, 1536, 13064), (1536, 384, 13064), (96, 448, 200704), (192, 768, 50696)])
+def test_gemm_tc_wgrad_split_k(Mo, No, Kr):
+    """Weight-gradient shape dW[Mo, No] = G[Kr, Mo]^T X[Kr, No] (fp32 out, both operands MN-major): few output tiles and a
+    very long reduction -> split-K with fp32 atomics."""
+    gen = torch.Generator().manual_seed(Mo + No)
+    G = (torch.randn(Kr, Mo, generator=gen) * 0.1).to(torch.bfloat16).to(DEV)
+    X = torch.randn(Kr, No, generator=gen).to(torch.bfloat16).to(DEV)
+    out = torch.full((Mo, No), float("nan"), dtype=torch.float32, device=DEV)
+    ops.gemm(G, X, out, Mo, No, Kr, Mo, No, No, 1, 0, impl=TC)
+    ref = G.float().t().double() @ X.float().double()
+    assert max_rel_err(cpu(out), ref.float().cpu()) < 2e-4
+
+
 def test_gemm_tc_matches_simt_on_model_shapes():
     """Every forward GEMM shape of configs/ssv2.yaml (M = tokens of one clip)."""
     gen = torch.Generator().manual_seed(29)
