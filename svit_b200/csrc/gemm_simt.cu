@@ -162,7 +162,33 @@ __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restri
 int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st);  // gemm_tc.cu
 int svit_gemm_tc_supported(const svit_gemm_args* a);
 
+// Skinny fp32 linear y = x W^T + b with few outputs (the SViTHead projections, video_model_builder.py:529-538):
+// CTA per input row, the row staged in shared memory, one warp per output column (coalesced W rows, shuffle reduce).
+__global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int N,
+                                                            int K, int64_t lda, int64_t ldb, int64_t ldc) {
+  extern __shared__ float xs[];
+  const int64_t m = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) xs[k] = x[m * lda + k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int n = warp; n < N; n += 8) {
+    const float* wr = w + (int64_t)n * ldb;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(xs[k], __ldg(wr + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[m * ldc + n] = acc + (bias ? bias[n] : 0.f);
+  }
+}
+
 static int gemm_simt(const svit_gemm_args* a, cudaStream_t st) {
+  if (a->dtype == SVIT_F32 && a->out_dtype == SVIT_F32 && !a->transA && a->transB && !a->residual && !a->gelu_pre &&
+      !a->pre_out && !a->sample_scale && a->act == 0 && a->rows_in == 0 && a->M * a->N <= 65536 && a->K <= 8192) {
+    linear_skinny_kernel<<<(unsigned)a->M, 256, (size_t)a->K * 4, st>>>((const float*)a->A, (const float*)a->B, a->bias,
+                                                                        (float*)a->C, (int)a->N, (int)a->K, a->lda, a->ldb, a->ldc);
+    SVIT_CHECK_LAUNCH();
+    return 0;
+  }
   dim3 grid((unsigned)ceil_div64(a->N, BN), (unsigned)ceil_div64(a->M, BM));
   if (a->dtype == SVIT_F32 && a->out_dtype == SVIT_F32)
     gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>(*a);
