@@ -488,9 +488,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-unsigned long long* g_attn_timeline = nullptr;
-
 }  // namespace
+
+unsigned long long* g_attn_timeline = nullptr;  // shared with attn_tc3.cu
 
 // Diagnostic hook (not part of the public header): see tools/attn_timeline.py
 extern "C" int svit_debug_attn_timeline(void* device_buffer) {

@@ -23,6 +23,8 @@
 #include "tc_common.cuh"
 #include "../../include/svit_b200.h"
 
+extern unsigned long long* g_attn_timeline;  // attn_tc.cu (diagnostic hook)
+
 namespace {
 
 constexpr int BM = 128;   // query rows per CTA
@@ -33,7 +35,6 @@ constexpr int EK = 32;    // E' / Sel columns of the first chunk (the last one i
 constexpr int EK2 = 16;   // optional second chunk
 constexpr int HD = SVIT_HEAD_DIM;
 constexpr int NTHREADS = 320;
-constexpr int STG_PITCH = TP + 1;
 
 constexpr int OFF_Q0 = 0;                 // 128 rows x 128 B (columns 0..63, SW128)
 constexpr int OFF_Q1 = 16384;             // 128 rows x 64 B  (columns 64..95, SW64)
@@ -41,18 +42,22 @@ constexpr int OFF_ET = 24576;             // 128 rows x 64 B  (E' columns 0..31,
 constexpr int OFF_ET2 = 32768;            // 128 rows x 32 B  (E' columns 32..47, SW32; only when ne > 31)
 constexpr int OFF_K = 36864;              // 2 stages x { K0 64 x 128 B | K1 64 x 64 B | Sel 64 x 64 B | Sel2 64 x 32 B }
 constexpr int K_STAGE = 18432, K1_OFF = 8192, SEL_OFF = 12288, SEL2_OFF = 16384;
-constexpr int OFF_V = OFF_K + 2 * K_STAGE;  // 2 stages x (2 boxes x 64 rows x 128 B)
-constexpr int V_STAGE = 16384;
-constexpr int OFF_T = OFF_K;              // tables alias K/V: 2 boxes x 80 rows x 128 B
-constexpr int OFF_STG = OFF_K;            // gather staging aliases K/V: 128 rows x 81 fp32; never live with the tables
-constexpr int OFF_X = OFF_V + 2 * V_STAGE;  // row max / row sum exchange [2][2][128] fp32
+constexpr int V_STAGE = 16384;            // 2 boxes x 64 rows x 128 B
+constexpr int OFF_V1 = OFF_K + 2 * K_STAGE;   // V stage 1 sits next to K stage 1: together they are the alias region
+constexpr int OFF_V0 = OFF_V1 + V_STAGE;      // V stage 0
+constexpr int OFF_ALIAS = OFF_K + K_STAGE;    // K stage 1 + V stage 1 = 34816 B: rel-pos tables, then gather staging
+constexpr int OFF_T = OFF_ALIAS;          // tables: 2 boxes x 80 rows x 128 B
+constexpr int OFF_STG = OFF_ALIAS;        // gather staging: 128 rows x 49 fp32 (one 48-column half of a table pass)
+constexpr int STG_COLS = 48, STG_PITCH = STG_COLS + 1;
+constexpr int OFF_X = OFF_V0 + V_STAGE;  // row max / row sum exchange [2][2][128] fp32
 constexpr int OFF_BAR = OFF_X + 4 * BM * 4;
 constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
 constexpr int TMEM_COLS = 256;
 constexpr int COL_S0 = 0, COL_O = 128;
-static_assert(BM * STG_PITCH * 4 <= 2 * K_STAGE + 2 * V_STAGE, "gather staging must fit the K/V ring");
+static_assert(BM * STG_PITCH * 4 <= K_STAGE + V_STAGE && 2 * TP * 128 <= K_STAGE + V_STAGE, "alias region too small");
 
 struct Params {
+  unsigned long long* dbg;
   int h, qh, qw, kh, kw, kt, O;
   int Nq, Nk, Lq, ne;
   int ntab, off_w, off_t, n_pass, n_tiles;
@@ -64,6 +69,20 @@ struct Params {
   bf16* out;
   float* lse;
 };
+
+// timeline probe (build with SVIT_NVCC_EXTRA=-DSVIT_TIMELINE; tools/attn_timeline.py)
+#ifdef SVIT_TIMELINE
+#define TL(role, tag)                                                                 \
+  do {                                                                                \
+    if (p.dbg && blockIdx.x == 1 && blockIdx.y == 0 && tl_n < 4096) {                 \
+      p.dbg[((role) * 4096 + tl_n) * 2] = (unsigned long long)(tag);                  \
+      p.dbg[((role) * 4096 + tl_n) * 2 + 1] = (unsigned long long)clock64();          \
+      ++tl_n;                                                                         \
+    }                                                                                 \
+  } while (0)
+#else
+#define TL(role, tag) do { (void)tl_n; } while (0)
+#endif
 
 enum {  // barrier slots
   BAR_Q_FULL = 0, BAR_T_FULL, BAR_E_FULL, BAR_E_EMPTY, BAR_E_READY, BAR_K_FULL0, BAR_K_FULL1, BAR_K_EMPTY0, BAR_K_EMPTY1,
@@ -137,20 +156,16 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
+      int tl_n = 0;
+      TL(0, 9000);
       tc::mbar_arrive_expect_tx(&bars[BAR_Q_FULL], 16384 + 8192);
       tc::tma_load_3d(smem + OFF_Q0, &tmap_q0, &bars[BAR_Q_FULL], 0, r0, bh);
       tc::tma_load_3d(smem + OFF_Q1, &tmap_q1, &bars[BAR_Q_FULL], 64, r0, bh);
-      for (int ps = 0; ps < p.n_pass; ++ps) {
-        if (ps > 0) tc::mbar_wait(&bars[BAR_E_EMPTY], (ps - 1) & 1);
-        tc::mbar_arrive_expect_tx(&bars[BAR_T_FULL], 2 * TP * 128);
-        tc::tma_load_2d(smem + OFF_T, &tmap_t, &bars[BAR_T_FULL], 0, ps * TP);
-        tc::tma_load_2d(smem + OFF_T + TP * 128, &tmap_t, &bars[BAR_T_FULL], 64, ps * TP);
-      }
-      tc::mbar_wait(&bars[BAR_E_EMPTY], (p.n_pass - 1) & 1);  // tables + staging alias the K/V buffers
-      for (int j = 0; j < p.n_tiles; ++j) {
+      auto load_kv = [&](int j) {
         const int ks = j & 1;
         const int n0 = j * BN;
         tc::mbar_wait(&bars[BAR_K_EMPTY0 + ks], ((j >> 1) & 1) ^ 1);
+        TL(0, 100 + j);
         unsigned char* kd = smem + OFF_K + ks * K_STAGE;
         tc::mbar_arrive_expect_tx(&bars[BAR_K_FULL0 + ks], X16 ? K_STAGE : SEL2_OFF);
         tc::tma_load_3d(kd, &tmap_k0, &bars[BAR_K_FULL0 + ks], 0, n0, bh);
@@ -158,11 +173,23 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
         tc::tma_load_2d(kd + SEL_OFF, &tmap_sel, &bars[BAR_K_FULL0 + ks], 0, n0);
         if (X16) tc::tma_load_2d(kd + SEL2_OFF, &tmap_sel2, &bars[BAR_K_FULL0 + ks], EK, n0);
         tc::mbar_wait(&bars[BAR_V_EMPTY0 + ks], ((j >> 1) & 1) ^ 1);
-        unsigned char* vd = smem + OFF_V + ks * V_STAGE;
+        unsigned char* vd = smem + (ks ? OFF_V1 : OFF_V0);
         tc::mbar_arrive_expect_tx(&bars[BAR_V_FULL0 + ks], V_STAGE);
         tc::tma_load_3d(vd, &tmap_v, &bars[BAR_V_FULL0 + ks], 0, n0, bh);
         tc::tma_load_3d(vd + 8192, &tmap_v, &bars[BAR_V_FULL0 + ks], 64, n0, bh);
+      };
+      tc::mbar_arrive_expect_tx(&bars[BAR_T_FULL], 2 * TP * 128);
+      tc::tma_load_2d(smem + OFF_T, &tmap_t, &bars[BAR_T_FULL], 0, 0);
+      tc::tma_load_2d(smem + OFF_T + TP * 128, &tmap_t, &bars[BAR_T_FULL], 64, 0);
+      load_kv(0);  // stage 0 is not part of the alias region: the first key tile arrives during phase E
+      for (int ps = 1; ps < p.n_pass; ++ps) {
+        tc::mbar_wait(&bars[BAR_E_EMPTY], (ps - 1) & 1);
+        tc::mbar_arrive_expect_tx(&bars[BAR_T_FULL], 2 * TP * 128);
+        tc::tma_load_2d(smem + OFF_T, &tmap_t, &bars[BAR_T_FULL], 0, ps * TP);
+        tc::tma_load_2d(smem + OFF_T + TP * 128, &tmap_t, &bars[BAR_T_FULL], 64, ps * TP);
       }
+      tc::mbar_wait(&bars[BAR_E_EMPTY], (p.n_pass - 1) & 1);  // tables + staging alias stage 1 of the K/V ring
+      for (int j = 1; j < p.n_tiles; ++j) load_kv(j);
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -173,7 +200,9 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       const uint32_t sq0 = tc::smem_u32(smem + OFF_Q0), sq1 = tc::smem_u32(smem + OFF_Q1), se = tc::smem_u32(smem + OFF_ET);
       const uint32_t se2 = tc::smem_u32(smem + OFF_ET2);
       (void)se2;
+      int tl_n = 0;
       tc::mbar_wait(&bars[BAR_Q_FULL], 0);
+      TL(1, 9001);
       for (int ps = 0; ps < p.n_pass; ++ps) {
         tc::mbar_wait(&bars[BAR_T_FULL], ps & 1);
         tc::fence_after_sync();
@@ -190,11 +219,13 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       }
       tc::mbar_wait(&bars[BAR_E_READY], 0);  // E' tile written; E_tab columns are about to become S0/S1
       tc::fence_after_sync();
+      TL(1, 9002);
       for (int j = 0; j <= p.n_tiles; ++j) {
         if (j < p.n_tiles) {
           const int ks = j & 1;
           tc::mbar_wait(&bars[BAR_K_FULL0 + ks], (j >> 1) & 1);
           tc::fence_after_sync();
+          TL(1, 100 + j);
           const uint32_t sk = tc::smem_u32(smem + OFF_K + ks * K_STAGE);
           const uint32_t d = tmem_base + COL_S0 + (j & 1) * BN;
 #pragma unroll
@@ -214,9 +245,11 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
         if (j >= 1) {
           const int i = j - 1;
           tc::mbar_wait(&bars[BAR_P_FULL0 + (i & 1)], (i >> 1) & 1);
+          TL(1, 200 + i);
           tc::mbar_wait(&bars[BAR_V_FULL0 + (i & 1)], (i >> 1) & 1);
           tc::fence_after_sync();
-          const uint32_t sv = tc::smem_u32(smem + OFF_V + (i & 1) * V_STAGE);
+          TL(1, 300 + i);
+          const uint32_t sv = tc::smem_u32(smem + ((i & 1) ? OFF_V1 : OFF_V0));
 #pragma unroll
           for (int k = 0; k < BN / 16; ++k) {
             const uint64_t db = tc::smem_desc_sw128(sv + k * 2048, 8192, 1024);
@@ -236,6 +269,8 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
     const int pair_bar = 1 + qd;
     const bool qpatch = row >= 1 && row <= p.Lq;
+    int tl_n = (warp == 2 && lane == 0) ? 0 : 4096;
+    TL(2, 9000);
     // ---- phase E: this thread owns E' columns [16 half, 16 half + 16) of the first chunk (column 31 = mask) and, with
     // X16, columns [8 half, 8 half + 8) of the second; bias entry e sits in column e (e < 31) or 32 + (e - 31)
     constexpr int NG = X16 ? 24 : 16;
@@ -264,22 +299,26 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
     for (int ps = 0; ps < p.n_pass; ++ps) {
       tc::mbar_wait_hot(&bars[BAR_E_FULL], ps & 1);
       tc::fence_after_sync();
-#pragma unroll
-      for (int c0 = 0; c0 < TP; c0 += 16) {
-        if (((c0 >> 4) & 1) == half) {  // warp-uniform: alternate 16-column chunks
-          float v[16];
-          tc::tmem_ld16(lane_addr + COL_S0 + c0, v);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) stg[c0 + i] = v[i];
-        }
-      }
-      named_bar_sync(pair_bar, 64);  // the staged row is complete
       const int lo = ps * TP;
 #pragma unroll
-      for (int u = 0; u < NG; ++u) {
-        const int gg = g[u] - lo;
-        if (g[u] >= 0 && gg >= 0 && gg < TP) ev[u] = stg[gg];
+      for (int hb = 0; hb < TP; hb += STG_COLS) {  // the 80 columns of a pass are staged 48 + 32 at a time
+        if (hb > 0) named_bar_sync(pair_bar, 64);  // both warps are done with the previous half
+#pragma unroll
+        for (int c0 = hb; c0 < TP && c0 < hb + STG_COLS; c0 += 16) {
+          if (((c0 >> 4) & 1) == half) {  // warp-uniform: alternate 16-column chunks
+            float v[16];
+            tc::tmem_ld16(lane_addr + COL_S0 + c0, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) stg[c0 - hb + i] = v[i];
+          }
+        }
+        named_bar_sync(pair_bar, 64);  // the staged half row is complete
+#pragma unroll
+        for (int u = 0; u < NG; ++u) {
+          const int gg = g[u] - lo - hb;
+          if (g[u] >= 0 && gg >= 0 && gg < STG_COLS && gg + hb < TP) ev[u] = stg[gg];
+        }
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -308,13 +347,16 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
     // ---- phase S: online softmax over the key tiles; the accumulator already holds (s + bias / scale)
     float m_ref = -INFINITY, l = 0.f;
     const float2 c1c1 = make_float2(p.c1, p.c1);
+    TL(2, 9001);
     for (int j = 0; j < p.n_tiles; ++j) {
       const int sb = j & 1;
       tc::mbar_wait_hot(&bars[BAR_S_FULL0 + sb], (j >> 1) & 1);
       tc::fence_after_sync();
+      TL(2, 100 + j);
       float y[HB];
       tc::tmem_ld32(lane_addr + COL_S0 + sb * BN + half * HB, y);
       tc::tmem_ld_wait();
+      TL(2, 200 + j);
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent max chains
 #pragma unroll
       for (int c = 0; c < HB; c += 4) {
@@ -327,14 +369,15 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       xch[((j & 1) * 2 + half) * BM + rl] = mx;
       named_bar_sync(pair_bar, 64);
       mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * BM + rl]) * p.c1;  // c1 > 0: max commutes with the scaling
+      TL(2, 300 + j);
       const float m_new = fmaxf(m_ref, mx);
       const bool grow = m_new > m_ref + 8.f;  // lazy rescale: a stale reference max is fine while p <= 2^8
-      // Observe every O_DONE phase in order: the parity wait only distinguishes "current" from "previous" phase.
-      if (j > 0) {
+      // O is only touched when some row of the warp needs a rescale.  Having seen S_FULL(j) implies PV_{j-2} is done
+      // (MMAs retire in issue order), so the parity wait for phase j-1 is unambiguous even if earlier phases were
+      // never observed.
+      if (__any_sync(0xffffffffu, grow) && j > 0) {  // both warps of the quarter take the same decision
         tc::mbar_wait_hot(&bars[BAR_O_DONE], (j - 1) & 1);
         tc::fence_after_sync();
-      }
-      if (__any_sync(0xffffffffu, grow) && j > 0) {  // both warps of the quarter take the same decision
         const float alpha = grow ? tc::ex2_approx(m_ref - m_new) : 1.f;
         const uint32_t oaddr = lane_addr + COL_O + half * (HD / 2);
         float o[32];
@@ -352,6 +395,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
         l *= alpha;
       }
       if (grow) m_ref = m_new;
+      TL(2, 400 + j);
       uint32_t pk[HB / 2];
       float2 sum2 = make_float2(0.f, 0.f);
       {
@@ -368,15 +412,20 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
         }
       }
       l += sum2.x + sum2.y;
+      TL(2, 500 + j);
       tc::tmem_st16(lane_addr + COL_S0 + sb * BN + half * (HB / 2), pk);
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars[BAR_P_FULL0 + sb]);
+      TL(2, 600 + j);
     }
     // ---- phase O: normalise, residual pooling, store
+    // phases <= n_tiles-3 are known complete (S_FULL of the last tile was seen): observe the last two in order
+    if (p.n_tiles >= 2) tc::mbar_wait_hot(&bars[BAR_O_DONE], (p.n_tiles - 2) & 1);
     tc::mbar_wait_hot(&bars[BAR_O_DONE], (p.n_tiles - 1) & 1);
     tc::fence_after_sync();
+    TL(2, 9003);
     xch[((p.n_tiles & 1) * 2 + half) * BM + rl] = l;  // partial row sums of the two halves
     named_bar_sync(pair_bar, 64);
     l += xch[((p.n_tiles & 1) * 2 + (half ^ 1)) * BM + rl];
@@ -430,6 +479,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
         }
       }
     }
+    TL(2, 9004);
     if (half == 0 && row < p.Nq && p.lse) p.lse[(int64_t)bh * p.Nq + row] = (m_ref + log2f(l)) * 0.6931471805599453f;
   }
   tc::fence_before_sync();
@@ -501,6 +551,7 @@ int svit_attn_fwd_tc3(const svit_attn_args* a, cudaStream_t st) {
   p.inv_scale = 1.0f / a->scale;
   p.idx_h = a->idx_h; p.idx_w = a->idx_w; p.idx_t = a->idx_t;
   p.out = (bf16*)a->out; p.lse = a->lse;
+  p.dbg = g_attn_timeline;
   const uint64_t BH = (uint64_t)a->B * a->h;
   CUtensorMap tq0, tq1, tk0, tk1, tsel, tsel2, tv, tt;
   const bool x16 = a->sel_cols == EK + EK2;

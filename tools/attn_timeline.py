@@ -16,7 +16,8 @@ rels = [(0.2 * torch.randn(2 * max(a, b) - 1, 96, generator=gen)).cuda() for a, 
 R = [msa.gathered_rel_pos(r, a, b) for r, (a, b) in zip(rels, pairs)]
 tabs = [r.bfloat16() for r in rels]
 tc_tables = (torch.cat(tabs).contiguous(), [t.shape[0] for t in tabs], msa._index32_on(q.device, qh, kh),
-             msa._index32_on(q.device, qw, kw), msa._index32_on(q.device, qt, kt), msa.key_column_codes(k_thw, O, q.device))
+             msa._index32_on(q.device, qw, kw), msa._index32_on(q.device, qt, kt), msa.key_column_codes(k_thw, O, q.device),
+             msa.key_select_table(k_thw, O, q.device))
 run = lambda: ops.attention(q, k, v, R[0], R[1], R[2], q_thw, k_thw, O, 96 ** -0.5, tc_tables)
 with torch.no_grad():
     for _ in range(3): run()
