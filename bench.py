@@ -157,7 +157,7 @@ def run_reference(args):
     times = times[min(args.warmup, len(times) - 1):] or times
     sec = statistics.median(times)
     val = 1.0 / sec
-    line = {"impl": "reference", "metric": "clips/sec (16x224^2) SViT forward", "value": val, "unit": "clips/s",
+    line = {"impl": "reference", "metric": "clips/sec (16x224^2, bf16) SViT forward", "value": val, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "SViT ssv2.yaml forward, 16x224^2 clips, 4 object tokens/frame; each step = a "
