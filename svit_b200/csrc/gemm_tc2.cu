@@ -14,6 +14,8 @@
 //              in place, so every global access of the epilogue is a bulk tensor copy.
 // Ring of SPG staging slots per group: a slot is rewritten only after the store that read it has drained
 // (cp.async.bulk.wait_group.read SPG-2 by the leader, published by the group's named barrier).
+#include <cstdlib>
+
 #include "tc_common.cuh"
 #include "../../include/svit_b200.h"
 
@@ -32,11 +34,11 @@ constexpr int SMEM_LIMIT = 232448;        // 227 KB
 
 enum { AUX_NONE = 0, AUX_RESIDUAL = 1, AUX_GELU_PRE = 2 };
 
-template <int BN, int G>
+template <int BN, int G, bool PAIR = false>
 struct Cfg {
   static constexpr int SPG = spg_of(G);
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // a CTA of a pair holds half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = G * SPG * SLOT_BYTES;
   static constexpr int FIXED = STG_BYTES + 512 + 1024;  // staging + barriers + alignment slack
@@ -117,9 +119,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // c = g, g+2, ... that start left of N.
 struct BoxIter {
   int t, num_tiles, n_tiles, N;
-  int c, g, BN, G;
-  __device__ BoxIter(int t0, int num_tiles_, int n_tiles_, int N_, int g_, int BN_, int G_)
-      : t(t0), num_tiles(num_tiles_), n_tiles(n_tiles_), N(N_), c(g_), g(g_), BN(BN_), G(G_) {
+  int c, g, BN, G, stride;
+  __device__ BoxIter(int t0, int stride_, int num_tiles_, int n_tiles_, int N_, int g_, int BN_, int G_)
+      : t(t0), num_tiles(num_tiles_), n_tiles(n_tiles_), N(N_), c(g_), g(g_), BN(BN_), G(G_), stride(stride_) {
     settle();
   }
   __device__ int nbox() const {
@@ -129,7 +131,7 @@ struct BoxIter {
   }
   __device__ void settle() {
     while (t < num_tiles && c >= nbox()) {
-      t += gridDim.x;
+      t += stride;
       c = g;
     }
   }
@@ -161,13 +163,17 @@ __device__ __forceinline__ int remap_row(const Epi& e, int m) {  // all row coun
   return q * (int)e.rows_out + (int)e.row_off + (m - q * ri);
 }
 
-template <int BN, bool B_MN, int G>
+// PAIR: clusters of two CTAs compute 256 x BN tiles with tcgen05.mma.cta_group::2 -- each CTA loads its 128 rows of A
+// and HALF of the B tile, the leader CTA issues the MMAs for both, completion is multicast to both CTAs' barriers.
+template <int BN, bool B_MN, int G, bool PAIR>
 __global__ void __launch_bounds__(threads_of(G), 1)
 gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_x, int M,
                    int N, int K, Epi e) {
-  using L = Cfg<BN, G>;
+  using L = Cfg<BN, G, PAIR>;
+  static_assert(!(PAIR && B_MN), "pair mode supports K-major B only");
   constexpr int STAGES = L::STAGES;
+  constexpr int TM = PAIR ? 2 * BM : BM;  // tile rows of the scheduling unit (CTA or CTA pair)
   constexpr int SPG = L::SPG;
   constexpr int EPI_WARPS = 4 * G;
   extern __shared__ unsigned char smem_raw[];
@@ -182,9 +188,12 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_full + G * SPG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int m_tiles = (M + TM - 1) / TM, n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
+  const uint32_t crank = PAIR ? tc::cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a);
@@ -197,14 +206,18 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&tmem_full[i], 1);
-      tc::mbar_init(&tmem_empty[i], EPI_WARPS);
+      tc::mbar_init(&tmem_empty[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // pair: both CTAs' epilogues report to the leader
     }
     for (int i = 0; i < G * SPG; ++i) tc::mbar_init(&aux_full[i], 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_ptr, L::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tc::tmem_alloc_pair(tmem_ptr, L::TMEM_COLS);
+    else tc::tmem_alloc(tmem_ptr, L::TMEM_COLS);
+  }
   tc::fence_before_sync();
   __syncthreads();
+  if (PAIR) tc::cluster_sync();  // the peer's barriers are initialised before anything signals them
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -214,20 +227,28 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int tl_n = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      for (int t = unit0; t < num_tiles; t += unit_stride) {
+        const int m0 = (t / n_tiles) * TM + (int)crank * BM, n0 = (t % n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           TL(0, kb);
           unsigned char* sa = smem + stage * L::STAGE_BYTES;
           unsigned char* sb = sa + L::A_BYTES;
-          tc::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tc::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
-          if (!B_MN) {
-            tc::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (PAIR) {
+            // both CTAs' bytes are accounted on the leader's barrier, which the leader arms for the pair
+            const uint32_t lbar = tc::mapa_shared(tc::smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+            tc::tma_load_2d_pair(sa, &tmap_a, lbar, kb * BK, m0);
+            tc::tma_load_2d_pair(sb, &tmap_b, lbar, kb * BK, n0 + (int)crank * (BN / 2));
           } else {
+            tc::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            tc::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            if (!B_MN) {
+              tc::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tc::tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * BK);
+              for (int j = 0; j < BN / 64; ++j) tc::tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * BK);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -235,13 +256,13 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, 0, B_MN ? 1 : 0);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16(TM, BN, 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       int tl_n = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = unit0; t < num_tiles; t += unit_stride, ++it) {
         const int as = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         tc::mbar_wait_hot(&tmem_empty[as], acc_phase ^ 1);
@@ -258,10 +279,16 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? tc::smem_desc_sw128(sb + k * 2048, 8192, 1024) : tc::smem_desc_sw128(sb + k * 32, 16, 1024);
-            tc::umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) tc::umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tc::umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc::umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) tc::umma_commit(&tmem_full[as]);
+          if (PAIR) {
+            tc::umma_commit_pair(&empty_bar[stage]);
+            if (kb == num_kb - 1) tc::umma_commit_pair(&tmem_full[as]);
+          } else {
+            tc::umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) tc::umma_commit(&tmem_full[as]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -278,11 +305,15 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int aux = e.aux;
 
     // leader: request the first PF_DIST aux boxes
-    BoxIter pf(blockIdx.x, num_tiles, n_tiles, N, g, BN, G);
+    BoxIter pf(unit0, unit_stride, num_tiles, n_tiles, N, g, BN, G);
+    auto release_tmem = [&](int as) {  // one arrival per epilogue warp on the (leader's) tmem_empty barrier
+      if (PAIR) tc::mbar_arrive_cluster(tc::mapa_shared(tc::smem_u32(&tmem_empty[as]), 0));
+      else tc::mbar_arrive(&tmem_empty[as]);
+    };
     uint32_t pf_cnt = 0;
     auto request_aux = [&]() {
       if (!pf.valid()) return;
-      const int m0 = (pf.t / n_tiles) * BM, n0 = (pf.t % n_tiles) * BN;
+      const int m0 = (pf.t / n_tiles) * TM + (int)crank * BM, n0 = (pf.t % n_tiles) * BN;
       const int row0 = aux == AUX_RESIDUAL ? remap_row(e, m0) : m0;
       const int slot = pf_cnt % SPG;
       tc::mbar_arrive_expect_tx(&my_aux[slot], SLOT_BYTES);
@@ -298,10 +329,10 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     int it = 0;
     int tl_n = leader ? 0 : 4096;
     if (g != 0) tl_n = 4096;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = unit0; t < num_tiles; t += unit_stride, ++it) {
       const int as = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      const int m0 = (t / n_tiles) * TM + (int)crank * BM, n0 = (t % n_tiles) * BN;
       const int rem = N - n0 < BN ? N - n0 : BN;
       const int nbox = (rem + BOX_N - 1) / BOX_N;
       const int orow0 = remap_row(e, m0);
@@ -320,7 +351,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (last_c < 0) {  // no box for this group in this tile (narrow tail): keep the arrival count uniform
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) release_tmem(as);
       }
 #pragma unroll 1
       for (int c = g; c < nbox; c += G) {
@@ -344,7 +375,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (c == last_c) {  // this warp's rows of the accumulator are in registers: release the TMEM buffer
           tc::fence_before_sync();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
+          if (lane == 0) release_tmem(as);
         }
         float2* v2 = reinterpret_cast<float2*>(v);
         if (e.bias) {
@@ -411,9 +442,11 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (PAIR) tc::cluster_sync();  // no CTA leaves (or frees TMEM) while its peer may still signal it
   if (warp == 1) {
     tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, L::TMEM_COLS);
+    if (PAIR) tc::tmem_dealloc_pair(tmem_base, L::TMEM_COLS);
+    else tc::tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
@@ -431,18 +464,28 @@ int make_box_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
   return r == CUDA_SUCCESS ? 0 : SVIT_EINVAL;
 }
 
+// SVIT_GEMM_PAIR=0 switches the cta_group::2 path off (diagnostics)
+bool svit_gemm_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SVIT_GEMM_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 unsigned long long* g_timeline = nullptr;
 unsigned long long* svit_gemm_timeline_buffer() { return g_timeline; }
 
-template <int BN, bool B_MN, int G>
+template <int BN, bool B_MN, int G, bool PAIR = false>
 int launch_g(const svit_gemm_args* a, cudaStream_t st) {
-  using L = Cfg<BN, G>;
+  using L = Cfg<BN, G, PAIR>;
   static_assert(L::STAGES >= 2, "pipeline too shallow");
   static_assert(L::TOTAL <= SMEM_LIMIT, "shared memory budget");
   CUtensorMap ta, tb, tcm, tx;
   int rc;
   if ((rc = svit_make_tmap_2d(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM))) return rc;
-  if (!B_MN) rc = svit_make_tmap_2d(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, BN);
+  if (!B_MN) rc = svit_make_tmap_2d(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, PAIR ? BN / 2 : BN);
   else rc = svit_make_tmap_2d(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK);
   if (rc) return rc;
   const uint64_t out_rows = a->rows_in > 0 ? (uint64_t)((a->M + a->rows_in - 1) / a->rows_in * a->rows_out) : (uint64_t)a->M;
@@ -458,22 +501,52 @@ int launch_g(const svit_gemm_args* a, cudaStream_t st) {
   if (e.aux == AUX_RESIDUAL) rc = make_box_map(&tx, a->residual, out_rows, (uint64_t)a->N, (uint64_t)a->ldr);
   else if (e.aux == AUX_GELU_PRE) rc = make_box_map(&tx, a->gelu_pre, (uint64_t)a->M, (uint64_t)a->N, (uint64_t)a->ldg);
   if (rc) return rc;
-  auto kern = gemm_tc_tma_kernel<BN, B_MN, G>;
+  auto kern = gemm_tc_tma_kernel<BN, B_MN, G, PAIR>;
   static bool configured = false;
   if (!configured) {
     SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  const int64_t tiles = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN);
-  const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
-  kern<<<grid, threads_of(G), L::TOTAL, st>>>(ta, tb, tcm, tx, (int)a->M, (int)a->N, (int)a->K, e);
-  SVIT_CHECK_LAUNCH();
+  constexpr int TM = PAIR ? 2 * BM : BM;
+  const int64_t tiles = ((a->M + TM - 1) / TM) * ((a->N + BN - 1) / BN);
+  if (!PAIR) {
+    const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
+    kern<<<grid, threads_of(G), L::TOTAL, st>>>(ta, tb, tcm, tx, (int)a->M, (int)a->N, (int)a->K, e);
+    SVIT_CHECK_LAUNCH();
+    return 0;
+  }
+  // clusters of two CTAs (one SM pair each)
+  int pairs = svit_num_sms() / 2;
+  if (tiles < pairs) pairs = (int)tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3((unsigned)threads_of(G));
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SVIT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tcm, tx, (int)a->M, (int)a->N, (int)a->K, e));
   return 0;
 }
 
 template <int BN, bool B_MN>
 int launch(const svit_gemm_args* a, cudaStream_t st) {
   // three epilogue groups when the epilogue dominates: GELU / gelu' math, or few K-steps per tile
+  // CTA pairs (256 x BN tiles, cta_group::2) when the reduction is long enough for operand delivery to dominate
+  // (measured on B200: +3..12 % for K >= 768; for K = 384 the extra epilogue coupling of the pair costs more than the
+  // halved B traffic saves)
+  constexpr bool CAN_PAIR = !B_MN && (BN == 256 || BN == 192 || BN == 128);
+  if constexpr (CAN_PAIR) {
+    if (svit_gemm_pair_enabled() && a->K >= 768 && a->M >= 2048) {
+      if (a->act == 1 || a->gelu_pre) return launch_g<BN, B_MN, 3, true>(a, st);
+      return launch_g<BN, B_MN, 2, true>(a, st);
+    }
+  }
   if (a->act == 1 || a->gelu_pre || a->K <= 256) return launch_g<BN, B_MN, 3>(a, st);
   return launch_g<BN, B_MN, 2>(a, st);
 }
