@@ -529,7 +529,7 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
 // ------------------------------------------------------------------------------------------------ direct
 // One half-warp per output token.  mode 0: all tokens; mode 1: only cls + object tokens (companion of the tiled
 // kernel, which writes the patch tokens).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 pool_ln_direct_kernel(const bf16* __restrict__ in, Geom g, const float* __restrict__ w, const float* __restrict__ frac,
                       const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ out, float eps,
                       int mode) {
@@ -570,34 +570,35 @@ pool_ln_direct_kernel(const bf16* __restrict__ in, Geom g, const float* __restri
     } else {
       const int64_t pp = tok - 1;
       const int wo = (int)(pp % g.Wo), ho = (int)((pp / g.Wo) % g.Ho), to = (int)(pp / ((int64_t)g.Wo * g.Ho));
-      // all 27 x 3 words of the window are requested before the first FMA (zero for padding taps), so the
-      // DRAM / L2 latency is paid once per token, not once per tap
-      uint32_t xw[TAPS][3];
+      // one temporal plane at a time: its 9 x 3 words are requested before the first FMA (zero for padding taps);
+      // 27 live registers instead of 81 keep four CTAs per SM resident, which is what hides the load latency
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
         const int t = to - 1 + kt;
+        if (t < 0 || t >= g.T) continue;
+        uint32_t xw[9][3];
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
           const int hh = ho * g.s - 1 + kh;
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const int ww = wo * g.s - 1 + kw;
-            const bool ok = t >= 0 && t < g.T && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W;
+            const bool ok = hh >= 0 && hh < g.H && ww >= 0 && ww < g.W;
             const uint32_t* q = reinterpret_cast<const uint32_t*>(
                 zin + (ok ? (1 + ((int64_t)t * g.H + hh) * g.W + ww) * g.in_ts : 0));
 #pragma unroll
-            for (int j = 0; j < 3; ++j) xw[(kt * 3 + kh) * 3 + kw][j] = ok ? __ldg(q + l16 + 16 * j) : 0u;
+            for (int j = 0; j < 3; ++j) xw[kh * 3 + kw][j] = ok ? __ldg(q + l16 + 16 * j) : 0u;
           }
         }
-      }
 #pragma unroll
-      for (int tap = 0; tap < TAPS; ++tap) {
-        const float* wr = sw + tap * PD;
+        for (int tap = 0; tap < 9; ++tap) {
+          const float* wr = sw + (kt * 9 + tap) * PD;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float2 f = *reinterpret_cast<const float2*>(wr + 2 * (l16 + 16 * j));
-          v[2 * j] = fmaf(lo_f(xw[tap][j]), f.x, v[2 * j]);
-          v[2 * j + 1] = fmaf(hi_f(xw[tap][j]), f.y, v[2 * j + 1]);
+          for (int j = 0; j < 3; ++j) {
+            const float2 f = *reinterpret_cast<const float2*>(wr + 2 * (l16 + 16 * j));
+            v[2 * j] = fmaf(lo_f(xw[tap][j]), f.x, v[2 * j]);
+            v[2 * j + 1] = fmaf(hi_f(xw[tap][j]), f.y, v[2 * j + 1]);
+          }
         }
       }
     }
