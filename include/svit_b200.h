@@ -86,6 +86,11 @@ typedef struct svit_gemm_args {
   int32_t dtype;             /* dtype of A, B, residual, gelu_pre, pre_out */
   int32_t out_dtype;         /* dtype of C */
   int32_t impl;              /* 0 auto (tcgen05 when bf16 and the shape qualifies), 1 CUDA cores, 2 tcgen05 */
+  /* batched form (tcgen05 path only; batch <= 1 = plain GEMM): problem i uses A + i*strideA, C + i*strideC and
+   * B + (i / b_inner)*strideB + (i % b_inner)*strideB_inner (two-level batch index, e.g. (sample, head) slices of a
+   * [B, N, h, 96] tensor); strides in elements.  No epilogue extras except bias. */
+  int64_t batch, strideA, strideB, strideC;
+  int64_t b_inner, strideB_inner;
 } svit_gemm_args;
 int svit_gemm(const svit_gemm_args* args, void* stream);
 /* out[n] += sum_m x[m,n]  (bias gradients) */

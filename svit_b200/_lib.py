@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("act", i32),
         ("rows_in", i64), ("rows_out", i64), ("row_off", i64),
         ("dtype", i32), ("out_dtype", i32), ("impl", i32),
+        ("batch", i64), ("strideA", i64), ("strideB", i64), ("strideC", i64), ("b_inner", i64), ("strideB_inner", i64),
     ]
 
 

@@ -52,6 +52,8 @@ struct EpiArgs {
   int64_t ldc;
   int out_f32;
   int splits;  // split-K: > 1 -> fp32 partial sums are accumulated with atomics into a zeroed C
+  int batch, b_inner;   // batched GEMM: work item = (batch, K split, output tile)
+  int64_t strideC;      // elements between consecutive problems' outputs
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -190,7 +192,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const int64_t out_tiles = m_tiles * n_tiles;
-  const int64_t num_tiles = out_tiles * e.splits;           // work item = (K split, output tile)
+  const int64_t per_batch = out_tiles * e.splits;           // work item = (batch, K split, output tile)
+  const int64_t num_tiles = per_batch * e.batch;
   const int num_kb_all = (int)((K + BK - 1) / BK);
   const int kb_per = (num_kb_all + e.splits - 1) / e.splits;  // K blocks per split
   constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -220,26 +223,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t w = blockIdx.x; w < num_tiles; w += gridDim.x) {
-        const int64_t t = w % out_tiles;
-        const int kb0 = (int)(w / out_tiles) * kb_per;
+        const int bi = (int)(w / per_batch);
+        const int64_t wb = w - (int64_t)bi * per_batch;
+        const int64_t t = wb % out_tiles;
+        const int kb0 = (int)(wb / out_tiles) * kb_per;
         const int kb1 = kb0 + kb_per < num_kb_all ? kb0 + kb_per : num_kb_all;
         const int m0 = (int)((t / n_tiles) * BM), n0 = (int)((t % n_tiles) * BN);
+        const int bo = bi / e.b_inner, bn = bi - bo * e.b_inner;  // B's two-level batch coordinate
         for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * L::STAGE_BYTES;
           unsigned char* sb = sa + L::A_BYTES;
           tc::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if (!A_MN) {
-            tc::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+            tc::tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, 0, bi);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tc::tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * BK);
+            for (int j = 0; j < BM / 64; ++j) tc::tma_load_4d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * BK, 0, bi);
           }
           if (!B_MN) {
-            tc::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+            tc::tma_load_4d(sb, &tmap_b, &full_bar[stage], kb * BK, n0, bn, bo);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tc::tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * BK);
+            for (int j = 0; j < BN / 64; ++j) tc::tma_load_4d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * BK, bn, bo);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -253,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int it = 0;
       for (int64_t w = blockIdx.x; w < num_tiles; w += gridDim.x, ++it) {
-        const int kb0 = (int)(w / out_tiles) * kb_per;
+        const int kb0 = (int)((w % per_batch) / out_tiles) * kb_per;
         const int kb1 = kb0 + kb_per < num_kb_all ? kb0 + kb_per : num_kb_all;
         const int as = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -287,7 +293,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int LAST_CH1 = ((NCH - 1) & 1) == 1 ? NCH - 1 : NCH - 2;
     int it = 0;
     for (int64_t w = blockIdx.x; w < num_tiles; w += gridDim.x, ++it) {
-      const int64_t t = w % out_tiles;
+      const int64_t t = (w % per_batch) % out_tiles;
+      EpiArgs eb = e;  // this problem's output
+      if (e.batch > 1) {
+        const int64_t off = (w / per_batch) * e.strideC;
+        eb.C = e.out_f32 ? (void*)(reinterpret_cast<float*>(e.C) + off) : (void*)(reinterpret_cast<bf16*>(e.C) + off);
+      }
       const int as = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
@@ -309,7 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = 0; j < CH; j += 4)
           *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
-        store_chunk(e, stg, lane, m0 + q * 32, n0 + ch * CH, M, N);
+        store_chunk(eb, stg, lane, m0 + q * 32, n0 + ch * CH, M, N);
         __syncwarp();
       }
       if (NCH == 1 && half == 1) {  // BN == 32 never instantiated; keeps the arrive count uniform
@@ -330,11 +341,12 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
   using L = SmemLayout<BN>;
   CUtensorMap ta, tb;
   int rc;
-  if (!A_MN) rc = svit_make_tmap_2d(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM);
-  else rc = svit_make_tmap_2d(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK);
+  const uint64_t nb = a->batch > 1 ? (uint64_t)a->batch : 1, bin = (a->batch > 1 && a->b_inner > 1) ? (uint64_t)a->b_inner : 1;
+  if (!A_MN) rc = svit_make_tmap_4d(&ta, a->A, nb, 1, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 0, (uint64_t)a->strideA, BM);
+  else rc = svit_make_tmap_4d(&ta, a->A, nb, 1, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, 0, (uint64_t)a->strideA, BK);
   if (rc) return rc;
-  if (!B_MN) rc = svit_make_tmap_2d(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, BN);
-  else rc = svit_make_tmap_2d(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK);
+  if (!B_MN) rc = svit_make_tmap_4d(&tb, a->B, nb / bin, bin, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, (uint64_t)a->strideB_inner, (uint64_t)a->strideB, BN);
+  else rc = svit_make_tmap_4d(&tb, a->B, nb / bin, bin, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, (uint64_t)a->strideB_inner, (uint64_t)a->strideB, BK);
   if (rc) return rc;
   EpiArgs e;
   e.bias = a->bias;
@@ -348,7 +360,8 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
   e.out_f32 = a->out_dtype == SVIT_F32;
   // split-K for the weight-gradient shape (few output tiles, very long reduction): fp32 partials via atomics
   e.splits = 1;
-  {
+  e.batch = (int)nb; e.b_inner = (int)bin; e.strideC = a->strideC;
+  if (nb == 1) {
     const int64_t tiles0 = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN);
     const int64_t nkb = (a->K + BK - 1) / BK;
     const bool plain = e.out_f32 && !a->bias && !a->residual && !a->gelu_pre && !a->pre_out && !a->sample_scale &&
@@ -369,7 +382,7 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
     SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  const int64_t tiles = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN) * e.splits;
+  const int64_t tiles = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN) * e.splits * e.batch;
   const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
   kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ta, tb, a->M, a->N, a->K, e);
   SVIT_CHECK_LAUNCH();
@@ -410,6 +423,10 @@ svit_tmap_encode_fn svit_get_tmap_encode() {
 
 int svit_gemm_tc_supported(const svit_gemm_args* a) {
   if (a->dtype != SVIT_BF16) return 0;
+  if (a->batch > 1) {  // batched form: no epilogue extras except bias, 16-byte aligned problem strides
+    if (a->residual || a->gelu_pre || a->pre_out || a->sample_scale || a->act || a->rows_in) return 0;
+    if (a->strideA % 8 || a->strideB % 8 || a->strideC % 8 || (a->b_inner > 1 && (a->strideB_inner % 8 || a->batch % a->b_inner))) return 0;
+  }
   if (a->out_dtype != SVIT_BF16 && a->out_dtype != SVIT_F32) return 0;
   if (a->K < 8 || a->N < 8 || a->M < 1) return 0;
   if (a->N % 8 || a->lda % 8 || a->ldb % 8) return 0;
@@ -420,7 +437,7 @@ int svit_gemm_tc_supported(const svit_gemm_args* a) {
   if (a->pre_out && (!aligned16(a->pre_out) || a->ldp % 8)) return 0;
   if (a->M >= (1ll << 31) || a->N >= (1ll << 31) || a->K >= (1ll << 31)) return 0;
   // operand extents along the contiguous dim must cover whole 16-byte units for TMA
-  if (a->transA ? (a->M % 8) : (a->K % 8)) return 0;
+  if (!a->transA && (a->K % 8)) return 0;  // (MN-major A: only the row pitch lda must be a 16-byte multiple)
   if (a->transB ? (a->K % 8) : (a->N % 8)) return 0;
   return 1;
 }
@@ -429,7 +446,7 @@ int svit_gemm_tc_tma_supported(const svit_gemm_args* a);  // gemm_tc2.cu
 int svit_gemm_tc_tma(const svit_gemm_args* a, cudaStream_t st);
 
 int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st) {
-  if (svit_gemm_tc_tma_supported(a)) return svit_gemm_tc_tma(a, st);
+  if (a->batch <= 1 && svit_gemm_tc_tma_supported(a)) return svit_gemm_tc_tma(a, st);
   const bool a_mn = a->transA != 0;  // A stored [K, M]
   const bool b_mn = a->transB == 0;  // B stored [K, N]
   if (!a_mn && !b_mn) return dispatch_bn<false, false>(a, st);

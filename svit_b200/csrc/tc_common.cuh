@@ -81,6 +81,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -295,6 +303,21 @@ static inline int svit_make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t ro
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : SVIT_EINVAL;
+}
+// 4-D bf16 tensor [outer, inner, rows, cols] (batched GEMM operands: batch index = outer * n_inner + inner)
+static inline int svit_make_tmap_4d(CUtensorMap* m, const void* ptr, uint64_t outer, uint64_t inner, uint64_t rows,
+                                    uint64_t cols, uint64_t ld_row, uint64_t ld_inner, uint64_t ld_outer, uint32_t box_rows,
+                                    uint32_t box_cols = 64) {
+  svit_tmap_encode_fn enc = svit_get_tmap_encode();
+  if (!enc) return SVIT_ENOTSUP;
+  cuuint64_t dims[4] = {cols, rows, inner, outer};
+  cuuint64_t strides[3] = {ld_row * 2, (inner > 1 ? ld_inner : ld_row * rows) * 2, (outer > 1 ? ld_outer : ld_row * rows) * 2};
+  cuuint32_t box[4] = {box_cols, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : SVIT_EINVAL;

@@ -135,8 +135,9 @@ def _call(name, *args, tag=None):
 # --------------------------------------------------------------------------------------------
 def gemm(A, B, out, M, N, K, lda, ldb, ldc, transA=0, transB=1, bias=None, residual=None, ldr=0,
          sample_scale=None, rows_per_sample=0, gelu_pre=None, ldg=0, pre_out=None, ldp=0, act=0,
-         remap=(0, 0, 0), impl=None):
+         remap=(0, 0, 0), impl=None, batch=0, strideA=0, strideB=0, strideC=0, b_inner=0, strideB_inner=0):
     a = GemmArgs()
+    a.batch, a.strideA, a.strideB, a.strideC, a.b_inner, a.strideB_inner = batch, strideA, strideB, strideC, b_inner, strideB_inner
     a.A, a.B, a.C = A.data_ptr(), B.data_ptr(), out.data_ptr()
     a.M, a.N, a.K, a.lda, a.ldb, a.ldc = M, N, K, lda, ldb, ldc
     a.transA, a.transB = transA, transB

@@ -135,6 +135,22 @@ def test_gemm_tc_wgrad_split_k(Mo, No, Kr):
     assert max_rel_err(cpu(out), ref.float().cpu()) < 2e-4
 
 
+@pytest.mark.parametrize("Bn,h,Nq,Nk", [(2, 4, 1633, 457), (1, 2, 700, 1633), (3, 1, 130, 65)])
+def test_gemm_tc_batched_attention_backward_shapes(Bn, h, Nq, Nk):
+    """Batched tcgen05 GEMM as the attention backward uses it: dV[b,h] = P[b,h]^T dO[b,:,h,:] -- A stored [Nq, Nkp]
+    (MN-major, padded key count), B a (sample, head) slice of a [B, Nq, h, 96] tensor (two-level batch index)."""
+    gen = torch.Generator().manual_seed(Nq + Nk)
+    Nkp = (Nk + 63) // 64 * 64
+    P = (torch.rand(Bn * h, Nq, Nkp, generator=gen) / Nk).to(torch.bfloat16).to(DEV)
+    dO = torch.randn(Bn, Nq, h, 96, generator=gen).to(torch.bfloat16).to(DEV)
+    dV = torch.full((Bn * h, Nk, 96), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.gemm(P, dO, dV, Nk, 96, Nq, Nkp, h * 96, 96, 1, 0, impl=TC, batch=Bn * h, strideA=Nq * Nkp, strideB=Nq * h * 96,
+             strideC=Nk * 96, b_inner=h, strideB_inner=96)
+    ref = torch.einsum("bqk,bqd->bkd", P.float()[:, :, :Nk], dO.float().permute(0, 2, 1, 3).reshape(Bn * h, Nq, 96))
+    assert not torch.isnan(dV.float()).any()
+    assert max_rel_err(cpu(dV), cpu(ref)) < 6e-3
+
+
 def test_gemm_tc_matches_simt_on_model_shapes():
     """Every forward GEMM shape of configs/ssv2.yaml (M = tokens of one clip)."""
     gen = torch.Generator().manual_seed(29)
