@@ -91,6 +91,9 @@ typedef struct svit_gemm_args {
    * [B, N, h, 96] tensor); strides in elements.  No epilogue extras except bias. */
   int64_t batch, strideA, strideB, strideC;
   int64_t b_inner, strideB_inner;
+  /* same two-level split for A: A + (i / a_inner)*strideA + (i % a_inner)*strideA_inner when a_inner > 1 */
+  int64_t a_inner, strideA_inner;
+  float alpha;               /* accumulator scale applied before the bias; 0 is read as 1 (tcgen05 path only) */
 } svit_gemm_args;
 int svit_gemm(const svit_gemm_args* args, void* stream);
 /* out[n] += sum_m x[m,n]  (bias gradients) */
@@ -143,6 +146,17 @@ typedef struct svit_attn_args {
    * -1e30 in the last column for padding keys (n >= Nk).  sel_cols must be 32 and kh + kw + kt <= 31. */
   const void* sel_tab;
   int32_t sel_cols;
+  /* tensor-core backward (bf16, attn_bwd_tc.cu), optional: all six present -> the five contractions of the backward
+   * run as batched tcgen05 GEMMs.  Nkp = Nk rounded up to 8; nep = kh+kw+kt rounded up to 8 (<= 64); with these,
+   * ws_e and ws_de are [B,h,Nq,nep].  sel_bwd [Nk, nep] (activation dtype): row n = key n with ones in columns
+   * i'(n), kh + j'(n), kh + kw + t'(n) for patch keys, zero rows for cls / object keys. */
+  float* ws_s;      /* scratch fp32 [B,h,Nq,Nkp]: q k^T */
+  float* ws_dp;     /* scratch fp32 [B,h,Nq,Nkp]: dO v^T */
+  void* ws_p;       /* scratch bf16 [B,h,Nq,Nkp]: softmax probabilities */
+  void* ws_ds;      /* scratch bf16 [B,h,Nq,Nkp]: dS */
+  float* ws_dq;     /* scratch fp32 [B,h,Nq,96] */
+  const void* sel_bwd;
+  int32_t nep;
 } svit_attn_args;
 int svit_attn_fwd(const svit_attn_args* args, void* stream);
 int svit_attn_bwd(const svit_attn_args* args, void* stream);

@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("rows_in", i64), ("rows_out", i64), ("row_off", i64),
         ("dtype", i32), ("out_dtype", i32), ("impl", i32),
         ("batch", i64), ("strideA", i64), ("strideB", i64), ("strideC", i64), ("b_inner", i64), ("strideB_inner", i64),
+        ("a_inner", i64), ("strideA_inner", i64), ("alpha", f32),
     ]
 
 
@@ -44,6 +45,7 @@ class AttnArgs(C.Structure):
         ("rel_tab", vp), ("idx_h", vp), ("idx_w", vp), ("idx_t", vp), ("key_cols", vp),
         ("ntab_h", i32), ("ntab_w", i32), ("ntab_t", i32),
         ("sel_tab", vp), ("sel_cols", i32),
+        ("ws_s", vp), ("ws_dp", vp), ("ws_p", vp), ("ws_ds", vp), ("ws_dq", vp), ("sel_bwd", vp), ("nep", i32),
     ]
 
 

@@ -1,0 +1,291 @@
+// Backward of the pooled attention core on the tensor cores (bf16 storage, fp32 accumulate).
+//
+// The five contractions of the backward (attention.py:429-459 differentiated)
+//     S  = q k^T            dP = dO v^T            dV = P^T dO
+//     dK = scale dS^T q     dQ = scale dS k        dE = dS Sel      (rel-pos bias gradient, see below)
+// run as batched problems of the tcgen05 GEMM (gemm_tc.cu: TMA-fed, TMEM accumulators, MN-major operand
+// descriptors instead of transposed copies, (sample, head) two-level batch index for the head-merged dO).
+// Between them three streaming kernels do the row-wise work:
+//   prep      delta = dO . (out - q[rows >= 1]),  E[r, c] = q_r . R_c   (bias terms, as the forward)
+//   softmax   P = exp(scale S + E[i'] + E[kh + j'] + E[kh + kw + t'] - lse),  dS = P (dP - delta)   -> bf16
+//   finish    dq = scale dS k + sum_c dE[c] R_c + dO[rows >= 1] ;  dR via attn_bwd_drel (attn_simt_bwd.cu)
+// The bias gradient dE[r, c] = sum over patch keys whose coordinate is c of dS[r, key] is the product of dS with the
+// 0/1 key-selection matrix Sel [Nk, nep] (row = key, ones in columns i', kh + j', kh + kw + t'; zero rows for
+// cls / object keys), i.e. one more GEMM with M = B h Nq.
+// S and dP are kept in fp32 between the GEMMs and the softmax kernel (bf16 scores would cost 2^-9 relative error in
+// the exponent argument); P and dS are the bf16 operands of the second round of GEMMs.
+#include "common.cuh"
+#include "../../include/svit_b200.h"
+
+#define D SVIT_HEAD_DIM
+
+int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st);  // gemm_tc.cu
+int svit_gemm_tc_supported(const svit_gemm_args* a);
+int svit_attn_bwd_drel(const svit_attn_args* a, int estride, cudaStream_t st);  // attn_simt_bwd.cu
+
+namespace {
+
+constexpr int PQ = 32;    // query rows per prep CTA
+constexpr int MAXE = 64;  // kh + kw + kt
+
+__device__ __forceinline__ const bf16* rel_row(const svit_attn_args& a, int c, int i, int j, int t) {
+  if (c < a.kh) return (const bf16*)a.rel_h + ((int64_t)i * a.kh + c) * D;
+  if (c < a.kh + a.kw) return (const bf16*)a.rel_w + ((int64_t)j * a.kw + (c - a.kh)) * D;
+  return (const bf16*)a.rel_t + ((int64_t)t * a.kt + (c - a.kh - a.kw)) * D;
+}
+
+// ---- prep: delta and the bias terms E ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, int nep) {
+  __shared__ float sq[PQ][D + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
+  const int64_t Nq = 1 + Lq + a.O;
+  const int ne = a.kh + a.kw + a.kt;
+  const int bh = blockIdx.y, b = bh / a.h, head = bh % a.h;
+  const int64_t r0 = (int64_t)blockIdx.x * PQ;
+  const bf16* q = (const bf16*)a.q + (int64_t)bh * Nq * D;
+  for (int idx = threadIdx.x; idx < PQ * D; idx += blockDim.x) {
+    const int r = idx / D, d = idx % D;
+    sq[r][d] = r0 + r < Nq ? __bfloat162float(q[(r0 + r) * D + d]) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rr = 0; rr < PQ / 8; ++rr) {
+    const int r = warp * (PQ / 8) + rr;
+    const int64_t row = r0 + r;
+    if (row >= Nq) continue;
+    const int64_t off = (((int64_t)b * Nq + row) * a.h + head) * D;
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float o = __bfloat162float(((const bf16*)a.out)[off + lane + 32 * j]);
+      if (row >= 1) o -= sq[r][lane + 32 * j];
+      part += o * __bfloat162float(((const bf16*)a.dout)[off + lane + 32 * j]);
+    }
+    part = warp_sum(part);
+    if (lane == 0) a.ws_delta[(int64_t)bh * Nq + row] = part;
+  }
+  for (int idx = threadIdx.x; idx < PQ * nep; idx += blockDim.x) {
+    const int r = idx / nep, c = idx % nep;
+    const int64_t row = r0 + r;
+    if (row >= Nq) continue;
+    float acc = 0.f;
+    if (c < ne && row >= 1 && row <= Lq) {
+      const int64_t p = row - 1;
+      const int j = (int)(p % a.qw), i = (int)((p / a.qw) % a.qh), t = (int)(p / ((int64_t)a.qw * a.qh));
+      const uint4* R = reinterpret_cast<const uint4*>(rel_row(a, c, i, j, t));
+#pragma unroll
+      for (int u = 0; u < D / 8; ++u) {
+        const uint4 w = __ldg(R + u);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h2[e]);
+          acc = fmaf(sq[r][u * 8 + 2 * e], f.x, acc);
+          acc = fmaf(sq[r][u * 8 + 2 * e + 1], f.y, acc);
+        }
+      }
+    }
+    a.ws_e[((int64_t)bh * Nq + row) * nep + c] = acc;
+  }
+}
+
+// ---- softmax recompute + dS ----------------------------------------------------------------------------------
+// One warp per (b, head, query row); lanes own 4 consecutive keys per 128-key step.  Key -> E-column codes are
+// built once per CTA in shared memory (slot 64 = the always-zero entry used by cls / object keys).
+__global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(svit_attn_args a, const float* __restrict__ S,
+                                                               const float* __restrict__ dP, bf16* __restrict__ P,
+                                                               bf16* __restrict__ dS, int nep, int64_t Nkp,
+                                                               int64_t total_rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* codes = reinterpret_cast<uint32_t*>(smem_raw);  // [Nkp]
+  float* es = reinterpret_cast<float*>(smem_raw + Nkp * 4);  // [8][MAXE + 4]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t Lq = (int64_t)a.qt * a.qh * a.qw, Lk = (int64_t)a.kt * a.kh * a.kw;
+  const int64_t Nq = 1 + Lq + a.O, Nk = 1 + Lk + a.O;
+  const int ne = a.kh + a.kw + a.kt;
+  for (int64_t n = threadIdx.x; n < Nkp; n += blockDim.x) {
+    uint32_t code = 64u | (64u << 8) | (64u << 16);
+    if (n >= 1 && n <= Lk) {
+      const int64_t p = n - 1;
+      const uint32_t jj = (uint32_t)(p % a.kw), ii = (uint32_t)((p / a.kw) % a.kh), tt = (uint32_t)(p / ((int64_t)a.kw * a.kh));
+      code = ii | ((a.kh + jj) << 8) | ((a.kh + a.kw + tt) << 16);
+    }
+    codes[n] = code;
+  }
+  float* e = es + warp * (MAXE + 4);
+  const float kLog2e = 1.4426950408889634f;
+  const float sc = a.scale * kLog2e;
+  __syncthreads();
+  for (int64_t R = (int64_t)blockIdx.x * 8 + warp; R < total_rows; R += (int64_t)gridDim.x * 8) {
+    const int64_t row = R % Nq;
+    const bool qpatch = row >= 1 && row <= Lq;
+    __syncwarp();
+#pragma unroll
+    for (int c = lane; c < MAXE + 4; c += 32)
+      e[c] = (qpatch && c < ne) ? a.ws_e[R * nep + c] * kLog2e : 0.f;
+    const float nlse = -a.lse[R] * kLog2e;
+    const float delta = a.ws_delta[R];
+    __syncwarp();
+    const float* srow = S + R * Nkp;
+    const float* dprow = dP + R * Nkp;
+    bf16* prow = P + R * Nkp;
+    bf16* dsrow = dS + R * Nkp;
+    for (int64_t n = 4 * lane; n < Nkp; n += 128) {
+      const float4 s4 = __ldcs(reinterpret_cast<const float4*>(srow + n));
+      const float4 d4 = __ldcs(reinterpret_cast<const float4*>(dprow + n));
+      const uint4 c4 = *reinterpret_cast<const uint4*>(codes + n);
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      const uint32_t cv[4] = {c4.x, c4.y, c4.z, c4.w};
+      float p[4], ds[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float bias = e[cv[u] & 255u] + e[(cv[u] >> 8) & 255u] + e[cv[u] >> 16];
+        float pv = exp2f(fmaf(sv[u], sc, bias + nlse));
+        if (n + u >= Nk) pv = 0.f;
+        p[u] = pv;
+        ds[u] = pv * (dv[u] - delta);
+      }
+      __nv_bfloat162 p01 = __floats2bfloat162_rn(p[0], p[1]), p23 = __floats2bfloat162_rn(p[2], p[3]);
+      __nv_bfloat162 d01 = __floats2bfloat162_rn(ds[0], ds[1]), d23 = __floats2bfloat162_rn(ds[2], ds[3]);
+      uint2 po = {*reinterpret_cast<uint32_t*>(&p01), *reinterpret_cast<uint32_t*>(&p23)};
+      uint2 dso = {*reinterpret_cast<uint32_t*>(&d01), *reinterpret_cast<uint32_t*>(&d23)};
+      *reinterpret_cast<uint2*>(prow + n) = po;
+      *reinterpret_cast<uint2*>(dsrow + n) = dso;
+    }
+  }
+}
+
+// ---- dq = dq_part (already scaled) + sum_c dE[c] R_c + dO[rows >= 1] -------------------------------------------
+__global__ void __launch_bounds__(256) attn_bwd_finish_kernel(svit_attn_args a, const float* __restrict__ dq_part,
+                                                              int nep, int64_t total_rows) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
+  const int64_t Nq = 1 + Lq + a.O;
+  const int ne = a.kh + a.kw + a.kt;
+  const int64_t R = (int64_t)blockIdx.x * 8 + warp;
+  if (R >= total_rows) return;
+  const int64_t bh = R / Nq, row = R % Nq;
+  const int b = (int)(bh / a.h), head = (int)(bh % a.h);
+  float g[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) g[j] = dq_part[R * D + lane + 32 * j];
+  if (row >= 1 && row <= Lq) {
+    const int64_t p = row - 1;
+    const int jq = (int)(p % a.qw), iq = (int)((p / a.qw) % a.qh), tq = (int)(p / ((int64_t)a.qw * a.qh));
+    const float* de = a.ws_de + R * nep;
+    for (int c = 0; c < ne; ++c) {
+      const float w = de[c];
+      const bf16* Rr = rel_row(a, c, iq, jq, tq);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) g[j] = fmaf(w, __bfloat162float(Rr[lane + 32 * j]), g[j]);
+    }
+  }
+  if (row >= 1) {
+    const bf16* dO = (const bf16*)a.dout + (((int64_t)b * Nq + row) * a.h + head) * D;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g[j] += __bfloat162float(dO[lane + 32 * j]);
+  }
+  bf16* dq = (bf16*)a.dq + R * D;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) dq[lane + 32 * j] = __float2bfloat16_rn(g[j]);
+}
+
+void gemm_defaults(svit_gemm_args& g) {
+  g = svit_gemm_args{};
+  g.dtype = SVIT_BF16;
+  g.impl = 2;
+}
+
+int run_gemm(const svit_gemm_args& g, cudaStream_t st) {
+  if (!svit_gemm_tc_supported(&g)) return SVIT_ENOTSUP;
+  return svit_gemm_tc(&g, st);
+}
+
+}  // namespace
+
+int svit_attn_bwd_tc_supported(const svit_attn_args* a) {
+  if (a->dtype != SVIT_BF16) return 0;
+  if (!a->ws_s || !a->ws_dp || !a->ws_p || !a->ws_ds || !a->ws_dq || !a->sel_bwd) return 0;
+  const int ne = a->kh + a->kw + a->kt;
+  if (ne > MAXE || a->nep < ne || a->nep % 8 || a->nep > MAXE) return 0;
+  const int64_t Nk = 1 + (int64_t)a->kt * a->kh * a->kw + a->O;
+  if (((Nk + 7) / 8) * 8 * 4 + 8 * (MAXE + 4) * 4 > 200 * 1024) return 0;  // key-code table must fit in smem
+  return 1;
+}
+
+int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
+  const int64_t Lq = (int64_t)a->qt * a->qh * a->qw, Lk = (int64_t)a->kt * a->kh * a->kw;
+  const int64_t Nq = 1 + Lq + a->O, Nk = 1 + Lk + a->O;
+  const int64_t Nkp = ((Nk + 7) / 8) * 8;
+  const int BH = a->B * a->h, h = a->h, nep = a->nep;
+  const int64_t rows = (int64_t)BH * Nq;
+  int rc;
+
+  attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep);
+  SVIT_CHECK_LAUNCH();
+
+  svit_gemm_args g;
+  // S = q k^T  (fp32 [BH, Nq, Nkp])
+  gemm_defaults(g);
+  g.A = a->q; g.lda = D; g.strideA = Nq * D;
+  g.B = a->k; g.ldb = D; g.strideB = Nk * D; g.transB = 1;
+  g.C = a->ws_s; g.ldc = Nkp; g.strideC = Nq * Nkp; g.out_dtype = SVIT_F32;
+  g.M = Nq; g.N = Nk; g.K = D; g.batch = BH;
+  if ((rc = run_gemm(g, st))) return rc;
+  // dP = dO v^T : dO is head-merged [B, Nq, h, 96] -> (sample, head) two-level batch index on A
+  gemm_defaults(g);
+  g.A = a->dout; g.lda = (int64_t)h * D; g.strideA = Nq * h * D; g.a_inner = h; g.strideA_inner = D;
+  g.B = a->v; g.ldb = D; g.strideB = Nk * D; g.transB = 1;
+  g.C = a->ws_dp; g.ldc = Nkp; g.strideC = Nq * Nkp; g.out_dtype = SVIT_F32;
+  g.M = Nq; g.N = Nk; g.K = D; g.batch = BH;
+  if ((rc = run_gemm(g, st))) return rc;
+
+  {
+    const size_t smem = (size_t)Nkp * 4 + 8 * (MAXE + 4) * 4;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      SVIT_CUDA(cudaFuncSetAttribute(attn_bwd_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    int64_t ctas = ceil_div64(rows, 8);
+    const int64_t cap = (int64_t)svit_num_sms() * 8;
+    if (ctas > cap) ctas = cap;
+    attn_bwd_softmax_kernel<<<(unsigned)ctas, 256, smem, st>>>(*a, a->ws_s, a->ws_dp, (bf16*)a->ws_p, (bf16*)a->ws_ds,
+                                                             nep, Nkp, rows);
+    SVIT_CHECK_LAUNCH();
+  }
+
+  // dV = P^T dO  (A = P stored [Nq, Nk]: MN-major A; B = dO stored [Nq, 96]: MN-major B)
+  gemm_defaults(g);
+  g.A = a->ws_p; g.lda = Nkp; g.strideA = Nq * Nkp; g.transA = 1;
+  g.B = a->dout; g.ldb = (int64_t)h * D; g.strideB = Nq * h * D; g.b_inner = h; g.strideB_inner = D; g.transB = 0;
+  g.C = a->dv; g.ldc = D; g.strideC = Nk * D; g.out_dtype = SVIT_BF16;
+  g.M = Nk; g.N = D; g.K = Nq; g.batch = BH;
+  if ((rc = run_gemm(g, st))) return rc;
+  // dK = scale dS^T q
+  gemm_defaults(g);
+  g.A = a->ws_ds; g.lda = Nkp; g.strideA = Nq * Nkp; g.transA = 1;
+  g.B = a->q; g.ldb = D; g.strideB = Nq * D; g.transB = 0;
+  g.C = a->dk; g.ldc = D; g.strideC = Nk * D; g.out_dtype = SVIT_BF16;
+  g.M = Nk; g.N = D; g.K = Nq; g.batch = BH; g.alpha = a->scale;
+  if ((rc = run_gemm(g, st))) return rc;
+  // dQ part = scale dS k  (fp32; the table term and the residual are added by the finish kernel)
+  gemm_defaults(g);
+  g.A = a->ws_ds; g.lda = Nkp; g.strideA = Nq * Nkp;
+  g.B = a->k; g.ldb = D; g.strideB = Nk * D; g.transB = 0;
+  g.C = a->ws_dq; g.ldc = D; g.strideC = Nq * D; g.out_dtype = SVIT_F32;
+  g.M = Nq; g.N = D; g.K = Nk; g.batch = BH; g.alpha = a->scale;
+  if ((rc = run_gemm(g, st))) return rc;
+  // dE = dS Sel  (one problem over all B h Nq rows)
+  gemm_defaults(g);
+  g.A = a->ws_ds; g.lda = Nkp;
+  g.B = a->sel_bwd; g.ldb = nep; g.transB = 0;
+  g.C = a->ws_de; g.ldc = nep; g.out_dtype = SVIT_F32;
+  g.M = rows; g.N = nep; g.K = Nk; g.batch = 1;
+  if ((rc = run_gemm(g, st))) return rc;
+
+  attn_bwd_finish_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(*a, a->ws_dq, nep, rows);
+  SVIT_CHECK_LAUNCH();
+  return svit_attn_bwd_drel(a, nep, st);
+}

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(svit_attn_args a) {
 
 // dR[a_idx, c, :] += sum over patch query rows whose coordinate on this axis is a_idx of dE[row][c] * q[row]
 template <typename T>
-__global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, int bh_per_cta) {
+__global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, int bh_per_cta, int estride) {
   const int d = threadIdx.x % D, g = threadIdx.x / D;  // 4 column groups
   const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
   const int64_t Nq = 1 + Lq + a.O;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, in
   const int bh1 = min(bh0 + bh_per_cta, a.B * a.h);
   for (int bh = bh0; bh < bh1; ++bh) {
     const T* q = (const T*)a.q + (int64_t)bh * Nq * D;
-    const float* de = a.ws_de + (int64_t)bh * Nq * ne;
+    const float* de = a.ws_de + (int64_t)bh * Nq * estride;
     for (int u = 0; u < n1; ++u)
       for (int w = 0; w < n2; ++w) {
         int t, i, j;
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, in
         else { t = idx; i = u; j = w; }
         int64_t row = 1 + ((int64_t)t * a.qh + i) * a.qw + j;
         float qv = to_f(q[row * D + d]);
-        const float* der = de + row * ne + coff;
+        const float* der = de + row * estride + coff;
 #pragma unroll
         for (int ci = 0; ci < MAXE / 4; ++ci) {
           int c = g + 4 * ci;
@@ -353,6 +353,17 @@ __global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, in
 }
 
 template <typename T>
+static int launch_drel(const svit_attn_args* a, int estride, cudaStream_t st) {
+  const int BH = a->B * a->h;
+  int chunks = BH < 8 ? BH : 8;
+  int per = (BH + chunks - 1) / chunks;
+  chunks = (BH + per - 1) / per;
+  attn_bwd_drel_kernel<T><<<dim3(a->qh + a->qw + a->qt, chunks), 384, 0, st>>>(*a, per, estride);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+template <typename T>
 static int launch_bwd(const svit_attn_args* a, cudaStream_t st) {
   const int64_t Nq = 1 + (int64_t)a->qt * a->qh * a->qw + a->O;
   const int64_t Nk = 1 + (int64_t)a->kt * a->kh * a->kw + a->O;
@@ -363,12 +374,16 @@ static int launch_bwd(const svit_attn_args* a, cudaStream_t st) {
   SVIT_CHECK_LAUNCH();
   attn_bwd_dkv_kernel<T><<<dim3((unsigned)ceil_div64(Nk, AK), BH), 256, sizeof(BwdKVSmem), st>>>(*a);
   SVIT_CHECK_LAUNCH();
-  int chunks = BH < 8 ? BH : 8;
-  int per = (BH + chunks - 1) / chunks;
-  chunks = (BH + per - 1) / per;
-  attn_bwd_drel_kernel<T><<<dim3(a->qh + a->qw + a->qt, chunks), 384, 0, st>>>(*a, per);
-  SVIT_CHECK_LAUNCH();
-  return 0;
+  return launch_drel<T>(a, a->kh + a->kw + a->kt, st);
+}
+
+int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st);  // attn_bwd_tc.cu
+int svit_attn_bwd_tc_supported(const svit_attn_args* a);
+
+// table-gradient reduction shared with the tensor-core backward (dE rows of `estride` floats)
+int svit_attn_bwd_drel(const svit_attn_args* a, int estride, cudaStream_t st) {
+  if (a->dtype == SVIT_F32) return launch_drel<float>(a, estride, st);
+  return launch_drel<bf16>(a, estride, st);
 }
 
 extern "C" int svit_attn_bwd(const svit_attn_args* a, void* stream) {
@@ -378,6 +393,8 @@ extern "C" int svit_attn_bwd(const svit_attn_args* a, void* stream) {
   if (a->kh + a->kw + a->kt > MAXE) return SVIT_ENOTSUP;
   if (a->B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->impl == 2) return svit_attn_bwd_tc_supported(a) ? svit_attn_bwd_tc(a, st) : SVIT_ENOTSUP;
+  if (a->impl == 0 && svit_attn_bwd_tc_supported(a)) return svit_attn_bwd_tc(a, st);
   if (a->dtype == SVIT_F32) return launch_bwd<float>(a, st);
   if (a->dtype == SVIT_BF16) return launch_bwd<bf16>(a, st);
   return SVIT_EINVAL;

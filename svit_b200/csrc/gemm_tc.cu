@@ -53,7 +53,9 @@ struct EpiArgs {
   int out_f32;
   int splits;  // split-K: > 1 -> fp32 partial sums are accumulated with atomics into a zeroed C
   int batch, b_inner;   // batched GEMM: work item = (batch, K split, output tile)
+  int a_inner;          // A's two-level batch split (1 = flat)
   int64_t strideC;      // elements between consecutive problems' outputs
+  float alpha;          // accumulator scale (applied before the bias)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -95,7 +97,7 @@ __device__ __forceinline__ void store_chunk(const EpiArgs& e, const unsigned cha
                                             int64_t n_base, int64_t M, int64_t N) {
   const int c8 = (lane & 3) * 8;
   const int64_t n = n_base + c8;
-  if (n >= N) return;
+  if (n >= N) return;  // N % 8 != 0: the last unit also writes the zero pad columns up to the next multiple of 8
   float bias[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (e.bias) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
@@ -124,7 +126,7 @@ __device__ __forceinline__ void store_chunk(const EpiArgs& e, const unsigned cha
     const float4 hi = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c8 * 4 + 16);
     float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += bias[i];
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], e.alpha, bias[i]);
     if (e.pre_out) {
       uint4 o = {pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])};
       *reinterpret_cast<uint4*>(e.pre_out + m * e.ldp + n) = o;
@@ -230,16 +232,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int kb1 = kb0 + kb_per < num_kb_all ? kb0 + kb_per : num_kb_all;
         const int m0 = (int)((t / n_tiles) * BM), n0 = (int)((t % n_tiles) * BN);
         const int bo = bi / e.b_inner, bn = bi - bo * e.b_inner;  // B's two-level batch coordinate
+        const int ao = bi / e.a_inner, an = bi - ao * e.a_inner;  // A's
         for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * L::STAGE_BYTES;
           unsigned char* sb = sa + L::A_BYTES;
           tc::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if (!A_MN) {
-            tc::tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, 0, bi);
+            tc::tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, an, ao);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tc::tma_load_4d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * BK, 0, bi);
+            for (int j = 0; j < BM / 64; ++j) tc::tma_load_4d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * BK, an, ao);
           }
           if (!B_MN) {
             tc::tma_load_4d(sb, &tmap_b, &full_bar[stage], kb * BK, n0, bn, bo);
@@ -342,8 +345,9 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
   CUtensorMap ta, tb;
   int rc;
   const uint64_t nb = a->batch > 1 ? (uint64_t)a->batch : 1, bin = (a->batch > 1 && a->b_inner > 1) ? (uint64_t)a->b_inner : 1;
-  if (!A_MN) rc = svit_make_tmap_4d(&ta, a->A, nb, 1, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 0, (uint64_t)a->strideA, BM);
-  else rc = svit_make_tmap_4d(&ta, a->A, nb, 1, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, 0, (uint64_t)a->strideA, BK);
+  const uint64_t ain = (a->batch > 1 && a->a_inner > 1) ? (uint64_t)a->a_inner : 1;
+  if (!A_MN) rc = svit_make_tmap_4d(&ta, a->A, nb / ain, ain, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, (uint64_t)a->strideA_inner, (uint64_t)a->strideA, BM);
+  else rc = svit_make_tmap_4d(&ta, a->A, nb / ain, ain, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, (uint64_t)a->strideA_inner, (uint64_t)a->strideA, BK);
   if (rc) return rc;
   if (!B_MN) rc = svit_make_tmap_4d(&tb, a->B, nb / bin, bin, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, (uint64_t)a->strideB_inner, (uint64_t)a->strideB, BN);
   else rc = svit_make_tmap_4d(&tb, a->B, nb / bin, bin, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, (uint64_t)a->strideB_inner, (uint64_t)a->strideB, BK);
@@ -360,7 +364,8 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
   e.out_f32 = a->out_dtype == SVIT_F32;
   // split-K for the weight-gradient shape (few output tiles, very long reduction): fp32 partials via atomics
   e.splits = 1;
-  e.batch = (int)nb; e.b_inner = (int)bin; e.strideC = a->strideC;
+  e.batch = (int)nb; e.b_inner = (int)bin; e.a_inner = (int)ain; e.strideC = a->strideC;
+  e.alpha = a->alpha == 0.f ? 1.f : a->alpha;
   if (nb == 1) {
     const int64_t tiles0 = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN);
     const int64_t nkb = (a->K + BK - 1) / BK;
@@ -426,19 +431,21 @@ int svit_gemm_tc_supported(const svit_gemm_args* a) {
   if (a->batch > 1) {  // batched form: no epilogue extras except bias, 16-byte aligned problem strides
     if (a->residual || a->gelu_pre || a->pre_out || a->sample_scale || a->act || a->rows_in) return 0;
     if (a->strideA % 8 || a->strideB % 8 || a->strideC % 8 || (a->b_inner > 1 && (a->strideB_inner % 8 || a->batch % a->b_inner))) return 0;
+    if (a->a_inner > 1 && (a->strideA_inner % 8 || a->batch % a->a_inner)) return 0;
   }
   if (a->out_dtype != SVIT_BF16 && a->out_dtype != SVIT_F32) return 0;
   if (a->K < 8 || a->N < 8 || a->M < 1) return 0;
-  if (a->N % 8 || a->lda % 8 || a->ldb % 8) return 0;
+  if (a->lda % 8 || a->ldb % 8) return 0;
+  // ragged N (e.g. the 457 keys of a score matrix): the last 8-column unit of a row also writes zeros into the pad
+  // columns, so the row pitch must cover them; no bias vector to read past
+  if (a->N % 8 && (a->bias || a->ldc < ((a->N + 7) / 8) * 8 || a->rows_in || a->residual || a->gelu_pre || a->pre_out)) return 0;
   if (a->out_dtype == SVIT_BF16 ? (a->ldc % 8) : (a->ldc % 4)) return 0;
   if (!aligned16(a->A) || !aligned16(a->B) || !aligned16(a->C)) return 0;
   if (a->residual && (!aligned16(a->residual) || a->ldr % 8)) return 0;
   if (a->gelu_pre && (!aligned16(a->gelu_pre) || a->ldg % 8)) return 0;
   if (a->pre_out && (!aligned16(a->pre_out) || a->ldp % 8)) return 0;
   if (a->M >= (1ll << 31) || a->N >= (1ll << 31) || a->K >= (1ll << 31)) return 0;
-  // operand extents along the contiguous dim must cover whole 16-byte units for TMA
-  if (!a->transA && (a->K % 8)) return 0;  // (MN-major A: only the row pitch lda must be a 16-byte multiple)
-  if (a->transB ? (a->K % 8) : (a->N % 8)) return 0;
+  // TMA needs 16-byte multiples for the pitches (checked above) only: ragged extents are zero-filled by the copy
   return 1;
 }
 
@@ -446,7 +453,8 @@ int svit_gemm_tc_tma_supported(const svit_gemm_args* a);  // gemm_tc2.cu
 int svit_gemm_tc_tma(const svit_gemm_args* a, cudaStream_t st);
 
 int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st) {
-  if (a->batch <= 1 && svit_gemm_tc_tma_supported(a)) return svit_gemm_tc_tma(a, st);
+  const bool plain_scale = a->alpha == 0.f || a->alpha == 1.f;
+  if (a->batch <= 1 && plain_scale && a->N % 8 == 0 && a->K % 8 == 0 && svit_gemm_tc_tma_supported(a)) return svit_gemm_tc_tma(a, st);
   const bool a_mn = a->transA != 0;  // A stored [K, M]
   const bool b_mn = a->transB == 0;  // B stored [K, N]
   if (!a_mn && !b_mn) return dispatch_bn<false, false>(a, st);

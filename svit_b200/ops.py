@@ -135,8 +135,10 @@ def _call(name, *args, tag=None):
 # --------------------------------------------------------------------------------------------
 def gemm(A, B, out, M, N, K, lda, ldb, ldc, transA=0, transB=1, bias=None, residual=None, ldr=0,
          sample_scale=None, rows_per_sample=0, gelu_pre=None, ldg=0, pre_out=None, ldp=0, act=0,
-         remap=(0, 0, 0), impl=None, batch=0, strideA=0, strideB=0, strideC=0, b_inner=0, strideB_inner=0):
+         remap=(0, 0, 0), impl=None, batch=0, strideA=0, strideB=0, strideC=0, b_inner=0, strideB_inner=0,
+         a_inner=0, strideA_inner=0, alpha=0.0):
     a = GemmArgs()
+    a.a_inner, a.strideA_inner, a.alpha = a_inner, strideA_inner, alpha
     a.batch, a.strideA, a.strideB, a.strideC, a.b_inner, a.strideB_inner = batch, strideA, strideB, strideC, b_inner, strideB_inner
     a.A, a.B, a.C = A.data_ptr(), B.data_ptr(), out.data_ptr()
     a.M, a.N, a.K, a.lda, a.ldb, a.ldc = M, N, K, lda, ldb, ldc
@@ -473,20 +475,60 @@ class _Attention(torch.autograd.Function):
         q_thw, k_thw, O, scale = ctx.geom
         dout = dout.contiguous()
         B, h, Nq, d = q.shape
+        Nk = k.shape[2]
         ne = k_thw[0] + k_thw[1] + k_thw[2]
+        dev = q.device
         a = _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale)
+        # bf16: the contractions run as batched tcgen05 GEMMs (attn_bwd_tc.cu); fp32 parity mode: CUDA-core kernels
+        tc = q.dtype == torch.bfloat16 and _state["attn_impl"] != _lib.IMPL_SIMT and ne <= 64
+        es = (ne + 7) // 8 * 8 if tc else ne
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        dRh = torch.zeros(Rh.shape, dtype=torch.float32, device=q.device)
-        dRw = torch.zeros(Rw.shape, dtype=torch.float32, device=q.device)
-        dRt = torch.zeros(Rt.shape, dtype=torch.float32, device=q.device)
-        ws_e = torch.empty(B, h, Nq, ne, dtype=torch.float32, device=q.device)
-        ws_de = torch.empty(B, h, Nq, ne, dtype=torch.float32, device=q.device)
-        ws_delta = torch.empty(B, h, Nq, dtype=torch.float32, device=q.device)
+        dRh = torch.zeros(Rh.shape, dtype=torch.float32, device=dev)
+        dRw = torch.zeros(Rw.shape, dtype=torch.float32, device=dev)
+        dRt = torch.zeros(Rt.shape, dtype=torch.float32, device=dev)
+        ws_e = torch.empty(B, h, Nq, es, dtype=torch.float32, device=dev)
+        ws_de = torch.empty(B, h, Nq, es, dtype=torch.float32, device=dev)
+        ws_delta = torch.empty(B, h, Nq, dtype=torch.float32, device=dev)
         a.dout, a.dq, a.dk, a.dv = dout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
         a.d_rel_h, a.d_rel_w, a.d_rel_t = dRh.data_ptr(), dRw.data_ptr(), dRt.data_ptr()
         a.ws_e, a.ws_de, a.ws_delta = ws_e.data_ptr(), ws_de.data_ptr(), ws_delta.data_ptr()
-        _call("svit_attn_bwd", C.byref(a), _stream())
+        if tc:
+            Nkp = (Nk + 7) // 8 * 8
+            ws_s = torch.empty(B, h, Nq, Nkp, dtype=torch.float32, device=dev)
+            ws_dp = torch.empty(B, h, Nq, Nkp, dtype=torch.float32, device=dev)
+            ws_p = torch.empty(B, h, Nq, Nkp, dtype=torch.bfloat16, device=dev)
+            ws_ds = torch.empty(B, h, Nq, Nkp, dtype=torch.bfloat16, device=dev)
+            ws_dq = torch.empty(B, h, Nq, d, dtype=torch.float32, device=dev)
+            sel = key_select_table_bwd(tuple(k_thw), O, es, dev)
+            a.ws_s, a.ws_dp, a.ws_p, a.ws_ds, a.ws_dq = (ws_s.data_ptr(), ws_dp.data_ptr(), ws_p.data_ptr(),
+                                                         ws_ds.data_ptr(), ws_dq.data_ptr())
+            a.sel_bwd, a.nep = sel.data_ptr(), es
+        _call("svit_attn_bwd", C.byref(a), _stream(),
+              tag=f"[B{B} h{h} Nq{Nq} Nk{Nk}]" if _prof is not None else None)
         return dq, dk, dv, dRh, dRw, dRt, None, None, None, None, None, None
+
+
+_sel_bwd_cache = {}
+
+
+def key_select_table_bwd(k_thw, O, nep, device) -> torch.Tensor:
+    """0/1 matrix [Nk, nep] (bf16): row n = key n, ones in columns i'(n), kh + j'(n), kh + kw + t'(n) for patch
+    keys, zero rows for cls / object keys.  dS @ Sel = the rel-pos bias gradient dE (attention.py:121-134, 175-181
+    differentiated: the bias of key (t', i', j') is E_h[i'] + E_w[j'] + E_t[t'])."""
+    key = (k_thw, O, nep, str(device))
+    t = _sel_bwd_cache.get(key)
+    if t is None:
+        kt, kh, kw = k_thw
+        Nk = 1 + kt * kh * kw + O
+        sel = torch.zeros(Nk, nep, dtype=torch.float32)
+        p = torch.arange(kt * kh * kw)
+        rows = 1 + p
+        sel[rows, (p // kw) % kh] = 1.0
+        sel[rows, kh + p % kw] = 1.0
+        sel[rows, kh + kw + p // (kw * kh)] = 1.0
+        t = sel.to(device=device, dtype=torch.bfloat16)
+        _sel_bwd_cache[key] = t
+    return t
 
 
 def attention(q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables=None):

@@ -226,3 +226,65 @@ def test_attention_tc_matches_simt(shape, bias_in_mma):
         ops.set_impl(attn=ops.IMPL_AUTO)
     err = max_rel_err(cpu(got), cpu(ref))
     assert err < 1.5e-2, (shape, err)
+
+
+@pytest.mark.parametrize("Bn,h,Nq,Nk", [(2, 4, 1633, 457), (1, 1, 300, 1633), (3, 2, 130, 73)])
+def test_gemm_tc_batched_ragged_scores(Bn, h, Nq, Nk):
+    """Batched score-shaped GEMMs of the attention backward: N (= key count) not a multiple of 8 (pad columns of the
+    fp32 output are written as zeros), A a (sample, head) slice of the head-merged dO, alpha scaling, and a K-major A
+    whose reduction extent (= key count) is ragged."""
+    gen = torch.Generator().manual_seed(Nq * 3 + Nk)
+    Nkp = (Nk + 7) // 8 * 8
+    dO = torch.randn(Bn, Nq, h, 96, generator=gen).to(torch.bfloat16).to(DEV)
+    V = torch.randn(Bn * h, Nk, 96, generator=gen).to(torch.bfloat16).to(DEV)
+    dP = torch.full((Bn * h, Nq, Nkp), float("nan"), dtype=torch.float32, device=DEV)
+    ops.gemm(dO, V, dP, Nq, Nk, 96, h * 96, 96, Nkp, 0, 1, impl=TC, batch=Bn * h, strideA=Nq * h * 96, strideB=Nk * 96,
+             strideC=Nq * Nkp, a_inner=h, strideA_inner=96, alpha=0.5)
+    ref = 0.5 * torch.einsum("bqd,bkd->bqk", dO.float().permute(0, 2, 1, 3).reshape(Bn * h, Nq, 96), V.float())
+    assert not torch.isnan(dP).any()
+    assert max_rel_err(cpu(dP[:, :, :Nk]), cpu(ref)) < 1e-5
+    assert float(dP[:, :, Nk:].abs().max()) == 0.0 if Nkp > Nk else True
+    # dQ-shaped: A = dS [Nq, Nk] with ragged K, B = k stored [Nk, 96] (MN-major)
+    dS = (torch.randn(Bn * h, Nq, Nkp, generator=gen) / Nk ** 0.5).to(torch.bfloat16).to(DEV)
+    dS[:, :, Nk:] = 0
+    dQ = torch.full((Bn * h, Nq, 96), float("nan"), dtype=torch.float32, device=DEV)
+    ops.gemm(dS, V, dQ, Nq, 96, Nk, Nkp, 96, 96, 0, 0, impl=TC, batch=Bn * h, strideA=Nq * Nkp, strideB=Nk * 96,
+             strideC=Nq * 96, alpha=2.0)
+    ref = 2.0 * torch.einsum("bqk,bkd->bqd", dS.float()[:, :, :Nk], V.float())
+    assert max_rel_err(cpu(dQ), cpu(ref)) < 1e-5
+
+
+BWD_SHAPES = [ATTN_SHAPES[i] for i in (0, 2, 3, 4, 6, 9, 10, 12, 14)]
+
+
+@pytest.mark.parametrize("shape", BWD_SHAPES)
+def test_attention_backward_tc_matches_simt(shape):
+    """attn_bwd_tc.cu (batched tcgen05 GEMMs + streaming softmax/dS kernels, bf16) against the CUDA-core fp32
+    backward on the same bf16-rounded inputs: dq, dk, dv and the three rel-pos table gradients."""
+    B, h, q_thw, k_thw, O = shape
+    q, k, v, R, _ = _attn_inputs(B, h, q_thw, k_thw, O, seed=47)
+    scale = 96 ** -0.5
+    gen = torch.Generator().manual_seed(5)
+    Nq = q.shape[2]
+    dout = torch.randn(B, Nq, h * 96, generator=gen).to(torch.bfloat16).to(DEV)
+
+    def run(dtype, impl):
+        ops.set_impl(attn=impl)
+        try:
+            ins = [t.detach().to(dtype).requires_grad_(True) for t in (q, k, v)]
+            Rs = [r.detach().to(torch.bfloat16).float().requires_grad_(True) for r in R]
+            out = ops.attention(ins[0], ins[1], ins[2], Rs[0], Rs[1], Rs[2], q_thw, k_thw, O, scale)
+            out.backward(dout.to(dtype))
+            torch.cuda.synchronize()
+            return [cpu(t.grad) for t in ins + Rs]
+        finally:
+            ops.set_impl(attn=ops.IMPL_AUTO)
+
+    ref = run(torch.float32, ops.IMPL_SIMT)
+    got = run(torch.bfloat16, ops.IMPL_AUTO)
+    for name, g, r in zip(("dq", "dk", "dv", "dRh", "dRw", "dRt"), got, ref):
+        assert torch.isfinite(g).all(), name
+        err = max_rel_err(g, r)
+        # table gradients sum dE = -(dS over the few cls / object keys) over thousands of rows: heavy cancellation on
+        # top of the bf16 rounding of dS, hence the wider bound
+        assert err < (5e-2 if name.startswith("dR") else 2e-2), (shape, name, err)
