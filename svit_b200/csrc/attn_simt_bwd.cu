@@ -307,47 +307,60 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(svit_attn_args a) {
   }
 }
 
-// dR[a_idx, c, :] += sum over patch query rows whose coordinate on this axis is a_idx of dE[row][c] * q[row]
-template <typename T>
-__global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, int bh_per_cta, int estride) {
+// dR[a_idx, c, :] += sum over patch query rows whose coordinate on this axis is a_idx of dE[row][c] * q[row].
+// grid = (table row = target, (b, head), row split): a CTA reduces up to `rows_per_cta` of the target's rows in
+// registers (thread = one of the 96 channels x one of 4 column groups), four rows in flight, then adds its partial
+// sums to the fp32 table gradient with atomics.
+template <typename T, int NC>
+__global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, int estride, int rows_per_cta) {
   const int d = threadIdx.x % D, g = threadIdx.x / D;  // 4 column groups
   const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
   const int64_t Nq = 1 + Lq + a.O;
-  const int ne = a.kh + a.kw + a.kt;
   int idx = blockIdx.x, axis, kn, coff;
   float* dR;
   if (idx < a.qh) { axis = 0; kn = a.kh; coff = 0; dR = a.d_rel_h; }
   else if (idx < a.qh + a.qw) { axis = 1; idx -= a.qh; kn = a.kw; coff = a.kh; dR = a.d_rel_w; }
   else { axis = 2; idx -= a.qh + a.qw; kn = a.kt; coff = a.kh + a.kw; dR = a.d_rel_t; }
-  float acc[MAXE / 4];
-#pragma unroll
-  for (int i = 0; i < MAXE / 4; ++i) acc[i] = 0.f;
-  const int n1 = axis == 0 ? a.qt : (axis == 1 ? a.qt : a.qh);
+  const int n1 = axis == 2 ? a.qh : a.qt;
   const int n2 = axis == 0 ? a.qw : (axis == 1 ? a.qh : a.qw);
-  const int bh0 = blockIdx.y * bh_per_cta;
-  const int bh1 = min(bh0 + bh_per_cta, a.B * a.h);
-  for (int bh = bh0; bh < bh1; ++bh) {
-    const T* q = (const T*)a.q + (int64_t)bh * Nq * D;
-    const float* de = a.ws_de + (int64_t)bh * Nq * estride;
-    for (int u = 0; u < n1; ++u)
-      for (int w = 0; w < n2; ++w) {
-        int t, i, j;
-        if (axis == 0) { t = u; i = idx; j = w; }
-        else if (axis == 1) { t = u; i = w; j = idx; }
-        else { t = idx; i = u; j = w; }
-        int64_t row = 1 + ((int64_t)t * a.qh + i) * a.qw + j;
-        float qv = to_f(q[row * D + d]);
-        const float* der = de + row * estride + coff;
+  const int total = n1 * n2;
+  const int rb = blockIdx.z * rows_per_cta;
+  if (rb >= total) return;
+  const int re = min(total, rb + rows_per_cta);
+  const int bh = blockIdx.y;
+  const T* q = (const T*)a.q + (int64_t)bh * Nq * D + d;
+  const float* de = a.ws_de + (int64_t)bh * Nq * estride + coff + g;
+  float acc[NC];
 #pragma unroll
-        for (int ci = 0; ci < MAXE / 4; ++ci) {
-          int c = g + 4 * ci;
-          if (c < kn) acc[ci] = fmaf(der[c], qv, acc[ci]);
-        }
-      }
+  for (int i = 0; i < NC; ++i) acc[i] = 0.f;
+  auto token = [&](int r) -> int64_t {
+    const int u = r / n2, w = r - u * n2;
+    int t, i, j;
+    if (axis == 0) { t = u; i = idx; j = w; }
+    else if (axis == 1) { t = u; i = w; j = idx; }
+    else { t = idx; i = u; j = w; }
+    return 1 + ((int64_t)t * a.qh + i) * a.qw + j;
+  };
+  constexpr int U = 4;
+  for (int r0 = rb; r0 < re; r0 += U) {
+    float qv[U], dv[U][NC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = r0 + u < re;
+      const int64_t row = token(ok ? r0 + u : r0);
+      qv[u] = ok ? to_f(q[row * D]) : 0.f;
+      const float* der = de + row * estride;
+#pragma unroll
+      for (int ci = 0; ci < NC; ++ci) dv[u][ci] = (g + 4 * ci < kn) ? der[4 * ci] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int ci = 0; ci < NC; ++ci) acc[ci] = fmaf(dv[u][ci], qv[u], acc[ci]);
   }
 #pragma unroll
-  for (int ci = 0; ci < MAXE / 4; ++ci) {
-    int c = g + 4 * ci;
+  for (int ci = 0; ci < NC; ++ci) {
+    const int c = g + 4 * ci;
     if (c < kn) atomicAdd(&dR[((int64_t)idx * kn + c) * D + d], acc[ci]);
   }
 }
@@ -355,10 +368,15 @@ __global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, in
 template <typename T>
 static int launch_drel(const svit_attn_args* a, int estride, cudaStream_t st) {
   const int BH = a->B * a->h;
-  int chunks = BH < 8 ? BH : 8;
-  int per = (BH + chunks - 1) / chunks;
-  chunks = (BH + per - 1) / per;
-  attn_bwd_drel_kernel<T><<<dim3(a->qh + a->qw + a->qt, chunks), 384, 0, st>>>(*a, per, estride);
+  const int kmax = max(a->kh, max(a->kw, a->kt));
+  const int rmax = max(a->qt * a->qw, max(a->qt * a->qh, a->qh * a->qw));
+  const int rows_per_cta = 256;
+  dim3 grid(a->qh + a->qw + a->qt, BH, (rmax + rows_per_cta - 1) / rows_per_cta);
+  if (BH > 65535 || grid.z > 65535) return SVIT_ENOTSUP;
+  if (kmax <= 16)
+    attn_bwd_drel_kernel<T, 4><<<grid, 384, 0, st>>>(*a, estride, rows_per_cta);
+  else
+    attn_bwd_drel_kernel<T, MAXE / 4><<<grid, 384, 0, st>>>(*a, estride, rows_per_cta);
   SVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -198,6 +198,79 @@ __global__ void skip_maxpool_bwd_kernel(const T* __restrict__ x, const T* __rest
   }
 }
 
+// bf16, C % 8 == 0: thread = 8 consecutive channels of one input token (16-byte accesses); same gather as above.
+__global__ void __launch_bounds__(256) skip_maxpool_bwd_vec8_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                                    bf16* __restrict__ dx, int B, int C, int T_, int H,
+                                                                    int W, int Ho, int Wo, int O, int s) {
+  const int C8 = C >> 3;
+  const int64_t Nin = 1 + (int64_t)T_ * H * W + O, Nout = 1 + (int64_t)T_ * Ho * Wo + O;
+  const int64_t total = (int64_t)B * Nin * C8;
+  auto unpack = [](const uint4& v, float f[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      f[2 * u] = __uint_as_float(w[u] << 16);
+      f[2 * u + 1] = __uint_as_float(w[u] & 0xffff0000u);
+    }
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const int64_t r = i / C8;
+    const int64_t tok = r % Nin;
+    const int b = (int)(r / Nin);
+    const bf16* xb = x + (int64_t)b * Nin * C + c;
+    const bf16* dyb = dy + (int64_t)b * Nout * C + c;
+    bf16* o = dx + r * C + c;
+    if (tok == 0) {
+      *reinterpret_cast<uint4*>(o) = __ldg(reinterpret_cast<const uint4*>(dyb));
+      continue;
+    }
+    if (tok > (int64_t)T_ * H * W) {
+      *reinterpret_cast<uint4*>(o) =
+          __ldg(reinterpret_cast<const uint4*>(dyb + (tok - (int64_t)T_ * H * W + (int64_t)T_ * Ho * Wo) * C));
+      continue;
+    }
+    const int64_t p = tok - 1;
+    const int w = (int)(p % W), h = (int)((p / W) % H), t = (int)(p / ((int64_t)W * H));
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ho = (h - 1 + s - 1) / s; ho * s <= h + 1 && ho < Ho; ++ho) {
+      if (ho < 0) continue;
+      for (int wo = (w - 1 + s - 1) / s; wo * s <= w + 1 && wo < Wo; ++wo) {
+        if (wo < 0) continue;
+        // per channel: is (h, w) the first maximum of this window in ATen's scan order (h then w)?
+        float m[8];
+        bool mine[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { m[u] = -INFINITY; mine[u] = false; }
+#pragma unroll
+        for (int dh = -1; dh <= 1; ++dh) {
+          const int hh = ho * s + dh;
+          if (hh < 0 || hh >= H) continue;
+#pragma unroll
+          for (int dw = -1; dw <= 1; ++dw) {
+            const int ww = wo * s + dw;
+            if (ww < 0 || ww >= W) continue;
+            float v[8];
+            unpack(__ldg(reinterpret_cast<const uint4*>(xb + (1 + ((int64_t)t * H + hh) * W + ww) * C)), v);
+            const bool here = hh == h && ww == w;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (v[u] > m[u] || v[u] != v[u]) { m[u] = v[u]; mine[u] = here; }
+          }
+        }
+        float d[8];
+        unpack(__ldg(reinterpret_cast<const uint4*>(dyb + (1 + ((int64_t)t * Ho + ho) * Wo + wo) * C)), d);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) g[u] += mine[u] ? d[u] : 0.f;
+      }
+    }
+    __nv_bfloat162 h2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) h2[u] = __floats2bfloat162_rn(g[2 * u], g[2 * u + 1]);
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h2);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Token assembly (video_model_builder.py:326-363): x[b, 0] = cls; x[b, 1+L + t*O + o] = query[o] + pos_t[t]
 // (no temporal term when Tx == 1).  Patch rows 1..L are written by the patch-embed GEMM epilogue.
@@ -400,6 +473,9 @@ int svit_skip_maxpool_bwd(const void* x, const void* dy, void* dx, int B, int C,
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SVIT_F32)
     skip_maxpool_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (const float*)dy, (float*)dx, B, C, T, H, W, Ho, Wo, O, stride_hw);
+  else if (dtype == SVIT_BF16 && C % 8 == 0 &&
+           ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0)
+    skip_maxpool_bwd_vec8_kernel<<<grid_for(total / 8, 256), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, B, C, T, H, W, Ho, Wo, O, stride_hw);
   else if (dtype == SVIT_BF16)
     skip_maxpool_bwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, B, C, T, H, W, Ho, Wo, O, stride_hw);
   else

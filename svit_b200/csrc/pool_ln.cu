@@ -279,6 +279,13 @@ int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
                           const float* tap_frac, const float* gamma, const float* beta, void* out, int B, int h, int T,
                           int H, int W, int O, int s, float eps, cudaStream_t st);  // pool_ln_tiled.cu
 
+int svit_pool_ln_bwd_bf16_supported(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const void* dout,
+                                    const void* dpre, const void* dz);  // pool_ln_bwd_bf16.cu
+int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const float* conv_w,
+                          const float* tap_frac, const float* gamma, const void* dout, void* dpre, void* dz, float* dw,
+                          float* dgamma, float* dbeta, int B, int h, int T, int H, int W, int O, int s, float eps,
+                          cudaStream_t st);
+
 static int make_geom(PoolGeom& g, int B, int h, int T, int H, int W, int O, int s, int64_t in_bs, int64_t in_ts,
                      int64_t in_hs) {
   if (B < 0 || h < 1 || T < 1 || H < 1 || W < 1 || O < 1 || s < 1) return SVIT_EINVAL;
@@ -333,6 +340,9 @@ int svit_pool_ln_bwd(const void* in, int64_t in_batch_stride, int64_t in_tok_str
   int64_t tok_in = (int64_t)B * h * (1 + (int64_t)T * H * W + O);
   if (tok_out == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SVIT_BF16 && svit_pool_ln_bwd_bf16_supported(in, in_batch_stride, in_tok_stride, in_head_stride, dout, dpre, dz))
+    return svit_pool_ln_bwd_bf16(in, in_batch_stride, in_tok_stride, in_head_stride, conv_w, tap_frac, gamma, dout, dpre,
+                                 dz, dw, dgamma, dbeta, B, h, T, H, W, O, stride_hw, eps, st);
   int g1 = pool_grid(tok_out);
   if (g1 > svit_num_sms() * 2) g1 = svit_num_sms() * 2;
   if (dtype == SVIT_F32) {

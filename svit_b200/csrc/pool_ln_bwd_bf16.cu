@@ -1,0 +1,334 @@
+// Backward of attention_pool (conv pool + LayerNorm, attention.py:13-65) for bf16 activations, vectorised.
+// Three kernels, all reading / writing the packed qkv layout in place:
+//   pre   warp per OUTPUT token, lanes 0..23 own 4 consecutive channels (8-byte accesses): recompute the pre-LN
+//         conv value, LayerNorm backward -> dpre (bf16 scratch), dgamma / dbeta partial sums
+//   dw    thread = (channel pair, temporal tap plane, token parity) marching over a chunk of output tokens:
+//         dw[c][tap] += dpre[tok][c] * z[tok + tap][c] in 18 registers, plus the object-token path
+//         (d w_eff = sum_obj dpre * z_obj, d w[c][tap] += tap_frac[tap] * d w_eff[c]); one atomic per entry and CTA
+//   in    warp per INPUT token: dz = transposed depthwise conv of dpre (patch), dpre (cls), dpre * w_eff (object)
+// HBM-bound in principle (two reads + two writes of the tensors); in practice bound by L2 latency, so the kernels
+// favour wide loads and many resident warps over register-resident accumulators.
+#include "common.cuh"
+
+#define PD 96
+#define TAPS 27
+
+namespace {
+
+struct Geom {
+  int B, h, T, H, W, Ho, Wo, O, s;
+  int64_t in_bs, in_ts, in_hs;
+};
+
+__device__ __forceinline__ void load_weights(const float* __restrict__ w, const float* __restrict__ frac, float* sw,
+                                             float* sweff) {
+  for (int i = threadIdx.x; i < PD * TAPS; i += blockDim.x) {
+    const int c = i / TAPS, t = i % TAPS;
+    sw[t * PD + c] = w[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < PD; c += blockDim.x) {
+    float a = 0.f;
+    for (int t = 0; t < TAPS; ++t) a += sw[t * PD + c] * frac[t];
+    sweff[c] = a;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void unpack4(const uint2 v, float f[4]) {
+  f[0] = __uint_as_float(v.x << 16);
+  f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16);
+  f[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+__device__ __forceinline__ uint2 pack4(const float f[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+__global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restrict__ in, Geom g,
+                                                           const float* __restrict__ w, const float* __restrict__ frac,
+                                                           const float* __restrict__ gamma, const bf16* __restrict__ dout,
+                                                           bf16* __restrict__ dpre, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, float eps) {
+  __shared__ __align__(16) float sw[TAPS * PD];
+  __shared__ __align__(16) float sweff[PD];
+  __shared__ float sred[2 * PD];
+  load_weights(w, frac, sw, sweff);
+  for (int i = threadIdx.x; i < 2 * PD; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < 24;
+  const int c0 = act ? lane * 4 : 0;
+  const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
+  const int64_t Nout = 1 + Lo + g.O;
+  const int64_t total = (int64_t)g.B * g.h * Nout;
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + c0);
+  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  const int wpb = blockDim.x >> 5;
+  for (int64_t i = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * wpb) {
+    const int64_t tok = i % Nout;
+    const int64_t bh = i / Nout;
+    const int head = (int)(bh % g.h), b = (int)(bh / g.h);
+    const bf16* zin = in + b * g.in_bs + head * g.in_hs + c0;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float dy[4];
+    unpack4(act ? __ldg(reinterpret_cast<const uint2*>(dout + i * PD + c0)) : make_uint2(0, 0), dy);
+    if (act) {
+      if (tok == 0) {
+        unpack4(__ldg(reinterpret_cast<const uint2*>(zin)), v);
+      } else if (tok > Lo) {
+        float z[4];
+        unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (tok - Lo + L) * g.in_ts)), z);
+        const float4 we = *reinterpret_cast<const float4*>(sweff + c0);
+        v[0] = z[0] * we.x; v[1] = z[1] * we.y; v[2] = z[2] * we.z; v[3] = z[3] * we.w;
+      } else {
+        const int64_t p = tok - 1;
+        const int wo = (int)(p % g.Wo), ho = (int)((p / g.Wo) % g.Ho), to = (int)(p / ((int64_t)g.Wo * g.Ho));
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          const int t = to - 1 + kt;
+          if (t < 0 || t >= g.T) continue;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const int hh = ho * g.s - 1 + kh;
+            if (hh < 0 || hh >= g.H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int ww = wo * g.s - 1 + kw;
+              if (ww < 0 || ww >= g.W) continue;
+              float z[4];
+              unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (1 + ((int64_t)t * g.H + hh) * g.W + ww) * g.in_ts)), z);
+              const float4 wr = *reinterpret_cast<const float4*>(sw + (kt * 9 + kh * 3 + kw) * PD + c0);
+              v[0] = fmaf(z[0], wr.x, v[0]); v[1] = fmaf(z[1], wr.y, v[1]);
+              v[2] = fmaf(z[2], wr.z, v[2]); v[3] = fmaf(z[3], wr.w, v[3]);
+            }
+          }
+        }
+      }
+    }
+    const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.f / PD);
+    float xh[4], q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      xh[j] = act ? v[j] - mean : 0.f;
+      q += xh[j] * xh[j];
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / PD) + eps);
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w};
+    float gy[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      xh[j] *= rstd;
+      gy[j] = dy[j] * gmv[j];
+      s1 += gy[j];
+      s2 += gy[j] * xh[j];
+      ag[j] += dy[j] * xh[j];
+      ab[j] += dy[j];
+    }
+    s1 = warp_sum(s1) * (1.f / PD);
+    s2 = warp_sum(s2) * (1.f / PD);
+    if (act) {
+      float dp[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dp[j] = rstd * (gy[j] - s1 - xh[j] * s2);
+      *reinterpret_cast<uint2*>(dpre + i * PD + c0) = pack4(dp);
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&sred[c0 + j], ag[j]);
+      atomicAdd(&sred[PD + c0 + j], ab[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < PD; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sred[c]);
+    atomicAdd(&dbeta[c], sred[PD + c]);
+  }
+}
+
+// block = 288 threads: pair = tid % 48 (channels 2 pair, 2 pair + 1), tg = (tid / 48) % 3 (temporal tap plane),
+// half = tid / 144 (token parity inside the chunk).  grid = (chunks, B * h).
+__global__ void __launch_bounds__(288) pool_bwd_dw_kernel(const bf16* __restrict__ in, Geom g,
+                                                          const float* __restrict__ frac, const bf16* __restrict__ dpre,
+                                                          float* __restrict__ dw, int chunk) {
+  __shared__ float sacc[144 * 18];
+  const int pair = threadIdx.x % 48, tg = (threadIdx.x / 48) % 3, half = threadIdx.x / 144;
+  const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
+  const int64_t Nout = 1 + Lo + g.O;
+  const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
+  const bf16* zin = in + b * g.in_bs + head * g.in_hs + 2 * pair;
+  const bf16* dp_base = dpre + (int64_t)bh * Nout * PD + 2 * pair;
+  const int64_t t0 = (int64_t)blockIdx.x * chunk;
+  const int64_t t1 = t0 + chunk < Nout ? t0 + chunk : Nout;
+  float acc[9][2], aweff[2] = {0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = 0.f;
+#pragma unroll 2
+  for (int64_t tok = t0 + half; tok < t1; tok += 2) {
+    if (tok == 0) continue;  // cls passes through: no weight gradient
+    const float2 dp = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp_base + tok * PD));
+    if (tok > Lo) {
+      if (tg == 0) {
+        const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zin + (tok - Lo + L) * g.in_ts));
+        aweff[0] = fmaf(dp.x, z.x, aweff[0]);
+        aweff[1] = fmaf(dp.y, z.y, aweff[1]);
+      }
+      continue;
+    }
+    const int64_t p = tok - 1;
+    const int wo = (int)(p % g.Wo), ho = (int)((p / g.Wo) % g.Ho), to = (int)(p / ((int64_t)g.Wo * g.Ho));
+    const int t = to - 1 + tg;
+    if (t < 0 || t >= g.T) continue;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hh = ho * g.s - 1 + kh;
+      if (hh < 0 || hh >= g.H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ww = wo * g.s - 1 + kw;
+        if (ww < 0 || ww >= g.W) continue;
+        const float2 z = __bfloat1622float2(
+            *reinterpret_cast<const __nv_bfloat162*>(zin + (1 + ((int64_t)t * g.H + hh) * g.W + ww) * g.in_ts));
+        acc[kh * 3 + kw][0] = fmaf(dp.x, z.x, acc[kh * 3 + kw][0]);
+        acc[kh * 3 + kw][1] = fmaf(dp.y, z.y, acc[kh * 3 + kw][1]);
+      }
+    }
+  }
+  // object-token path: every tap of the plane gets tap_frac * d w_eff (tg 0 holds d w_eff; share it through smem)
+  float* swe = sacc;  // [2][48][2] reused before the main reduction
+  if (tg == 0) {
+    swe[(half * 48 + pair) * 2] = aweff[0];
+    swe[(half * 48 + pair) * 2 + 1] = aweff[1];
+  }
+  __syncthreads();
+  if (half == 0) {
+    const float e0 = swe[pair * 2] + swe[(48 + pair) * 2], e1 = swe[pair * 2 + 1] + swe[(48 + pair) * 2 + 1];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float f = frac[tg * 9 + k];
+      acc[k][0] = fmaf(f, e0, acc[k][0]);
+      acc[k][1] = fmaf(f, e1, acc[k][1]);
+    }
+  }
+  __syncthreads();
+  if (half == 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      sacc[(threadIdx.x - 144) * 18 + 2 * k] = acc[k][0];
+      sacc[(threadIdx.x - 144) * 18 + 2 * k + 1] = acc[k][1];
+    }
+  }
+  __syncthreads();
+  if (half == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float a0 = acc[k][0] + sacc[threadIdx.x * 18 + 2 * k], a1 = acc[k][1] + sacc[threadIdx.x * 18 + 2 * k + 1];
+      const int tap = tg * 9 + k;
+      if (a0 != 0.f) atomicAdd(&dw[(2 * pair) * TAPS + tap], a0);
+      if (a1 != 0.f) atomicAdd(&dw[(2 * pair + 1) * TAPS + tap], a1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict__ dpre, Geom g,
+                                                          const float* __restrict__ w, const float* __restrict__ frac,
+                                                          bf16* __restrict__ dz) {
+  __shared__ __align__(16) float sw[TAPS * PD];
+  __shared__ __align__(16) float sweff[PD];
+  load_weights(w, frac, sw, sweff);
+  const int lane = threadIdx.x & 31;
+  if (lane >= 24) return;
+  const int c0 = lane * 4;
+  const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
+  const int64_t Nout = 1 + Lo + g.O, Nin = 1 + L + g.O;
+  const int64_t total = (int64_t)g.B * g.h * Nin;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t i = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * wpb) {
+    const int64_t tok = i % Nin;
+    const int64_t bh = i / Nin;
+    const int head = (int)(bh % g.h), b = (int)(bh / g.h);
+    const bf16* dp = dpre + bh * Nout * PD + c0;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tok == 0) {
+      unpack4(__ldg(reinterpret_cast<const uint2*>(dp)), v);
+    } else if (tok > L) {
+      float z[4];
+      unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (tok - L + Lo) * PD)), z);
+      const float4 we = *reinterpret_cast<const float4*>(sweff + c0);
+      v[0] = z[0] * we.x; v[1] = z[1] * we.y; v[2] = z[2] * we.z; v[3] = z[3] * we.w;
+    } else {
+      const int64_t p = tok - 1;
+      const int ww = (int)(p % g.W), hh = (int)((p / g.W) % g.H), t = (int)(p / ((int64_t)g.W * g.H));
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        const int to = t + 1 - kt;
+        if (to < 0 || to >= g.T) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int num = hh + 1 - kh;
+          if (num < 0 || num % g.s != 0) continue;
+          const int ho = num / g.s;
+          if (ho >= g.Ho) continue;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int numw = ww + 1 - kw;
+            if (numw < 0 || numw % g.s != 0) continue;
+            const int wo = numw / g.s;
+            if (wo >= g.Wo) continue;
+            float z[4];
+            unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (1 + ((int64_t)to * g.Ho + ho) * g.Wo + wo) * PD)), z);
+            const float4 wr = *reinterpret_cast<const float4*>(sw + (kt * 9 + kh * 3 + kw) * PD + c0);
+            v[0] = fmaf(z[0], wr.x, v[0]); v[1] = fmaf(z[1], wr.y, v[1]);
+            v[2] = fmaf(z[2], wr.z, v[2]); v[3] = fmaf(z[3], wr.w, v[3]);
+          }
+        }
+      }
+    }
+    *reinterpret_cast<uint2*>(dz + b * g.in_bs + head * g.in_hs + tok * g.in_ts + c0) = pack4(v);
+  }
+}
+
+inline int grid_for_tokens(int64_t tokens) {
+  int64_t gsz = ceil_div64(tokens, 8);
+  const int64_t cap = (int64_t)svit_num_sms() * 8;
+  return (int)(gsz < cap ? (gsz > 0 ? gsz : 1) : cap);
+}
+
+}  // namespace
+
+int svit_pool_ln_bwd_bf16_supported(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const void* dout,
+                                    const void* dpre, const void* dz) {
+  if (in_bs % 4 || in_ts % 4 || in_hs % 4) return 0;
+  const uintptr_t m = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(dout) |
+                      reinterpret_cast<uintptr_t>(dpre) | reinterpret_cast<uintptr_t>(dz);
+  return (m & 7) == 0;
+}
+
+int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const float* conv_w,
+                          const float* tap_frac, const float* gamma, const void* dout, void* dpre, void* dz, float* dw,
+                          float* dgamma, float* dbeta, int B, int h, int T, int H, int W, int O, int s, float eps,
+                          cudaStream_t st) {
+  Geom g;
+  g.B = B; g.h = h; g.T = T; g.H = H; g.W = W; g.O = O; g.s = s;
+  g.Ho = (H - 1) / s + 1;
+  g.Wo = (W - 1) / s + 1;
+  g.in_bs = in_bs; g.in_ts = in_ts; g.in_hs = in_hs;
+  const int64_t Nout = 1 + (int64_t)T * g.Ho * g.Wo + O, Nin = 1 + (int64_t)T * H * W + O;
+  const int64_t tok_out = (int64_t)B * h * Nout, tok_in = (int64_t)B * h * Nin;
+  if (B * h > 65535) return SVIT_ENOTSUP;
+  pool_bwd_pre_kernel<<<grid_for_tokens(tok_out), 256, 0, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma,
+                                                                (const bf16*)dout, (bf16*)dpre, dgamma, dbeta, eps);
+  SVIT_CHECK_LAUNCH();
+  int64_t chunk = ceil_div64(tok_out, (int64_t)svit_num_sms() * 3);
+  if (chunk < 64) chunk = 64;
+  if (chunk > 2048) chunk = 2048;
+  pool_bwd_dw_kernel<<<dim3((unsigned)ceil_div64(Nout, chunk), (unsigned)(B * h)), 288, 0, st>>>(
+      (const bf16*)in, g, tap_frac, (const bf16*)dpre, dw, (int)chunk);
+  SVIT_CHECK_LAUNCH();
+  pool_bwd_in_kernel<<<grid_for_tokens(tok_in), 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}

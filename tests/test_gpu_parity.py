@@ -439,3 +439,26 @@ def test_full_size_properties_bf16():
     assert torch.allclose(p4.float().sum(1).cpu(), torch.ones(4), atol=1e-3)
     assert e4["obj_desc"].shape == (4, 16, 4, 768) and e4["pred_bboxes"].shape == (4, 16, 4, 5)
     assert e4["pred_contact_state"].shape == (4, 16, 2, 5)
+
+
+@pytest.mark.parametrize("spec", [(2, 192, 2, 9, 11, 5, 2), (1, 96, 3, 14, 14, 8, 2), (1, 384, 1, 7, 8, 4, 2)])
+def test_skip_maxpool_bf16_backward_vectorised(spec):
+    """bf16 skip-path max-pool (attention.py:549-555): forward bit-exact and the 8-channel-per-thread backward equal to
+    ATen's max_pool3d backward (gradient routed to the first maximum in scan order) on the same bf16 values."""
+    B, C, T, H, W, Ot, s = spec
+    g = torch.Generator().manual_seed(C + H)
+    N = 1 + T * H * W + Ot
+    x = torch.randn(B, N, C, generator=g).bfloat16()
+    # ties exercise the first-maximum rule
+    x[:, 1:1 + T * H * W:3] = x[:, 2:2 + T * H * W:3][:, : x[:, 1:1 + T * H * W:3].shape[1]]
+    xd = x.to(DEV).requires_grad_(True)
+    out = ops.skip_pool(xd, (T, H, W), Ot, s)
+    xr = x.float().requires_grad_(True)
+    patch = xr[:, 1:1 + T * H * W].reshape(B, T, H, W, C).permute(0, 4, 1, 2, 3)
+    pooled = torch.nn.functional.max_pool3d(patch, (1, 3, 3), (1, s, s), (0, 1, 1))
+    ref = torch.cat([xr[:, :1], pooled.flatten(2).transpose(1, 2), xr[:, 1 + T * H * W:]], 1)
+    assert torch.equal(cpu(out), ref.detach())
+    gy = torch.randn(ref.shape, generator=g).bfloat16()
+    out.backward(gy.to(DEV))
+    ref.backward(gy.float())
+    assert torch.equal(cpu(xd.grad), xr.grad.bfloat16().float())
