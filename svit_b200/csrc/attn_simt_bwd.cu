@@ -308,12 +308,13 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(svit_attn_args a) {
 }
 
 // dR[a_idx, c, :] += sum over patch query rows whose coordinate on this axis is a_idx of dE[row][c] * q[row].
-// grid = (table row = target, (b, head), row split): a CTA reduces up to `rows_per_cta` of the target's rows in
-// registers (thread = one of the 96 channels x one of 4 column groups), four rows in flight, then adds its partial
-// sums to the fp32 table gradient with atomics.
+// grid = (table row = target, (b, head), row split).  Thread = one of the 96 channels x one of 4 row streams; it
+// keeps all NC columns of its target in registers, so a row costs one q load, NC uniform dE loads and NC FMAs.
+// The four streams are combined in shared memory and added to the fp32 table gradient with coalesced atomics.
 template <typename T, int NC>
 __global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, int estride, int rows_per_cta) {
-  const int d = threadIdx.x % D, g = threadIdx.x / D;  // 4 column groups
+  __shared__ float sred[3][NC][D];
+  const int d = threadIdx.x % D, g = threadIdx.x / D;  // 4 row streams
   const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
   const int64_t Nq = 1 + Lq + a.O;
   int idx = blockIdx.x, axis, kn, coff;
@@ -329,39 +330,33 @@ __global__ void __launch_bounds__(384) attn_bwd_drel_kernel(svit_attn_args a, in
   const int re = min(total, rb + rows_per_cta);
   const int bh = blockIdx.y;
   const T* q = (const T*)a.q + (int64_t)bh * Nq * D + d;
-  const float* de = a.ws_de + (int64_t)bh * Nq * estride + coff + g;
+  const float* de = a.ws_de + (int64_t)bh * Nq * estride + coff;
   float acc[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) acc[i] = 0.f;
-  auto token = [&](int r) -> int64_t {
+#pragma unroll 2
+  for (int r = rb + g; r < re; r += 4) {
     const int u = r / n2, w = r - u * n2;
     int t, i, j;
     if (axis == 0) { t = u; i = idx; j = w; }
     else if (axis == 1) { t = u; i = w; j = idx; }
     else { t = idx; i = u; j = w; }
-    return 1 + ((int64_t)t * a.qh + i) * a.qw + j;
-  };
-  constexpr int U = 4;
-  for (int r0 = rb; r0 < re; r0 += U) {
-    float qv[U], dv[U][NC];
+    const int row = 1 + (t * a.qh + i) * a.qw + j;
+    const float qv = to_f(q[(int64_t)row * D]);
+    const float* der = de + (int64_t)row * estride;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const bool ok = r0 + u < re;
-      const int64_t row = token(ok ? r0 + u : r0);
-      qv[u] = ok ? to_f(q[row * D]) : 0.f;
-      const float* der = de + row * estride;
-#pragma unroll
-      for (int ci = 0; ci < NC; ++ci) dv[u][ci] = (g + 4 * ci < kn) ? der[4 * ci] : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int ci = 0; ci < NC; ++ci) acc[ci] = fmaf(dv[u][ci], qv[u], acc[ci]);
+    for (int c = 0; c < NC; ++c)
+      if (c < kn) acc[c] = fmaf(der[c], qv, acc[c]);
   }
+  if (g > 0) {
 #pragma unroll
-  for (int ci = 0; ci < NC; ++ci) {
-    const int c = g + 4 * ci;
-    if (c < kn) atomicAdd(&dR[((int64_t)idx * kn + c) * D + d], acc[ci]);
+    for (int c = 0; c < NC; ++c) sred[g - 1][c][d] = acc[c];
+  }
+  __syncthreads();
+  if (g == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c < kn) atomicAdd(&dR[((int64_t)idx * kn + c) * D + d], acc[c] + sred[0][c][d] + sred[1][c][d] + sred[2][c][d]);
   }
 }
 
@@ -370,13 +365,17 @@ static int launch_drel(const svit_attn_args* a, int estride, cudaStream_t st) {
   const int BH = a->B * a->h;
   const int kmax = max(a->kh, max(a->kw, a->kt));
   const int rmax = max(a->qt * a->qw, max(a->qt * a->qh, a->qh * a->qw));
-  const int rows_per_cta = 256;
+  const int rows_per_cta = 128;
   dim3 grid(a->qh + a->qw + a->qt, BH, (rmax + rows_per_cta - 1) / rows_per_cta);
   if (BH > 65535 || grid.z > 65535) return SVIT_ENOTSUP;
-  if (kmax <= 16)
-    attn_bwd_drel_kernel<T, 4><<<grid, 384, 0, st>>>(*a, estride, rows_per_cta);
+  if (kmax <= 8)
+    attn_bwd_drel_kernel<T, 8><<<grid, 384, 0, st>>>(*a, estride, rows_per_cta);
+  else if (kmax <= 16)
+    attn_bwd_drel_kernel<T, 16><<<grid, 384, 0, st>>>(*a, estride, rows_per_cta);
+  else if (kmax <= 32)
+    attn_bwd_drel_kernel<T, 32><<<grid, 384, 0, st>>>(*a, estride, rows_per_cta);
   else
-    attn_bwd_drel_kernel<T, MAXE / 4><<<grid, 384, 0, st>>>(*a, estride, rows_per_cta);
+    return SVIT_ENOTSUP;
   SVIT_CHECK_LAUNCH();
   return 0;
 }

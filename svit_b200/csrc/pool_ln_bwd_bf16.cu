@@ -60,17 +60,15 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
   const int lane = threadIdx.x & 31;
   const bool act = lane < 24;
   const int c0 = act ? lane * 4 : 0;
-  const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
-  const int64_t Nout = 1 + Lo + g.O;
-  const int64_t total = (int64_t)g.B * g.h * Nout;
+  const int Lo = g.T * g.Ho * g.Wo, L = g.T * g.H * g.W;
+  const int Nout = 1 + Lo + g.O;
   const float4 gm = *reinterpret_cast<const float4*>(gamma + c0);
   float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
   const int wpb = blockDim.x >> 5;
-  for (int64_t i = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * wpb) {
-    const int64_t tok = i % Nout;
-    const int64_t bh = i / Nout;
-    const int head = (int)(bh % g.h), b = (int)(bh / g.h);
-    const bf16* zin = in + b * g.in_bs + head * g.in_hs + c0;
+  const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
+  const bf16* zin = in + b * g.in_bs + head * g.in_hs + c0;
+  for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < Nout; tok += gridDim.x * wpb) {
+    const int64_t i = (int64_t)bh * Nout + tok;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     float dy[4];
     unpack4(act ? __ldg(reinterpret_cast<const uint2*>(dout + i * PD + c0)) : make_uint2(0, 0), dy);
@@ -79,12 +77,13 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
         unpack4(__ldg(reinterpret_cast<const uint2*>(zin)), v);
       } else if (tok > Lo) {
         float z[4];
-        unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (tok - Lo + L) * g.in_ts)), z);
+        unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (int64_t)(tok - Lo + L) * g.in_ts)), z);
         const float4 we = *reinterpret_cast<const float4*>(sweff + c0);
         v[0] = z[0] * we.x; v[1] = z[1] * we.y; v[2] = z[2] * we.z; v[3] = z[3] * we.w;
       } else {
-        const int64_t p = tok - 1;
-        const int wo = (int)(p % g.Wo), ho = (int)((p / g.Wo) % g.Ho), to = (int)(p / ((int64_t)g.Wo * g.Ho));
+        const unsigned p = tok - 1;
+        const unsigned pr = p / (unsigned)g.Wo;
+        const int wo = (int)(p - pr * g.Wo), to = (int)(pr / (unsigned)g.Ho), ho = (int)(pr - to * g.Ho);
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
           const int t = to - 1 + kt;
@@ -98,7 +97,7 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
               const int ww = wo * g.s - 1 + kw;
               if (ww < 0 || ww >= g.W) continue;
               float z[4];
-              unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (1 + ((int64_t)t * g.H + hh) * g.W + ww) * g.in_ts)), z);
+              unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (int64_t)(1 + (t * g.H + hh) * g.W + ww) * g.in_ts)), z);
               const float4 wr = *reinterpret_cast<const float4*>(sw + (kt * 9 + kh * 3 + kw) * PD + c0);
               v[0] = fmaf(z[0], wr.x, v[0]); v[1] = fmaf(z[1], wr.y, v[1]);
               v[2] = fmaf(z[2], wr.z, v[2]); v[3] = fmaf(z[3], wr.w, v[3]);
@@ -156,30 +155,31 @@ __global__ void __launch_bounds__(288) pool_bwd_dw_kernel(const bf16* __restrict
                                                           float* __restrict__ dw, int chunk) {
   __shared__ float sacc[144 * 18];
   const int pair = threadIdx.x % 48, tg = (threadIdx.x / 48) % 3, half = threadIdx.x / 144;
-  const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
-  const int64_t Nout = 1 + Lo + g.O;
+  const int Lo = g.T * g.Ho * g.Wo, L = g.T * g.H * g.W;
+  const int Nout = 1 + Lo + g.O;
   const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
   const bf16* zin = in + b * g.in_bs + head * g.in_hs + 2 * pair;
   const bf16* dp_base = dpre + (int64_t)bh * Nout * PD + 2 * pair;
-  const int64_t t0 = (int64_t)blockIdx.x * chunk;
-  const int64_t t1 = t0 + chunk < Nout ? t0 + chunk : Nout;
+  const int t0 = blockIdx.x * chunk;
+  const int t1 = t0 + chunk < Nout ? t0 + chunk : Nout;
   float acc[9][2], aweff[2] = {0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = 0.f;
 #pragma unroll 2
-  for (int64_t tok = t0 + half; tok < t1; tok += 2) {
+  for (int tok = t0 + half; tok < t1; tok += 2) {
     if (tok == 0) continue;  // cls passes through: no weight gradient
-    const float2 dp = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp_base + tok * PD));
+    const float2 dp = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp_base + (int64_t)tok * PD));
     if (tok > Lo) {
       if (tg == 0) {
-        const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zin + (tok - Lo + L) * g.in_ts));
+        const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zin + (int64_t)(tok - Lo + L) * g.in_ts));
         aweff[0] = fmaf(dp.x, z.x, aweff[0]);
         aweff[1] = fmaf(dp.y, z.y, aweff[1]);
       }
       continue;
     }
-    const int64_t p = tok - 1;
-    const int wo = (int)(p % g.Wo), ho = (int)((p / g.Wo) % g.Ho), to = (int)(p / ((int64_t)g.Wo * g.Ho));
+    const unsigned p = tok - 1;
+    const unsigned pr = p / (unsigned)g.Wo;
+    const int wo = (int)(p - pr * g.Wo), to = (int)(pr / (unsigned)g.Ho), ho = (int)(pr - to * g.Ho);
     const int t = to - 1 + tg;
     if (t < 0 || t >= g.T) continue;
 #pragma unroll
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(288) pool_bwd_dw_kernel(const bf16* __restrict
         const int ww = wo * g.s - 1 + kw;
         if (ww < 0 || ww >= g.W) continue;
         const float2 z = __bfloat1622float2(
-            *reinterpret_cast<const __nv_bfloat162*>(zin + (1 + ((int64_t)t * g.H + hh) * g.W + ww) * g.in_ts));
+            *reinterpret_cast<const __nv_bfloat162*>(zin + (int64_t)(1 + (t * g.H + hh) * g.W + ww) * g.in_ts));
         acc[kh * 3 + kw][0] = fmaf(dp.x, z.x, acc[kh * 3 + kw][0]);
         acc[kh * 3 + kw][1] = fmaf(dp.y, z.y, acc[kh * 3 + kw][1]);
       }
@@ -222,17 +222,31 @@ __global__ void __launch_bounds__(288) pool_bwd_dw_kernel(const bf16* __restrict
     }
   }
   __syncthreads();
+  // combine the two halves in place, laid out like dw ([channel][tap]) so that the global atomics of a warp fall on
+  // consecutive addresses (one L2 transaction per 128-byte line instead of one per element)
+  __syncthreads();
+  float* sdw = sacc;  // [96 * 27], written by half 0 after reading its partner's partials
+  float mine[9][2];
   if (half == 0) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float a0 = acc[k][0] + sacc[threadIdx.x * 18 + 2 * k], a1 = acc[k][1] + sacc[threadIdx.x * 18 + 2 * k + 1];
-      const int tap = tg * 9 + k;
-      if (a0 != 0.f) atomicAdd(&dw[(2 * pair) * TAPS + tap], a0);
-      if (a1 != 0.f) atomicAdd(&dw[(2 * pair + 1) * TAPS + tap], a1);
+      mine[k][0] = acc[k][0] + sacc[threadIdx.x * 18 + 2 * k];
+      mine[k][1] = acc[k][1] + sacc[threadIdx.x * 18 + 2 * k + 1];
     }
   }
+  __syncthreads();
+  if (half == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      sdw[(2 * pair) * TAPS + tg * 9 + k] = mine[k][0];
+      sdw[(2 * pair + 1) * TAPS + tg * 9 + k] = mine[k][1];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PD * TAPS; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
 }
 
+template <int LS>  // log2(stride) for power-of-two strides, -1 = generic
 __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict__ dpre, Geom g,
                                                           const float* __restrict__ w, const float* __restrict__ frac,
                                                           bf16* __restrict__ dz) {
@@ -242,26 +256,26 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
   const int lane = threadIdx.x & 31;
   if (lane >= 24) return;
   const int c0 = lane * 4;
-  const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
-  const int64_t Nout = 1 + Lo + g.O, Nin = 1 + L + g.O;
-  const int64_t total = (int64_t)g.B * g.h * Nin;
+  const int Lo = g.T * g.Ho * g.Wo, L = g.T * g.H * g.W;
+  const int Nout = 1 + Lo + g.O, Nin = 1 + L + g.O;
   const int wpb = blockDim.x >> 5;
-  for (int64_t i = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * wpb) {
-    const int64_t tok = i % Nin;
-    const int64_t bh = i / Nin;
-    const int head = (int)(bh % g.h), b = (int)(bh / g.h);
-    const bf16* dp = dpre + bh * Nout * PD + c0;
+  const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
+  const bf16* dp = dpre + (int64_t)bh * Nout * PD + c0;
+  bf16* dzb = dz + b * g.in_bs + head * g.in_hs + c0;
+  const int smask = (1 << LS) - 1;
+  for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < Nin; tok += gridDim.x * wpb) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (tok == 0) {
       unpack4(__ldg(reinterpret_cast<const uint2*>(dp)), v);
     } else if (tok > L) {
       float z[4];
-      unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (tok - L + Lo) * PD)), z);
+      unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (int64_t)(tok - L + Lo) * PD)), z);
       const float4 we = *reinterpret_cast<const float4*>(sweff + c0);
       v[0] = z[0] * we.x; v[1] = z[1] * we.y; v[2] = z[2] * we.z; v[3] = z[3] * we.w;
     } else {
-      const int64_t p = tok - 1;
-      const int ww = (int)(p % g.W), hh = (int)((p / g.W) % g.H), t = (int)(p / ((int64_t)g.W * g.H));
+      const unsigned p = tok - 1;
+      const unsigned pr = p / (unsigned)g.W;
+      const int ww = (int)(p - pr * g.W), t = (int)(pr / (unsigned)g.H), hh = (int)(pr - t * g.H);
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
         const int to = t + 1 - kt;
@@ -269,17 +283,17 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
           const int num = hh + 1 - kh;
-          if (num < 0 || num % g.s != 0) continue;
-          const int ho = num / g.s;
+          if (num < 0 || (LS >= 0 ? (num & smask) != 0 : num % g.s != 0)) continue;
+          const int ho = LS >= 0 ? num >> LS : num / g.s;
           if (ho >= g.Ho) continue;
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const int numw = ww + 1 - kw;
-            if (numw < 0 || numw % g.s != 0) continue;
-            const int wo = numw / g.s;
+            if (numw < 0 || (LS >= 0 ? (numw & smask) != 0 : numw % g.s != 0)) continue;
+            const int wo = LS >= 0 ? numw >> LS : numw / g.s;
             if (wo >= g.Wo) continue;
             float z[4];
-            unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (1 + ((int64_t)to * g.Ho + ho) * g.Wo + wo) * PD)), z);
+            unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (int64_t)(1 + (to * g.Ho + ho) * g.Wo + wo) * PD)), z);
             const float4 wr = *reinterpret_cast<const float4*>(sw + (kt * 9 + kh * 3 + kw) * PD + c0);
             v[0] = fmaf(z[0], wr.x, v[0]); v[1] = fmaf(z[1], wr.y, v[1]);
             v[2] = fmaf(z[2], wr.z, v[2]); v[3] = fmaf(z[3], wr.w, v[3]);
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
         }
       }
     }
-    *reinterpret_cast<uint2*>(dz + b * g.in_bs + head * g.in_hs + tok * g.in_ts + c0) = pack4(v);
+    *reinterpret_cast<uint2*>(dzb + (int64_t)tok * g.in_ts) = pack4(v);
   }
 }
 
@@ -318,17 +332,30 @@ int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   g.in_bs = in_bs; g.in_ts = in_ts; g.in_hs = in_hs;
   const int64_t Nout = 1 + (int64_t)T * g.Ho * g.Wo + O, Nin = 1 + (int64_t)T * H * W + O;
   const int64_t tok_out = (int64_t)B * h * Nout, tok_in = (int64_t)B * h * Nin;
-  if (B * h > 65535) return SVIT_ENOTSUP;
-  pool_bwd_pre_kernel<<<grid_for_tokens(tok_out), 256, 0, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma,
+  if (B * h > 65535 || Nin >= (1ll << 30)) return SVIT_ENOTSUP;
+  (void)tok_out; (void)tok_in;
+  const unsigned BH = (unsigned)(B * h);
+  auto gx = [&](int64_t n) {  // CTAs along x so that x * BH is about 8 CTAs per SM, 8 tokens per CTA pass
+    int64_t want = ceil_div64((int64_t)svit_num_sms() * 8, BH), need = ceil_div64(n, 8);
+    return (unsigned)(need < want ? need : want);
+  };
+  pool_bwd_pre_kernel<<<dim3(gx(Nout), BH), 256, 0, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma,
                                                                 (const bf16*)dout, (bf16*)dpre, dgamma, dbeta, eps);
   SVIT_CHECK_LAUNCH();
-  int64_t chunk = ceil_div64(tok_out, (int64_t)svit_num_sms() * 3);
-  if (chunk < 64) chunk = 64;
+  int64_t chunk = ceil_div64(tok_out, (int64_t)svit_num_sms() * 8);  // ~8 CTAs (72 warps) per SM: latency-bound loop
+  if (chunk < 32) chunk = 32;
   if (chunk > 2048) chunk = 2048;
   pool_bwd_dw_kernel<<<dim3((unsigned)ceil_div64(Nout, chunk), (unsigned)(B * h)), 288, 0, st>>>(
       (const bf16*)in, g, tap_frac, (const bf16*)dpre, dw, (int)chunk);
   SVIT_CHECK_LAUNCH();
-  pool_bwd_in_kernel<<<grid_for_tokens(tok_in), 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz);
+  const dim3 gin(gx(Nin), BH);
+  switch (s) {
+    case 1: pool_bwd_in_kernel<0><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
+    case 2: pool_bwd_in_kernel<1><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
+    case 4: pool_bwd_in_kernel<2><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
+    case 8: pool_bwd_in_kernel<3><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
+    default: pool_bwd_in_kernel<-1><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
+  }
   SVIT_CHECK_LAUNCH();
   return 0;
 }
