@@ -150,7 +150,7 @@ typedef struct svit_attn_args {
    * run as batched tcgen05 GEMMs.  Nkp = Nk rounded up to 8; nep = kh+kw+kt rounded up to 8 (<= 64); with these,
    * ws_e and ws_de are [B,h,Nq,nep].  sel_bwd [Nk, nep] (activation dtype): row n = key n with ones in columns
    * i'(n), kh + j'(n), kh + kw + t'(n) for patch keys, zero rows for cls / object keys. */
-  float* ws_s;      /* scratch fp32 [B,h,Nq,Nkp]: q k^T */
+  float* ws_s;      /* scratch fp32 [B,h,Nq,Nkp]: q k^T; ws_s / ws_dp may be NULL when Nk <= 4096 (fused kernel) */
   float* ws_dp;     /* scratch fp32 [B,h,Nq,Nkp]: dO v^T */
   void* ws_p;       /* scratch bf16 [B,h,Nq,Nkp]: softmax probabilities */
   void* ws_ds;      /* scratch bf16 [B,h,Nq,Nkp]: dS */

@@ -22,6 +22,8 @@
 int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st);  // gemm_tc.cu
 int svit_gemm_tc_supported(const svit_gemm_args* a);
 int svit_attn_bwd_drel(const svit_attn_args* a, int estride, cudaStream_t st);  // attn_simt_bwd.cu
+int svit_attn_bwd_sdp_supported(const svit_attn_args* a);                         // attn_bwd_sdp.cu
+int svit_attn_bwd_sdp(const svit_attn_args* a, cudaStream_t st);
 
 namespace {
 
@@ -206,7 +208,8 @@ int run_gemm(const svit_gemm_args& g, cudaStream_t st) {
 
 int svit_attn_bwd_tc_supported(const svit_attn_args* a) {
   if (a->dtype != SVIT_BF16) return 0;
-  if (!a->ws_s || !a->ws_dp || !a->ws_p || !a->ws_ds || !a->ws_dq || !a->sel_bwd) return 0;
+  if (!a->ws_p || !a->ws_ds || !a->ws_dq || !a->sel_bwd) return 0;
+  if ((!a->ws_s || !a->ws_dp) && !svit_attn_bwd_sdp_supported(a)) return 0;  // fp32 scratch only for the unfused path
   const int ne = a->kh + a->kw + a->kt;
   if (ne > MAXE || a->nep < ne || a->nep % 8 || a->nep > MAXE) return 0;
   const int64_t Nk = 1 + (int64_t)a->kt * a->kh * a->kw + a->O;
@@ -226,34 +229,40 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
   SVIT_CHECK_LAUNCH();
 
   svit_gemm_args g;
-  // S = q k^T  (fp32 [BH, Nq, Nkp])
-  gemm_defaults(g);
-  g.A = a->q; g.lda = D; g.strideA = Nq * D;
-  g.B = a->k; g.ldb = D; g.strideB = Nk * D; g.transB = 1;
-  g.C = a->ws_s; g.ldc = Nkp; g.strideC = Nq * Nkp; g.out_dtype = SVIT_F32;
-  g.M = Nq; g.N = Nk; g.K = D; g.batch = BH;
-  if ((rc = run_gemm(g, st))) return rc;
-  // dP = dO v^T : dO is head-merged [B, Nq, h, 96] -> (sample, head) two-level batch index on A
-  gemm_defaults(g);
-  g.A = a->dout; g.lda = (int64_t)h * D; g.strideA = Nq * h * D; g.a_inner = h; g.strideA_inner = D;
-  g.B = a->v; g.ldb = D; g.strideB = Nk * D; g.transB = 1;
-  g.C = a->ws_dp; g.ldc = Nkp; g.strideC = Nq * Nkp; g.out_dtype = SVIT_F32;
-  g.M = Nq; g.N = Nk; g.K = D; g.batch = BH;
-  if ((rc = run_gemm(g, st))) return rc;
+  if (!(a->ws_s && a->ws_dp) && svit_attn_bwd_sdp_supported(a)) {
+    // S, dP, softmax and dS in one tcgen05 kernel: the fp32 matrices stay in TMEM (callers that pass the fp32 scratch
+    // ask for the unfused path: key counts beyond the fused kernel's table, and the tests that compare the two)
+    if ((rc = svit_attn_bwd_sdp(a, st))) return rc;
+  } else {
+    // S = q k^T  (fp32 [BH, Nq, Nkp])
+    gemm_defaults(g);
+    g.A = a->q; g.lda = D; g.strideA = Nq * D;
+    g.B = a->k; g.ldb = D; g.strideB = Nk * D; g.transB = 1;
+    g.C = a->ws_s; g.ldc = Nkp; g.strideC = Nq * Nkp; g.out_dtype = SVIT_F32;
+    g.M = Nq; g.N = Nk; g.K = D; g.batch = BH;
+    if ((rc = run_gemm(g, st))) return rc;
+    // dP = dO v^T : dO is head-merged [B, Nq, h, 96] -> (sample, head) two-level batch index on A
+    gemm_defaults(g);
+    g.A = a->dout; g.lda = (int64_t)h * D; g.strideA = Nq * h * D; g.a_inner = h; g.strideA_inner = D;
+    g.B = a->v; g.ldb = D; g.strideB = Nk * D; g.transB = 1;
+    g.C = a->ws_dp; g.ldc = Nkp; g.strideC = Nq * Nkp; g.out_dtype = SVIT_F32;
+    g.M = Nq; g.N = Nk; g.K = D; g.batch = BH;
+    if ((rc = run_gemm(g, st))) return rc;
 
-  {
-    const size_t smem = (size_t)Nkp * 4 + 8 * (MAXE + 4) * 4;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      SVIT_CUDA(cudaFuncSetAttribute(attn_bwd_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
+    {
+      const size_t smem = (size_t)Nkp * 4 + 8 * (MAXE + 4) * 4;
+      static size_t configured = 0;
+      if (smem > 48 * 1024 && smem > configured) {
+        SVIT_CUDA(cudaFuncSetAttribute(attn_bwd_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+      }
+      int64_t ctas = ceil_div64(rows, 8);
+      const int64_t cap = (int64_t)svit_num_sms() * 8;
+      if (ctas > cap) ctas = cap;
+      attn_bwd_softmax_kernel<<<(unsigned)ctas, 256, smem, st>>>(*a, a->ws_s, a->ws_dp, (bf16*)a->ws_p, (bf16*)a->ws_ds,
+                                                               nep, Nkp, rows);
+      SVIT_CHECK_LAUNCH();
     }
-    int64_t ctas = ceil_div64(rows, 8);
-    const int64_t cap = (int64_t)svit_num_sms() * 8;
-    if (ctas > cap) ctas = cap;
-    attn_bwd_softmax_kernel<<<(unsigned)ctas, 256, smem, st>>>(*a, a->ws_s, a->ws_dp, (bf16*)a->ws_p, (bf16*)a->ws_ds,
-                                                             nep, Nkp, rows);
-    SVIT_CHECK_LAUNCH();
   }
 
   // dV = P^T dO  (A = P stored [Nq, Nk]: MN-major A; B = dO stored [Nq, 96]: MN-major B)

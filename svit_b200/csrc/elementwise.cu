@@ -105,6 +105,95 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   }
 }
 
+// bf16, C % 8 == 0, C <= 256 * NV8: warp per row, lane owns the 8-channel units lane, lane + 32, ... (16-byte accesses).
+template <int NV8>
+__global__ void __launch_bounds__(256) layernorm_bwd_bf16x8_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ mean_in,
+                                                                   const float* __restrict__ rstd_in, bf16* __restrict__ dx,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                   int64_t rows, int C) {
+  __shared__ float sg[NV8 * 256], sb[NV8 * 256];
+  const int lane = threadIdx.x & 31;
+  const int n8 = C >> 3;
+  float gm[NV8][8], ag[NV8][8], ab[NV8][8];
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int u = lane + 32 * i;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gm[i][e] = u < n8 ? gamma[u * 8 + e] : 0.f;
+      ag[i][e] = ab[i][e] = 0.f;
+    }
+  }
+  auto unpack = [](const uint4& v, float f[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      f[2 * e] = __uint_as_float(w[e] << 16);
+      f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+  };
+  const float invC = 1.f / (float)C;
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (; row < rows; row += stride) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[NV8][8], g[NV8][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) {
+      const int u = lane + 32 * i;
+      if (u < n8) {
+        float d[8], xv[8];
+        unpack(__ldg(reinterpret_cast<const uint4*>(dy + row * C + u * 8)), d);
+        unpack(__ldg(reinterpret_cast<const uint4*>(x + row * C + u * 8)), xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[i][e] = (xv[e] - mean) * rstd;
+          g[i][e] = d[e] * gm[i][e];
+          s1 += g[i][e];
+          s2 = fmaf(g[i][e], xh[i][e], s2);
+          ag[i][e] = fmaf(d[e], xh[i][e], ag[i][e]);
+          ab[i][e] += d[e];
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) {
+      const int u = lane + 32 * i;
+      if (u < n8) {
+        __nv_bfloat162 h2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          h2[e] = __floats2bfloat162_rn(rstd * (g[i][2 * e] - s1 - xh[i][2 * e] * s2),
+                                        rstd * (g[i][2 * e + 1] - s1 - xh[i][2 * e + 1] * s2));
+        *reinterpret_cast<uint4*>(dx + row * C + u * 8) = *reinterpret_cast<uint4*>(h2);
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sg[i] = sb[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int u = lane + 32 * i;
+    if (u < n8) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&sg[u * 8 + e], ag[i][e]);
+        atomicAdd(&sb[u * 8 + e], ab[i][e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&dgamma[i], sg[i]);
+    atomicAdd(&dbeta[i], sb[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Skip-path pooling (attention.py:562-564): MaxPool3d k(1,3,3) s(1,2,2) p(0,1,1) on the patch tokens
 // of a [B, N, C] sequence; cls row and object tail copied.  One thread per (token, channel).
@@ -432,7 +521,13 @@ int svit_layernorm_bwd(const void* dy, const void* x, const float* gamma, const 
   if (dtype == SVIT_F32)
     layernorm_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)x, gamma, mean, rstd, (float*)dx,
                                                       dgamma, dbeta, rows, C);
-  else if (dtype == SVIT_BF16)
+  else if (dtype == SVIT_BF16 && C % 8 == 0 && C <= 768 &&
+           ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+    const bf16 *dyb = (const bf16*)dy, *xb = (const bf16*)x;
+    if (C <= 256) layernorm_bwd_bf16x8_kernel<1><<<grid, 256, 0, st>>>(dyb, xb, gamma, mean, rstd, (bf16*)dx, dgamma, dbeta, rows, C);
+    else if (C <= 512) layernorm_bwd_bf16x8_kernel<2><<<grid, 256, 0, st>>>(dyb, xb, gamma, mean, rstd, (bf16*)dx, dgamma, dbeta, rows, C);
+    else layernorm_bwd_bf16x8_kernel<3><<<grid, 256, 0, st>>>(dyb, xb, gamma, mean, rstd, (bf16*)dx, dgamma, dbeta, rows, C);
+  } else if (dtype == SVIT_BF16)
     layernorm_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (bf16*)dx,
                                                      dgamma, dbeta, rows, C);
   else

@@ -130,9 +130,10 @@ __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restri
   const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
-  for (int c8 = blockIdx.x * tpr + tx; c8 < n8; c8 += gridDim.x * tpr) {
+  for (int c8_0 = blockIdx.x * tpr; c8_0 < n8; c8_0 += gridDim.x * tpr) {  // uniform trip count: barriers inside
+    const int c8 = c8_0 + tx;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (ty < rg) {
+    if (ty < rg && c8 < n8) {
 #pragma unroll 4
       for (int64_t r = r0 + ty; r < r1; r += rg) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * ld + c8 * 8));
@@ -147,13 +148,14 @@ __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restri
 #pragma unroll
     for (int u = 0; u < 8; ++u) red[threadIdx.x * 8 + u] = acc[u];
     __syncthreads();
-    if (ty == 0) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float sum = 0.f;
-        for (int g = 0; g < rg; ++g) sum += red[(g * tpr + tx) * 8 + u];
-        atomicAdd(&out[c8 * 8 + u], sum);
-      }
+    // column sums of this CTA's column block, then atomics on consecutive addresses (a warp = one 128-byte line:
+    // same-line atomics serialise in L2 at ~10 ns per transaction, so one transaction per line and CTA)
+    const int ncols = min(tpr, n8 - c8_0) * 8;
+    for (int n = threadIdx.x; n < ncols; n += blockDim.x) {
+      const int t = n >> 3, u = n & 7;
+      float sum = 0.f;
+      for (int g = 0; g < rg; ++g) sum += red[(g * tpr + t) * 8 + u];
+      atomicAdd(&out[c8_0 * 8 + n], sum);
     }
     __syncthreads();
   }

@@ -494,14 +494,15 @@ class _Attention(torch.autograd.Function):
         a.ws_e, a.ws_de, a.ws_delta = ws_e.data_ptr(), ws_de.data_ptr(), ws_delta.data_ptr()
         if tc:
             Nkp = (Nk + 7) // 8 * 8
-            ws_s = torch.empty(B, h, Nq, Nkp, dtype=torch.float32, device=dev)
-            ws_dp = torch.empty(B, h, Nq, Nkp, dtype=torch.float32, device=dev)
+            if Nk > 4096 or _state.get("attn_bwd_unfused"):  # beyond the fused S / dP / softmax kernel's key table: fp32 scratch for the unfused path
+                ws_s = torch.empty(B, h, Nq, Nkp, dtype=torch.float32, device=dev)
+                ws_dp = torch.empty(B, h, Nq, Nkp, dtype=torch.float32, device=dev)
+                a.ws_s, a.ws_dp = ws_s.data_ptr(), ws_dp.data_ptr()
             ws_p = torch.empty(B, h, Nq, Nkp, dtype=torch.bfloat16, device=dev)
             ws_ds = torch.empty(B, h, Nq, Nkp, dtype=torch.bfloat16, device=dev)
             ws_dq = torch.empty(B, h, Nq, d, dtype=torch.float32, device=dev)
             sel = key_select_table_bwd(tuple(k_thw), O, es, dev)
-            a.ws_s, a.ws_dp, a.ws_p, a.ws_ds, a.ws_dq = (ws_s.data_ptr(), ws_dp.data_ptr(), ws_p.data_ptr(),
-                                                         ws_ds.data_ptr(), ws_dq.data_ptr())
+            a.ws_p, a.ws_ds, a.ws_dq = ws_p.data_ptr(), ws_ds.data_ptr(), ws_dq.data_ptr()
             a.sel_bwd, a.nep = sel.data_ptr(), es
         _call("svit_attn_bwd", C.byref(a), _stream(),
               tag=f"[B{B} h{h} Nq{Nq} Nk{Nk}]" if _prof is not None else None)

@@ -257,8 +257,9 @@ def test_gemm_tc_batched_ragged_scores(Bn, h, Nq, Nk):
 BWD_SHAPES = [ATTN_SHAPES[i] for i in (0, 2, 3, 4, 6, 9, 10, 12, 14)]
 
 
+@pytest.mark.parametrize("unfused", [False, True])
 @pytest.mark.parametrize("shape", BWD_SHAPES)
-def test_attention_backward_tc_matches_simt(shape):
+def test_attention_backward_tc_matches_simt(shape, unfused):
     """attn_bwd_tc.cu (batched tcgen05 GEMMs + streaming softmax/dS kernels, bf16) against the CUDA-core fp32
     backward on the same bf16-rounded inputs: dq, dk, dv and the three rel-pos table gradients."""
     B, h, q_thw, k_thw, O = shape
@@ -270,6 +271,7 @@ def test_attention_backward_tc_matches_simt(shape):
 
     def run(dtype, impl):
         ops.set_impl(attn=impl)
+        ops._state["attn_bwd_unfused"] = unfused  # fp32 S / dP scratch + streaming softmax instead of attn_bwd_sdp.cu
         try:
             ins = [t.detach().to(dtype).requires_grad_(True) for t in (q, k, v)]
             Rs = [r.detach().to(torch.bfloat16).float().requires_grad_(True) for r in R]
@@ -279,6 +281,7 @@ def test_attention_backward_tc_matches_simt(shape):
             return [cpu(t.grad) for t in ins + Rs]
         finally:
             ops.set_impl(attn=ops.IMPL_AUTO)
+            ops._state["attn_bwd_unfused"] = False
 
     ref = run(torch.float32, ops.IMPL_SIMT)
     got = run(torch.bfloat16, ops.IMPL_AUTO)
