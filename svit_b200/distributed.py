@@ -75,6 +75,16 @@ class GradAllReducer:
             for p in b:
                 self._where[p] = (bi, off)
                 off += p.numel()
+        self._views = []
+        for bi, b in enumerate(self.buckets):
+            off, vs = 0, []
+            for p in b:
+                vs.append(self.flat[bi][off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self._views.append(vs)
+        # NCCL averages inside the collective; gloo has no AVG: sum, then divide
+        nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self._op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
         self._pending = [0] * len(self.buckets)
         self._works = [None] * len(self.buckets)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
@@ -84,21 +94,29 @@ class GradAllReducer:
         for i, b in enumerate(self.buckets):
             self._pending[i] = len(b)
             self._works[i] = None
-            self.flat[i].zero_()
 
     def _launch(self, bi: int):
+        """Pack the bucket with ONE multi-tensor copy (torch._foreach_copy_), then start its all-reduce."""
+        b, views = self.buckets[bi], self._views[bi]
+        missing = [v for v, p in zip(views, b) if p.grad is None]
+        if missing:
+            torch._foreach_zero_(missing)  # parameters without a gradient are reduced as zeros
+        # gradients accumulated in place into last step's bucket views are already where they belong
+        have = [(v, p.grad) for v, p in zip(views, b) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g.view_as(v) for v, g in have])
         if self.world > 1:
-            self._works[bi] = dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._works[bi] = dist.all_reduce(self.flat[bi], op=self._op, group=self.group, async_op=True)
 
     def _on_grad(self, p: torch.nn.Parameter):
-        bi, off = self._where[p]
-        self.flat[bi][off:off + p.numel()].copy_(p.grad.reshape(-1))
+        bi = self._where[p][0]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
             self._launch(bi)
 
     def finish(self):
-        """Launch the buckets whose parameters got no gradient, wait, average, write back into .grad."""
+        """Launch the buckets whose parameters got no gradient, wait, average; .grad becomes a view of the bucket
+        (no copy back: 405 attribute assignments instead of 405 kernels)."""
         for bi in range(len(self.buckets)):
             if self._pending[bi] > 0:
                 self._pending[bi] = 0
@@ -106,16 +124,10 @@ class GradAllReducer:
         for bi, b in enumerate(self.buckets):
             if self._works[bi] is not None:
                 self._works[bi].wait()
-            if self.world > 1:
+            if self.world > 1 and self._op == dist.ReduceOp.SUM:
                 self.flat[bi].div_(self.world)
-            off = 0
-            for p in b:
-                g = self.flat[bi][off:off + p.numel()].view_as(p)
-                if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.copy_(g)
-                off += p.numel()
+            for p, v in zip(b, self._views[bi]):
+                p.grad = v
 
     def remove(self):
         for h in self._hooks:

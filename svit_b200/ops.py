@@ -298,8 +298,8 @@ class _LayerNorm(torch.autograd.Function):
         Cn = x.shape[-1]
         rows = x.numel() // Cn
         dx = torch.empty_like(x)
-        dg = torch.zeros(Cn, dtype=torch.float32, device=x.device)
-        db = torch.zeros(Cn, dtype=torch.float32, device=x.device)
+        dgb = torch.zeros(2, Cn, dtype=torch.float32, device=x.device)  # one fill for both accumulators
+        dg, db = dgb[0], dgb[1]
         _call("svit_layernorm_bwd", dy.data_ptr(), x.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
               dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, Cn, _dt(x), _stream())
         return dx, dg, db, None, None
@@ -375,13 +375,12 @@ class _QKVPool(torch.autograd.Function):
         D3 = 3 * h * HEAD_DIM
         dqkv = torch.empty_like(qkv)
         grads = []
+        acc = torch.zeros(3, HEAD_DIM * 29, dtype=torch.float32, device=qkv.device)  # dw | dgamma | dbeta x (q, k, v)
         for which, (dout, s) in enumerate(((dq, sq), (dk, skv), (dv, skv))):
             w32, g32 = saved[2 * which], saved[2 * which + 1]
             dout = dout.contiguous()
             dpre = torch.empty_like(dout)
-            dw = torch.zeros(HEAD_DIM * 27, dtype=torch.float32, device=qkv.device)
-            dg = torch.zeros(HEAD_DIM, dtype=torch.float32, device=qkv.device)
-            db = torch.zeros(HEAD_DIM, dtype=torch.float32, device=qkv.device)
+            dw, dg, db = acc[which, :HEAD_DIM * 27], acc[which, HEAD_DIM * 27:HEAD_DIM * 28], acc[which, HEAD_DIM * 28:]
             frac = tap_fractions(s, qkv.device)
             off = which * h * HEAD_DIM * qkv.element_size()
             _call("svit_pool_ln_bwd", qkv.data_ptr() + off, N * D3, D3, HEAD_DIM, w32.data_ptr(), frac.data_ptr(),
@@ -483,9 +482,10 @@ class _Attention(torch.autograd.Function):
         tc = q.dtype == torch.bfloat16 and _state["attn_impl"] != _lib.IMPL_SIMT and ne <= 64
         es = (ne + 7) // 8 * 8 if tc else ne
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        dRh = torch.zeros(Rh.shape, dtype=torch.float32, device=dev)
-        dRw = torch.zeros(Rw.shape, dtype=torch.float32, device=dev)
-        dRt = torch.zeros(Rt.shape, dtype=torch.float32, device=dev)
+        dR = torch.zeros(Rh.numel() + Rw.numel() + Rt.numel(), dtype=torch.float32, device=dev)  # one fill
+        dRh = dR[:Rh.numel()].view(Rh.shape)
+        dRw = dR[Rh.numel():Rh.numel() + Rw.numel()].view(Rw.shape)
+        dRt = dR[Rh.numel() + Rw.numel():].view(Rt.shape)
         ws_e = torch.empty(B, h, Nq, es, dtype=torch.float32, device=dev)
         ws_de = torch.empty(B, h, Nq, es, dtype=torch.float32, device=dev)
         ws_delta = torch.empty(B, h, Nq, dtype=torch.float32, device=dev)
