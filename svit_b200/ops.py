@@ -338,6 +338,72 @@ def pooled_hw(n: int, s: int) -> int:
     return (n - 1) // s + 1
 
 
+_side_streams = {}
+
+
+def _branches(n: int):
+    """n CUDA streams for independent kernel chains of one op (stream 0 = the current stream).  The q / k / v pooling
+    kernels are small and latency-bound; running the three chains side by side fills the SMs that each kernel's tail
+    leaves idle.  Fork / join are event waits, so the pattern is graph-capturable."""
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, n)
+    if key not in _side_streams:
+        _side_streams[key] = [torch.cuda.Stream(device=cur.device) for _ in range(n - 1)]
+    return [cur] + _side_streams[key]
+
+
+class _Fork:
+    """with _Fork(3) as f: for i in range(3): with f.branch(i): launch chain i   -> joined on exit."""
+
+    def __init__(self, n):
+        # per-kernel event timing (profile mode) needs the kernels one at a time
+        self.streams = _branches(n) if (_state.get("multi_stream", True) and _prof is None) else None
+        self.n = n
+
+    def __enter__(self):
+        if self.streams is not None:
+            self.start = torch.cuda.Event()
+            self.start.record(self.streams[0])
+            self.done = []
+        return self
+
+    def branch(self, i):
+        if self.streams is None or i == 0:
+            return _NullCtx()
+        return _Branch(self, i)
+
+    def __exit__(self, *exc):
+        if self.streams is not None:
+            for ev in self.done:
+                self.streams[0].wait_event(ev)
+        return False
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class _Branch:
+    def __init__(self, fork, i):
+        self.fork, self.s = fork, fork.streams[i]
+        self.ctx = torch.cuda.stream(self.s)
+
+    def __enter__(self):
+        self.s.wait_event(self.fork.start)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        ev = torch.cuda.Event()
+        ev.record(self.s)
+        self.fork.done.append(ev)
+        return self.ctx.__exit__(*exc)
+
+
 class _QKVPool(torch.autograd.Function):
     """q, k, v = attention_pool(qkv[which], pool_which, thw, norm_which) for which in (q, k, v)
     (attention.py:368-388), reading the packed [B, N, 3, h, 96] GEMM output in place."""
@@ -352,17 +418,20 @@ class _QKVPool(torch.autograd.Function):
         outs = []
         params = ((wq, gq, bq, stride_q), (wk, gk, bk, stride_kv), (wv, gv, bv, stride_kv))
         saved = []
-        for which, (w, g, b, s) in enumerate(params):
+        prepared = []
+        for which, (w, g, b, s) in enumerate(params):  # allocations and parameter casts stay on the current stream
             Ho, Wo = pooled_hw(H, s), pooled_hw(W, s)
             out = torch.empty(B, h, 1 + T * Ho * Wo + O, HEAD_DIM, dtype=qkv.dtype, device=qkv.device)
-            w32, g32 = _f32(w).reshape(HEAD_DIM, 27), _f32(g)
-            frac = tap_fractions(s, qkv.device)
-            _call("svit_pool_ln_fwd", qkv.data_ptr() + which * h * HEAD_DIM * qkv.element_size(), N * D3, D3, HEAD_DIM,
-                  w32.data_ptr(), frac.data_ptr(), g32.data_ptr(), _f32(b).data_ptr(), out.data_ptr(),
-                  B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream(),
-                  tag=f"[{'qkv'[which]} B{B} h{h} {T}x{H}x{W} s{s}]" if _prof is not None else None)
-            outs.append(out)
-            saved += [w32, g32]
+            prepared.append((out, _f32(w).reshape(HEAD_DIM, 27), _f32(g), _f32(b), tap_fractions(s, qkv.device), s))
+        with _Fork(3) as fork:
+            for which, (out, w32, g32, b32, frac, s) in enumerate(prepared):
+                with fork.branch(which):
+                    _call("svit_pool_ln_fwd", qkv.data_ptr() + which * h * HEAD_DIM * qkv.element_size(), N * D3, D3,
+                          HEAD_DIM, w32.data_ptr(), frac.data_ptr(), g32.data_ptr(), b32.data_ptr(), out.data_ptr(),
+                          B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream(),
+                          tag=f"[{'qkv'[which]} B{B} h{h} {T}x{H}x{W} s{s}]" if _prof is not None else None)
+                outs.append(out)
+                saved += [w32, g32]
         ctx.save_for_backward(qkv, *saved)
         ctx.geom = (B, N, h, T, H, W, O, stride_q, stride_kv)
         ctx.wshape = wq.shape
@@ -376,17 +445,20 @@ class _QKVPool(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         grads = []
         acc = torch.zeros(3, HEAD_DIM * 29, dtype=torch.float32, device=qkv.device)  # dw | dgamma | dbeta x (q, k, v)
-        for which, (dout, s) in enumerate(((dq, sq), (dk, skv), (dv, skv))):
-            w32, g32 = saved[2 * which], saved[2 * which + 1]
-            dout = dout.contiguous()
-            dpre = torch.empty_like(dout)
-            dw, dg, db = acc[which, :HEAD_DIM * 27], acc[which, HEAD_DIM * 27:HEAD_DIM * 28], acc[which, HEAD_DIM * 28:]
-            frac = tap_fractions(s, qkv.device)
-            off = which * h * HEAD_DIM * qkv.element_size()
-            _call("svit_pool_ln_bwd", qkv.data_ptr() + off, N * D3, D3, HEAD_DIM, w32.data_ptr(), frac.data_ptr(),
-                  g32.data_ptr(), dout.data_ptr(), dpre.data_ptr(), dqkv.data_ptr() + off, dw.data_ptr(), dg.data_ptr(),
-                  db.data_ptr(), B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream())
-            grads += [dw.reshape(ctx.wshape), dg, db]
+        douts = [d.contiguous() for d in (dq, dk, dv)]
+        dpres = [torch.empty_like(d) for d in douts]  # allocated (and later freed) on the current stream
+        fracs = [tap_fractions(s, qkv.device) for s in (sq, skv, skv)]
+        with _Fork(3) as fork:
+            for which, s in enumerate((sq, skv, skv)):
+                w32, g32 = saved[2 * which], saved[2 * which + 1]
+                dw, dg, db = acc[which, :HEAD_DIM * 27], acc[which, HEAD_DIM * 27:HEAD_DIM * 28], acc[which, HEAD_DIM * 28:]
+                off = which * h * HEAD_DIM * qkv.element_size()
+                with fork.branch(which):
+                    _call("svit_pool_ln_bwd", qkv.data_ptr() + off, N * D3, D3, HEAD_DIM, w32.data_ptr(),
+                          fracs[which].data_ptr(), g32.data_ptr(), douts[which].data_ptr(), dpres[which].data_ptr(),
+                          dqkv.data_ptr() + off, dw.data_ptr(), dg.data_ptr(), db.data_ptr(), B, h, T, H, W, O, s, LN_EPS,
+                          _dt(qkv), _stream())
+                grads += [dw.reshape(ctx.wshape), dg, db]
         return (dqkv, None, None, None, None, *grads)
 
 
