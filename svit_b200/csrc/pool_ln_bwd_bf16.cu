@@ -18,6 +18,7 @@ namespace {
 struct Geom {
   int B, h, T, H, W, Ho, Wo, O, s;
   int64_t in_bs, in_ts, in_hs;
+  int its;  // in_ts as int: offsets inside one (b, head) slice fit 32 bits (checked at launch)
 };
 
 __device__ __forceinline__ void load_weights(const float* __restrict__ w, const float* __restrict__ frac, float* sw,
@@ -67,7 +68,17 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
   const int wpb = blockDim.x >> 5;
   const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
   const bf16* zin = in + b * g.in_bs + head * g.in_hs + c0;
-  for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < Nout; tok += gridDim.x * wpb) {
+  // patch-token coordinates advance with the token stride (decomposed once): no division in the loop
+  const int step = gridDim.x * wpb;
+  const int step_w = step % g.Wo, step_h = (step / g.Wo) % g.Ho, step_t = step / (g.Wo * g.Ho);
+  int wo, ho, to;
+  {
+    const int tok0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const unsigned p = (tok0 < 1 ? tok0 + step : tok0) - 1;
+    const unsigned pr = p / (unsigned)g.Wo;
+    wo = (int)(p - pr * g.Wo); to = (int)(pr / (unsigned)g.Ho); ho = (int)(pr - to * g.Ho);
+  }
+  for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < Nout; tok += step) {
     const int64_t i = (int64_t)bh * Nout + tok;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     float dy[4];
@@ -77,13 +88,10 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
         unpack4(__ldg(reinterpret_cast<const uint2*>(zin)), v);
       } else if (tok > Lo) {
         float z[4];
-        unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (int64_t)(tok - Lo + L) * g.in_ts)), z);
+        unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (tok - Lo + L) * g.its)), z);
         const float4 we = *reinterpret_cast<const float4*>(sweff + c0);
         v[0] = z[0] * we.x; v[1] = z[1] * we.y; v[2] = z[2] * we.z; v[3] = z[3] * we.w;
       } else {
-        const unsigned p = tok - 1;
-        const unsigned pr = p / (unsigned)g.Wo;
-        const int wo = (int)(p - pr * g.Wo), to = (int)(pr / (unsigned)g.Ho), ho = (int)(pr - to * g.Ho);
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
           const int t = to - 1 + kt;
@@ -97,7 +105,7 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
               const int ww = wo * g.s - 1 + kw;
               if (ww < 0 || ww >= g.W) continue;
               float z[4];
-              unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (int64_t)(1 + (t * g.H + hh) * g.W + ww) * g.in_ts)), z);
+              unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (1 + (t * g.H + hh) * g.W + ww) * g.its)), z);
               const float4 wr = *reinterpret_cast<const float4*>(sw + (kt * 9 + kh * 3 + kw) * PD + c0);
               v[0] = fmaf(z[0], wr.x, v[0]); v[1] = fmaf(z[1], wr.y, v[1]);
               v[2] = fmaf(z[2], wr.z, v[2]); v[3] = fmaf(z[3], wr.w, v[3]);
@@ -105,6 +113,13 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
           }
         }
       }
+    }
+    if (tok >= 1) {  // advance (to, ho, wo) to this warp's next token
+      wo += step_w;
+      if (wo >= g.Wo) { wo -= g.Wo; ++ho; }
+      ho += step_h;
+      if (ho >= g.Ho) { ho -= g.Ho; ++to; }
+      to += step_t;
     }
     const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.f / PD);
     float xh[4], q = 0.f;
@@ -165,33 +180,45 @@ __global__ void __launch_bounds__(288) pool_bwd_dw_kernel(const bf16* __restrict
   float acc[9][2], aweff[2] = {0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = 0.f;
+  // (to, ho, wo) of the thread's current patch token, advanced by 2 per iteration (no division in the loop)
+  int wo, ho, to;
+  {
+    const int first = t0 + half < 1 ? t0 + half + 2 : t0 + half;  // first token this thread decodes as a patch token
+    const unsigned p = first - 1;
+    const unsigned pr = p / (unsigned)g.Wo;
+    wo = (int)(p - pr * g.Wo); to = (int)(pr / (unsigned)g.Ho); ho = (int)(pr - to * g.Ho);
+  }
 #pragma unroll 2
   for (int tok = t0 + half; tok < t1; tok += 2) {
     if (tok == 0) continue;  // cls passes through: no weight gradient
-    const float2 dp = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp_base + (int64_t)tok * PD));
+    const float2 dp = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp_base + tok * PD));
     if (tok > Lo) {
       if (tg == 0) {
-        const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zin + (int64_t)(tok - Lo + L) * g.in_ts));
+        const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zin + (tok - Lo + L) * g.its));
         aweff[0] = fmaf(dp.x, z.x, aweff[0]);
         aweff[1] = fmaf(dp.y, z.y, aweff[1]);
       }
       continue;
     }
-    const unsigned p = tok - 1;
-    const unsigned pr = p / (unsigned)g.Wo;
-    const int wo = (int)(p - pr * g.Wo), to = (int)(pr / (unsigned)g.Ho), ho = (int)(pr - to * g.Ho);
-    const int t = to - 1 + tg;
+    const int cwo = wo, cho = ho, cto = to;
+    wo += 2;
+    while (wo >= g.Wo) {
+      wo -= g.Wo;
+      if (++ho == g.Ho) { ho = 0; ++to; }
+    }
+    const int t = cto - 1 + tg;
     if (t < 0 || t >= g.T) continue;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      const int hh = ho * g.s - 1 + kh;
+      const int hh = cho * g.s - 1 + kh;
       if (hh < 0 || hh >= g.H) continue;
+      const int rowbase = 1 + (t * g.H + hh) * g.W;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int ww = wo * g.s - 1 + kw;
+        const int ww = cwo * g.s - 1 + kw;
         if (ww < 0 || ww >= g.W) continue;
         const float2 z = __bfloat1622float2(
-            *reinterpret_cast<const __nv_bfloat162*>(zin + (int64_t)(1 + (t * g.H + hh) * g.W + ww) * g.in_ts));
+            *reinterpret_cast<const __nv_bfloat162*>(zin + (rowbase + ww) * g.its));
         acc[kh * 3 + kw][0] = fmaf(dp.x, z.x, acc[kh * 3 + kw][0]);
         acc[kh * 3 + kw][1] = fmaf(dp.y, z.y, acc[kh * 3 + kw][1]);
       }
@@ -263,19 +290,25 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
   const bf16* dp = dpre + (int64_t)bh * Nout * PD + c0;
   bf16* dzb = dz + b * g.in_bs + head * g.in_hs + c0;
   const int smask = (1 << LS) - 1;
-  for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < Nin; tok += gridDim.x * wpb) {
+  const int step = gridDim.x * wpb;
+  const int step_w = step % g.W, step_h = (step / g.W) % g.H, step_t = step / (g.W * g.H);
+  int ww, hh, t;
+  {
+    const int tok0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const unsigned p = (tok0 < 1 ? tok0 + step : tok0) - 1;
+    const unsigned pr = p / (unsigned)g.W;
+    ww = (int)(p - pr * g.W); t = (int)(pr / (unsigned)g.H); hh = (int)(pr - t * g.H);
+  }
+  for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < Nin; tok += step) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (tok == 0) {
       unpack4(__ldg(reinterpret_cast<const uint2*>(dp)), v);
     } else if (tok > L) {
       float z[4];
-      unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (int64_t)(tok - L + Lo) * PD)), z);
+      unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (tok - L + Lo) * PD)), z);
       const float4 we = *reinterpret_cast<const float4*>(sweff + c0);
       v[0] = z[0] * we.x; v[1] = z[1] * we.y; v[2] = z[2] * we.z; v[3] = z[3] * we.w;
     } else {
-      const unsigned p = tok - 1;
-      const unsigned pr = p / (unsigned)g.W;
-      const int ww = (int)(p - pr * g.W), t = (int)(pr / (unsigned)g.H), hh = (int)(pr - t * g.H);
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
         const int to = t + 1 - kt;
@@ -293,7 +326,7 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
             const int wo = LS >= 0 ? numw >> LS : numw / g.s;
             if (wo >= g.Wo) continue;
             float z[4];
-            unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (int64_t)(1 + (to * g.Ho + ho) * g.Wo + wo) * PD)), z);
+            unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (1 + (to * g.Ho + ho) * g.Wo + wo) * PD)), z);
             const float4 wr = *reinterpret_cast<const float4*>(sw + (kt * 9 + kh * 3 + kw) * PD + c0);
             v[0] = fmaf(z[0], wr.x, v[0]); v[1] = fmaf(z[1], wr.y, v[1]);
             v[2] = fmaf(z[2], wr.z, v[2]); v[3] = fmaf(z[3], wr.w, v[3]);
@@ -301,7 +334,14 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
         }
       }
     }
-    *reinterpret_cast<uint2*>(dzb + (int64_t)tok * g.in_ts) = pack4(v);
+    *reinterpret_cast<uint2*>(dzb + tok * g.its) = pack4(v);
+    if (tok >= 1) {
+      ww += step_w;
+      if (ww >= g.W) { ww -= g.W; ++hh; }
+      hh += step_h;
+      if (hh >= g.H) { hh -= g.H; ++t; }
+      t += step_t;
+    }
   }
 }
 
@@ -329,10 +369,10 @@ int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   g.B = B; g.h = h; g.T = T; g.H = H; g.W = W; g.O = O; g.s = s;
   g.Ho = (H - 1) / s + 1;
   g.Wo = (W - 1) / s + 1;
-  g.in_bs = in_bs; g.in_ts = in_ts; g.in_hs = in_hs;
+  g.in_bs = in_bs; g.in_ts = in_ts; g.in_hs = in_hs; g.its = (int)in_ts;
   const int64_t Nout = 1 + (int64_t)T * g.Ho * g.Wo + O, Nin = 1 + (int64_t)T * H * W + O;
   const int64_t tok_out = (int64_t)B * h * Nout, tok_in = (int64_t)B * h * Nin;
-  if (B * h > 65535 || Nin >= (1ll << 30)) return SVIT_ENOTSUP;
+  if (B * h > 65535 || Nin * in_ts >= (1ll << 31) || Nin * PD >= (1ll << 31)) return SVIT_ENOTSUP;  // 32-bit offsets
   (void)tok_out; (void)tok_in;
   const unsigned BH = (unsigned)(B * h);
   auto gx = [&](int64_t n) {  // CTAs along x so that x * BH is about 8 CTAs per SM, 8 tokens per CTA pass
