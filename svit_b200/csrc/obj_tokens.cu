@@ -68,6 +68,123 @@ __global__ void roi_tokens_kernel(const T* __restrict__ feat, int64_t feat_bs, c
   }
 }
 
+// bf16, C % 8 == 0: same arithmetic, restructured for the memory system.
+//   * the 1-D interpolation set-up (clamps, neighbour indices, weights, validity: separable in y and x) is computed once per
+//     box into shared memory instead of once per channel thread and sample;
+//   * a thread owns 8 consecutive channels (16-byte loads of the token-major feature rows) and the 256 threads of the CTA
+//     split into 256 / (C/8) groups that take the 49 bins round-robin; the per-bin maxima are combined through smem.
+struct Samp1D {
+  int lo, hi;
+  float wlo, whi;  // both 0 for an invalid (out-of-range) sample
+};
+constexpr int ROI_MAXS = 512;
+
+__device__ __forceinline__ Samp1D samp1d(float v, int n) {
+  Samp1D s;
+  s.lo = s.hi = 0;
+  s.wlo = s.whi = 0.f;
+  if (v < -1.0f || v > (float)n) return s;
+  if (v <= 0.f) v = 0.f;
+  int lo = (int)v, hi;
+  if (lo >= n - 1) { hi = lo = n - 1; v = (float)lo; } else { hi = lo + 1; }
+  const float l = v - lo;
+  s.lo = lo; s.hi = hi; s.wlo = 1.f - l; s.whi = l;
+  return s;
+}
+
+__global__ void __launch_bounds__(256) roi_tokens_vec8_kernel(const bf16* __restrict__ feat, int64_t feat_bs,
+                                                              const float* __restrict__ boxes, bf16* __restrict__ tokens,
+                                                              int32_t* __restrict__ assign, int B, int C, int Tf, int Hf,
+                                                              int Wf, int Tx, int K, int pst, float scale, int P) {
+  __shared__ Samp1D ys[ROI_MAXS], xs[ROI_MAXS];
+  __shared__ float red[256 * 8];
+  const int box = blockIdx.x;  // (b, t, k) flattened
+  const int t = (box / K) % Tx, b = box / (K * Tx);
+  const int slice = (Tf == 1) ? 0 : (Tx == 1 ? t : t / pst);
+  if (threadIdx.x == 0 && assign) {
+    assign[2 * box] = b;
+    assign[2 * box + 1] = slice;
+  }
+  const float* bx = boxes + (int64_t)box * 4;
+  const float x1 = bx[0] * scale - 0.5f, y1 = bx[1] * scale - 0.5f;
+  const float x2 = bx[2] * scale - 0.5f, y2 = bx[3] * scale - 0.5f;
+  const float rw = x2 - x1, rh = y2 - y1;
+  const float bw = rw / (float)P, bh = rh / (float)P;
+  const int gh = (int)ceilf(rh / (float)P), gw = (int)ceilf(rw / (float)P);
+  // boxes far larger than the frame (more than ROI_MAXS 1-D samples) compute the set-up on the fly instead
+  const bool tab = (int64_t)P * gh <= ROI_MAXS && (int64_t)P * gw <= ROI_MAXS;
+  if (tab) {
+    for (int i = threadIdx.x; i < P * gh; i += blockDim.x) {
+      const int ph = i / gh, iy = i - ph * gh;
+      ys[i] = samp1d(y1 + ph * bh + (iy + 0.5f) * bh / (float)gh, Hf);
+    }
+    for (int i = threadIdx.x; i < P * gw; i += blockDim.x) {
+      const int pw = i / gw, ix = i - pw * gw;
+      xs[i] = samp1d(x1 + pw * bw + (ix + 0.5f) * bw / (float)gw, Wf);
+    }
+  }
+  __syncthreads();
+  const int ct = C >> 3;                 // channel threads
+  const int ngrp = blockDim.x / ct;      // bin groups
+  const int cthr = threadIdx.x % ct, grp = threadIdx.x / ct;
+  const bf16* fm = feat + (int64_t)b * feat_bs + (1 + (int64_t)slice * Hf * Wf) * C + cthr * 8;
+  const int cnt = gh * gw;
+  const float inv = 1.f / (float)(cnt > 0 ? cnt : 1);
+  float best[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) best[u] = -INFINITY;
+  auto fma8 = [](float acc[8], const uint4& v, float w) {
+    const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc[2 * u] = fmaf(w, __uint_as_float(q[u] << 16), acc[2 * u]);
+      acc[2 * u + 1] = fmaf(w, __uint_as_float(q[u] & 0xffff0000u), acc[2 * u + 1]);
+    }
+  };
+  if (grp < ngrp) {
+    for (int bin = grp; bin < P * P; bin += ngrp) {
+      const int ph = bin / P, pw = bin - ph * P;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int iy = 0; iy < gh; ++iy) {
+        const Samp1D sy = tab ? ys[ph * gh + iy] : samp1d(y1 + ph * bh + (iy + 0.5f) * bh / (float)gh, Hf);
+        if (sy.wlo == 0.f && sy.whi == 0.f) continue;
+        const bf16* r0 = fm + (int64_t)sy.lo * Wf * C;
+        const bf16* r1 = fm + (int64_t)sy.hi * Wf * C;
+        for (int ix = 0; ix < gw; ++ix) {
+          const Samp1D sx = tab ? xs[pw * gw + ix] : samp1d(x1 + pw * bw + (ix + 0.5f) * bw / (float)gw, Wf);
+          if (sx.wlo == 0.f && sx.whi == 0.f) continue;
+          const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(r0 + sx.lo * C));
+          const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(r0 + sx.hi * C));
+          const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(r1 + sx.lo * C));
+          const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(r1 + sx.hi * C));
+          fma8(acc, v00, sy.wlo * sx.wlo);
+          fma8(acc, v01, sy.wlo * sx.whi);
+          fma8(acc, v10, sy.whi * sx.wlo);
+          fma8(acc, v11, sy.whi * sx.whi);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) best[u] = fmaxf(best[u], acc[u] * inv);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[threadIdx.x * 8 + u] = best[u];
+  __syncthreads();
+  if (threadIdx.x < ct) {
+    const int ng = ngrp < P * P ? ngrp : P * P;  // groups that owned at least one bin
+    float m[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m[u] = red[threadIdx.x * 8 + u];
+    for (int g2 = 1; g2 < ng; ++g2)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) m[u] = fmaxf(m[u], red[(g2 * ct + threadIdx.x) * 8 + u]);
+    __nv_bfloat162 h2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) h2[u] = __floats2bfloat162_rn(m[2 * u], m[2 * u + 1]);
+    *reinterpret_cast<uint4*>(tokens + (int64_t)box * C + threadIdx.x * 8) = *reinterpret_cast<uint4*>(h2);
+  }
+}
+
 template <typename T>
 __global__ void roi_align_kernel(const T* __restrict__ feat, const float* __restrict__ rois, T* __restrict__ out, int N,
                                  int C, int H, int W, int R, int P, float scale, int sampling, int aligned) {
@@ -145,6 +262,9 @@ int svit_roi_tokens_fwd(const void* feat, int64_t feat_batch_stride, const float
   int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 96);
   if (dtype == SVIT_F32)
     roi_tokens_kernel<float><<<(unsigned)nbox, threads, 0, st>>>((const float*)feat, feat_batch_stride, boxes, (float*)tokens, assign, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
+  else if (dtype == SVIT_BF16 && C % 8 == 0 && C <= 2048 && feat_batch_stride % 8 == 0 &&
+           ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(tokens)) & 15) == 0)
+    roi_tokens_vec8_kernel<<<(unsigned)nbox, 256, 0, st>>>((const bf16*)feat, feat_batch_stride, boxes, (bf16*)tokens, assign, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
   else if (dtype == SVIT_BF16)
     roi_tokens_kernel<bf16><<<(unsigned)nbox, threads, 0, st>>>((const bf16*)feat, feat_batch_stride, boxes, (bf16*)tokens, assign, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
   else

@@ -379,11 +379,15 @@ def test_object_token_indices_bit_exact():
     assert torch.equal(co[:, 0], x[:, 0]) and torch.equal(co[:, 1:], x[:, -16:])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("K", [1, 4, 16])
-def test_roi_object_tokens_vs_oracle(K):
+def test_roi_object_tokens_vs_oracle(K, dtype):
+    """fp32: the channel-per-thread kernel; bf16: the 8-channels-per-thread kernel with per-box 1-D sample tables
+    (roi_tokens_vec8_kernel) on bf16-rounded features, output rounded to bf16."""
     gen = torch.Generator().manual_seed(K)
-    for (B, C, Tp, Hf, Tx, scale) in ((2, 96, 2, 7, 4, 1 / 16), (1, 192, 4, 14, 8, 1 / 8), (1, 96, 1, 7, 1, 1 / 16)):
-        feat = torch.randn(B, C, Tp, Hf, Hf, generator=gen)
+    for (B, C, Tp, Hf, Tx, scale) in ((2, 96, 2, 7, 4, 1 / 16), (1, 192, 4, 14, 8, 1 / 8), (1, 96, 1, 7, 1, 1 / 16),
+                                      (1, 384, 2, 14, 4, 1 / 16)):
+        feat = torch.randn(B, C, Tp, Hf, Hf, generator=gen).to(dtype).float()
         size = Hf / scale
         boxes = torch.rand(B, Tx, K, 4, generator=gen) * size
         boxes[..., 2:] = boxes[..., :2] + torch.rand(B, Tx, K, 2, generator=gen) * size * 0.6
@@ -393,9 +397,9 @@ def test_roi_object_tokens_vs_oracle(K):
         want, assign_w = O.roi_object_tokens(feat, boxes, patch_stride_t=2, spatial_scale=scale)
         tokens = torch.zeros(B, 1 + Tp * Hf * Hf + 3, C)
         tokens[:, 1:1 + Tp * Hf * Hf] = feat.permute(0, 2, 3, 4, 1).reshape(B, -1, C)
-        got, assign = ops.roi_tokens(tokens.to(DEV), [Tp, Hf, Hf], boxes, 2, scale, 7)
+        got, assign = ops.roi_tokens(tokens.to(DEV, dtype), [Tp, Hf, Hf], boxes, 2, scale, 7)
         assert torch.equal(cpu(assign).long(), assign_w.float().long())   # (batch, slice): bit exact
-        assert max_rel_err(cpu(got), want) < 1e-5
+        assert max_rel_err(cpu(got), want) < (1e-5 if dtype == torch.float32 else 6e-3)
 
 
 def test_roi_align_vs_torchvision():
