@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel breakdown here")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--frames-pass", action="store_true",
+                    help="train mode: also run the reference's no-grad pass over the B*16 single frames "
+                         "(TRAIN.FORWARD_VIDEO_FRAMES, tools/train_net.py:105-110)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: configs[1] (the headline metric); train: configs[2], fwd + bwd + gradient all-reduce")
     args = ap.parse_args()
@@ -413,6 +416,11 @@ def run_train(args):
             reducer.prepare()
         preds, extra = model([clips[i & 1]])
         loss = torch.nn.functional.cross_entropy(extra["logits"].float(), labels)
+        if args.frames_pass:
+            from svit_b200.distributed import consistency_loss, forward_video_frames
+            _p, _e = forward_video_frames(model, clips[i & 1])
+            for k, v in consistency_loss(model._lambda, extra, _e).items():  # empty with the stock lambda keys
+                loss = loss + model._lambda[k] * v
         loss.backward()
         if reducer is not None:
             reducer.finish()
@@ -444,7 +452,8 @@ def run_train(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "gpu_launches": ops.launches() - l0, "loss": float(loss),
                 "config": {"workload": f"SViT (configs/ssv2.yaml) training step, batch {B} clips per GPU, random init, "
-                                       "cross-entropy on the class logits, no optimizer step",
+                                       "cross-entropy on the class logits, no optimizer step"
+                                       + (", + no-grad frames pass (B*16 frames, T=1)" if args.frames_pass else ""),
                            "parallelism": f"dp{world}", "global_batch": B * world}}
         print(json.dumps(line))
     if world > 1:

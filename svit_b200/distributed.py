@@ -134,13 +134,46 @@ class GradAllReducer:
             h.remove()
 
 
-def train_step(model, reducer: Optional[GradAllReducer], clip, labels, optimizer=None, max_norm: Optional[float] = 1.0):
-    """One data-parallel training step on this rank's shard: forward, CE loss (losses.py:156-168, video rank),
-    backward with overlapped gradient all-reduce, optional clip (tools/train_net.py:144-147) and optimizer step."""
+def forward_video_frames(model, clip):
+    """The reference's second, gradient-free pass of every training step (tools/train_net.py:105-110,
+    TRAIN.FORWARD_VIDEO_FRAMES, on by default): the B clips are re-fed as B*T single frames
+    ([B, C, T, H, W] -> [B*T, C, 1, H, W]), i.e. the T = 1 shapes of every kernel (N = 3141 / 789 / 201 / 54 tokens,
+    rel_pos_t interpolated 15 -> 1).  Returns (preds, extra_preds) of the frames."""
+    with torch.no_grad():
+        frames = clip.transpose(1, 2).flatten(0, 1).unsqueeze(2)
+        return model([frames])
+
+
+def consistency_loss(lambdas: dict, extra_preds: dict, frames_extra_preds: dict) -> dict:
+    """VideoImageLoss._consistency_loss (models/losses.py:127-136), verbatim semantics: the terms are keyed
+    'video_image_desc_l1_loss' / '..._l2_loss', while get_lambdas_dict (utils/misc.py:411-423) only ever defines
+    'video_image_boxes_l1_loss' -- so with the stock config the dict is empty and the frames pass adds compute but
+    no loss term.  Kept as is: a drop-in must not change the optimisation problem."""
+    ret = {}
+    pred = extra_preds["obj_desc"]                                   # [B, T, O, d]
+    tar = frames_extra_preds["obj_desc"].reshape(pred.shape).detach()  # [B*T, 1, O, d] -> [B, T, O, d]
+    if "video_image_desc_l1_loss" in lambdas:
+        ret["video_image_desc_l1_loss"] = torch.nn.functional.l1_loss(pred, tar)
+    if "video_image_desc_l2_loss" in lambdas:
+        ret["video_image_desc_l2_loss"] = torch.nn.functional.mse_loss(pred, tar)
+    return ret
+
+
+def train_step(model, reducer: Optional[GradAllReducer], clip, labels, optimizer=None, max_norm: Optional[float] = 1.0,
+               frames_pass: bool = False, lambdas: Optional[dict] = None):
+    """One data-parallel training step on this rank's shard: forward, optional frames pass (train_net.py:105-110),
+    CE loss (+ the consistency terms the lambda dict enables; losses.py:156-168, video rank), backward with
+    overlapped gradient all-reduce, optional clip (tools/train_net.py:144-147) and optimizer step."""
     if reducer is not None:
         reducer.prepare()
     logits, extra = model([clip])
     loss = torch.nn.functional.cross_entropy(logits.float(), labels)
+    if frames_pass and clip.size(2) > 1:
+        _preds, _extra = forward_video_frames(model, clip)
+        extra["frames_output"] = {"preds": _preds, "extra_preds": _extra}
+        lam = lambdas if lambdas is not None else getattr(model, "_lambda", {})
+        for k, v in consistency_loss(lam, extra, _extra).items():
+            loss = loss + lam[k] * v
     loss.backward()
     if reducer is not None:
         reducer.finish()

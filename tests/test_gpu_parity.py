@@ -466,3 +466,35 @@ def test_skip_maxpool_bf16_backward_vectorised(spec):
     out.backward(gy.to(DEV))
     ref.backward(gy.float())
     assert torch.equal(cpu(xd.grad), xr.grad.bfloat16().float())
+
+
+def test_frames_pass_full_ssv2_vs_oracle():
+    """the reference's no-grad pass over single frames (tools/train_net.py:105-110) at the real ssv2
+    geometry -- T = 1 shapes of every kernel (N = 3141 / 789 / 201 / 54, rel_pos_t interpolated 15 -> 1) -- against
+    the CPU oracle on the same two frames: fp32 mode <= 3e-4, bf16 mode <= 2e-2 on logits and object descriptors."""
+    from svit_b200.distributed import consistency_loss, forward_video_frames
+    cfg = ssv2_cfg()
+    state = synth_state(state_shapes(cfg), 77, w_std=0.04)
+    clip = synth_input("frames.clip", (1, 3, 2, 224, 224), 8)       # B = 1, T = 2 -> two frames
+    frames = clip.transpose(1, 2).flatten(0, 1).unsqueeze(2)
+    want_out, want = O.svit_forward(frames, state, block_specs(cfg)[0], cfg, training=False)
+    m = svit_b200.SViT(cfg, compute_dtype=torch.float32)
+    m.load_state_dict(state)
+    m = m.to(DEV).eval()
+    for dtype, tol, impl in ((torch.float32, 3e-4, ops.IMPL_SIMT), (torch.bfloat16, 2e-2, ops.IMPL_AUTO)):
+        ops.set_impl(gemm=impl, attn=impl)
+        try:
+            m.compute_dtype = dtype
+            probs, extra = forward_video_frames(m, clip.to(DEV))
+        finally:
+            ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+        assert extra["obj_desc"].shape == want["obj_desc"].shape == (2, 1, 4, 768)
+        assert max_rel_err(cpu(extra["logits"]), want["logits"]) < tol, dtype
+        assert max_rel_err(cpu(extra["obj_desc"]), want["obj_desc"]) < tol, dtype
+        assert max_rel_err(cpu(probs), want_out) < 5 * tol, dtype
+    # losses.py:127-136 with the stock lambda keys: no consistency term (key mismatch kept on purpose)
+    vid = {"obj_desc": torch.zeros(1, 2, 4, 768, device=DEV)}
+    assert consistency_loss(m._lambda, vid, extra) == {}
+    lam = dict(m._lambda, video_image_desc_l1_loss=1.5)
+    got = consistency_loss(lam, vid, extra)["video_image_desc_l1_loss"]
+    assert abs(float(got) - float(want["obj_desc"].abs().mean())) < 2e-2 * float(want["obj_desc"].abs().mean()) + 1e-6
