@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel breakdown here")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--optimizer", action="store_true",
+                    help="train mode: finish the step with the fused clip_grad_norm(1.0) + AdamW update "
+                         "(svit_b200.optim, SOLVER settings of configs/ssv2.yaml)")
     ap.add_argument("--frames-pass", action="store_true",
                     help="train mode: also run the reference's no-grad pass over the B*16 single frames "
                          "(TRAIN.FORWARD_VIDEO_FRAMES, tools/train_net.py:105-110)")
@@ -405,6 +408,10 @@ def run_train(args):
     torch.manual_seed(0)
     model = svit_b200.SViT(cfg, compute_dtype=torch.bfloat16).to(dev).train()
     reducer = GradAllReducer(model.parameters()) if world > 1 else None
+    optimizer = None
+    if args.optimizer:
+        from svit_b200.optim import construct_optimizer
+        optimizer = construct_optimizer(model, cfg)
     gen = torch.Generator().manual_seed(1234 + rank)
     clips = [torch.randn(B, 3, 16, 224, 224, generator=gen).to(torch.bfloat16).to(dev) for _ in range(2)]
     labels = torch.randint(0, cfg.MODEL.NUM_CLASSES, (B,), generator=gen).to(dev)
@@ -424,6 +431,8 @@ def run_train(args):
         loss.backward()
         if reducer is not None:
             reducer.finish()
+        if optimizer is not None:
+            optimizer.step(max_norm=cfg.SOLVER.CLIP_GRAD_L2NORM)
         return loss
 
     def barrier():
@@ -453,6 +462,8 @@ def run_train(args):
                 "data": "synthetic", "gpu_launches": ops.launches() - l0, "loss": float(loss),
                 "config": {"workload": f"SViT (configs/ssv2.yaml) training step, batch {B} clips per GPU, random init, "
                                        "cross-entropy on the class logits, no optimizer step"
+                                       .replace("no optimizer step", "fused clip_grad_norm + AdamW step" if args.optimizer
+                                                else "no optimizer step")
                                        + (", + no-grad frames pass (B*16 frames, T=1)" if args.frames_pass else ""),
                            "parallelism": f"dp{world}", "global_batch": B * world}}
         print(json.dumps(line))

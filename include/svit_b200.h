@@ -198,6 +198,28 @@ int svit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, in
 int svit_match_haog(float* boxes, int64_t* contact, int64_t n, void* stream);
 int svit_zero_empty_boxes(float* boxes_cxcywh, int64_t n, float eps, void* stream);
 
+/* ---- fused optimizer step: clip_grad_norm_ + torch.optim.AdamW over all parameter tensors
+ * (tools/train_net.py:133-151, models/optimizer.py:89-104) in two launches.  `table` [ntensors] and the chunk map
+ * (chunk c covers elements [chunk_start[c], chunk_start[c] + chunk) of tensor chunk_tensor[c]) live in device memory;
+ * all tensors are fp32.  svit_grad_sqnorm writes sum(g^2) over every tensor to *out (zeroed first).  svit_adamw_step
+ * applies, per element and in torch's operation order, g *= min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) (skipped when
+ * max_norm <= 0 or sqnorm is NULL), p *= 1 - lr * wd, m = lerp(m, g, 1 - beta1), v = beta2 v + (1 - beta2) g^2,
+ * p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps). */
+typedef struct svit_optim_tensor {
+  void* param;
+  const void* grad;
+  void* exp_avg;
+  void* exp_avg_sq;
+  int64_t numel;
+  float weight_decay;
+  int32_t pad_;
+} svit_optim_tensor;
+int svit_grad_sqnorm(const svit_optim_tensor* table, const int32_t* chunk_tensor, const int64_t* chunk_start, int nchunks,
+                     int chunk, float* out, void* stream);
+int svit_adamw_step(const svit_optim_tensor* table, const int32_t* chunk_tensor, const int64_t* chunk_start, int nchunks,
+                    int chunk, float lr, float beta1, float beta2, float eps, int step, float max_norm, const float* sqnorm,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,7 +103,8 @@ _SSV2 = {
     },
     "TRAIN": {"DATASET": "ssv2", "FORWARD_VIDEO_FRAMES": True, "BATCH_SIZE": 63},
     "TEST": {"BATCH_SIZE": 64},
-    "SOLVER": {"CLIP_GRAD_L2NORM": 1.0, "BASE_LR": 2e-4, "WEIGHT_DECAY": 1e-4},
+    "SOLVER": {"CLIP_GRAD_L2NORM": 1.0, "BASE_LR": 2e-4, "WEIGHT_DECAY": 1e-4, "OPTIMIZING_METHOD": "adamw",
+               "ZERO_WD_1D_PARAM": True},
 }
 
 

@@ -1,0 +1,155 @@
+"""Fused optimizer step for the SViT training loop.
+
+Reference: `construct_optimizer` (slowfast/models/optimizer.py:15-112; configs/ssv2.yaml: AdamW, lr 2e-4, weight decay
+1e-4, ZERO_WD_1D_PARAM) and the step in tools/train_net.py:133-151 (`clip_grad_norm_(params, 1.0)` then
+`optimizer.step()`).  torch steps the 405 parameter tensors through foreach kernels after a separate norm pass; here a
+device-side pointer table drives two launches of libsvit_sm100.so (`svit_grad_sqnorm`, `svit_adamw_step`): the clip
+coefficient is computed on the device from the squared norm, so the step has no host synchronisation.
+
+`FusedAdamW` keeps torch.optim.AdamW's interface for what the loop uses (param_groups with per-group lr /
+weight_decay, `step()`, `zero_grad()`); results match torch.optim.AdamW to fp32 rounding
+(tests/test_gpu_parity.py::test_fused_adamw_matches_torch).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional
+
+import torch
+
+from . import _lib
+from .ops import _call, _stream
+
+CHUNK = 8192  # elements per scheduling unit
+
+
+def split_weight_decay_groups(model, weight_decay: float, zero_wd_1d: bool = True):
+    """The grouping rule of optimizer.py:31-58 (no BatchNorm on this path): 1-D parameters and biases get zero weight
+    decay when SOLVER.ZERO_WD_1D_PARAM, as do names returned by model.no_weight_decay()."""
+    skip = model.no_weight_decay() if hasattr(model, "no_weight_decay") else {}
+    decay, zero = [], []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        if name in skip or ((p.dim() == 1 or name.endswith(".bias")) and zero_wd_1d):
+            zero.append(p)
+        else:
+            decay.append(p)
+    groups = [{"params": decay, "weight_decay": weight_decay}, {"params": zero, "weight_decay": 0.0}]
+    return [g for g in groups if g["params"]]
+
+
+def construct_optimizer(model, cfg):
+    """optimizer.py:15-112 for OPTIMIZING_METHOD == 'adamw' (what configs/ssv2.yaml selects)."""
+    if cfg.SOLVER.OPTIMIZING_METHOD != "adamw":
+        raise NotImplementedError(f"Does not support {cfg.SOLVER.OPTIMIZING_METHOD} optimizer")
+    groups = split_weight_decay_groups(model, cfg.SOLVER.WEIGHT_DECAY, cfg.SOLVER.ZERO_WD_1D_PARAM)
+    return FusedAdamW(groups, lr=cfg.SOLVER.BASE_LR, eps=1e-8, weight_decay=cfg.SOLVER.WEIGHT_DECAY)
+
+
+class FusedAdamW:
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        params = list(params)
+        if params and not isinstance(params[0], dict):
+            params = [{"params": params}]
+        self.param_groups: List[dict] = []
+        for g in params:
+            g = dict(g)
+            g["params"] = [p for p in g["params"]]
+            g.setdefault("lr", lr)
+            g.setdefault("betas", betas)
+            g.setdefault("eps", eps)
+            g.setdefault("weight_decay", weight_decay)
+            self.param_groups.append(g)
+        self.state = {}
+        self._step = 0
+        self._tables = None
+        self._sqnorm = None
+
+    # ---- table construction -----------------------------------------------------------------------------------
+    def _build(self):
+        self._tables = []
+        for g in self.param_groups:
+            ps = [p for p in g["params"] if p.requires_grad]
+            if not ps:
+                self._tables.append(None)
+                continue
+            dev = ps[0].device
+            for p in ps:
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("FusedAdamW: parameters must be contiguous fp32 tensors")
+                if p not in self.state:
+                    self.state[p] = {"exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)}
+            tab = torch.zeros(len(ps), 6, dtype=torch.int64)
+            wd_bits = torch.tensor([g["weight_decay"]], dtype=torch.float32).view(torch.int32).item()
+            chunk_tensor, chunk_start = [], []
+            for i, p in enumerate(ps):
+                st = self.state[p]
+                tab[i, 0], tab[i, 2], tab[i, 3] = p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                tab[i, 4] = p.numel()
+                tab[i, 5] = wd_bits & 0xFFFFFFFF  # float in the low 4 bytes, padding above
+                for s in range(0, p.numel(), CHUNK):
+                    chunk_tensor.append(i)
+                    chunk_start.append(s)
+            self._tables.append({
+                "params": ps, "host": tab.pin_memory() if torch.cuda.is_available() else tab,
+                "dev": torch.empty(len(ps), 6, dtype=torch.int64, device=dev),
+                "chunk_tensor": torch.tensor(chunk_tensor, dtype=torch.int32, device=dev),
+                "chunk_start": torch.tensor(chunk_start, dtype=torch.int64, device=dev),
+                "nchunks": len(chunk_tensor), "wd": g["weight_decay"], "grad_ptrs": None})
+        dev = next(t for t in self._tables if t is not None)["dev"].device
+        self._sqnorm = torch.zeros(len(self._tables) + 1, dtype=torch.float32, device=dev)
+
+    def _refresh(self, t):
+        """Gradient pointers change whenever autograd allocates fresh .grad tensors: re-upload the table when they did."""
+        ptrs = []
+        for p in t["params"]:
+            g = p.grad
+            if g is None:  # torch.optim skips parameters without a gradient: a zero-length table entry does the same
+                ptrs.append(0)
+                continue
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                raise RuntimeError("FusedAdamW: gradients must be contiguous fp32 tensors")
+            ptrs.append(g.data_ptr())
+        if ptrs != t["grad_ptrs"]:
+            t["host"][:, 1] = torch.tensor(ptrs, dtype=torch.int64)
+            t["host"][:, 4] = torch.tensor([p.numel() if a else 0 for p, a in zip(t["params"], ptrs)], dtype=torch.int64)
+            t["dev"].copy_(t["host"], non_blocking=True)
+            t["grad_ptrs"] = ptrs
+
+    # ---- public API -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, max_norm: Optional[float] = None):
+        """One AdamW step over every group; `max_norm` fuses torch.nn.utils.clip_grad_norm_(all params, max_norm)."""
+        if self._tables is None:
+            self._build()
+        self._step += 1
+        live = [(g, t) for g, t in zip(self.param_groups, self._tables) if t is not None]
+        for _, t in live:
+            self._refresh(t)
+        total = None
+        if max_norm is not None and max_norm > 0:
+            for i, (_, t) in enumerate(live):
+                _call("svit_grad_sqnorm", t["dev"].data_ptr(), t["chunk_tensor"].data_ptr(), t["chunk_start"].data_ptr(),
+                      t["nchunks"], CHUNK, self._sqnorm[i:].data_ptr(), _stream())
+            total = self._sqnorm[len(live):len(live) + 1]
+            torch.sum(self._sqnorm[:len(live)], dim=0, keepdim=True, out=total)  # norm over all groups
+        for g, t in live:
+            b1, b2 = g["betas"]
+            _call("svit_adamw_step", t["dev"].data_ptr(), t["chunk_tensor"].data_ptr(), t["chunk_start"].data_ptr(),
+                  t["nchunks"], CHUNK, float(g["lr"]), float(b1), float(b2), float(g["eps"]), self._step,
+                  float(max_norm) if total is not None else 0.0, total.data_ptr() if total is not None else None, _stream())
+
+    def grad_norm(self) -> torch.Tensor:
+        """Total gradient norm seen by the last clipped step (device scalar)."""
+        n = sum(1 for t in self._tables if t is not None)
+        return self._sqnorm[n].sqrt()
+
+    def zero_grad(self, set_to_none: bool = True):
+        for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is not None:
+                    if set_to_none:
+                        p.grad = None
+                    else:
+                        p.grad.zero_()

@@ -498,3 +498,32 @@ def test_frames_pass_full_ssv2_vs_oracle():
     lam = dict(m._lambda, video_image_desc_l1_loss=1.5)
     got = consistency_loss(lam, vid, extra)["video_image_desc_l1_loss"]
     assert abs(float(got) - float(want["obj_desc"].abs().mean())) < 2e-2 * float(want["obj_desc"].abs().mean()) + 1e-6
+
+
+def test_fused_adamw_matches_torch():
+    """clip_grad_norm_(1.0) + torch.optim.AdamW over two weight-decay groups (optimizer.py:31-104,
+    train_net.py:133-151) against the two-launch fused step, three steps, odd tensor sizes, fresh .grad tensors each step."""
+    from svit_b200.optim import FusedAdamW
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(96, 1, 3, 3, 3), (288, 96), (288,), (8193,), (1, 1, 96), (17, 33)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=gen).to(DEV)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    def groups(ps):
+        return [{"params": [p for p in ps if p.dim() > 1], "weight_decay": 1e-2},
+                {"params": [p for p in ps if p.dim() == 1], "weight_decay": 0.0}]
+    ref = torch.optim.AdamW(groups(ref_p), lr=2e-3, eps=1e-8)
+    ours = FusedAdamW(groups(our_p), lr=2e-3, eps=1e-8)
+    for step in range(3):
+        grads = [torch.randn(s, generator=gen).to(DEV) * (3.0 if step == 1 else 0.01) for s in shapes]  # clipped / not
+        for p, q, g in zip(ref_p, our_p, grads):
+            p.grad, q.grad = g.clone(), g.clone()
+        norm = torch.nn.utils.clip_grad_norm_(ref_p, 1.0)
+        ref.step()
+        ours.step(max_norm=1.0)
+        assert abs(float(ours.grad_norm()) - float(norm)) <= 1e-5 * float(norm)
+        for p, q in zip(ref_p, our_p):
+            assert max_rel_err(cpu(q), cpu(p)) < 2e-6, (step, tuple(p.shape))
+    for p, q in zip(ref_p, our_p):
+        # second moments: (1 - beta2) g * g is rounded in a different order than addcmul_ and g carries the clip factor
+        assert max_rel_err(cpu(ours.state[q]["exp_avg_sq"]), cpu(ref.state[p]["exp_avg_sq"])) < 5e-5
+        assert max_rel_err(cpu(ours.state[q]["exp_avg"]), cpu(ref.state[p]["exp_avg"])) < 5e-6
