@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel breakdown here")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--host-input", default="uint8", choices=["uint8", "bf16"],
+                    help="e2e leg: what crosses PCIe each step -- decoded uint8 frames [B,T,H,W,3] (normalised on the "
+                         "device by svit_normalize_u8, datasets/utils.py:287-303) or pre-normalised bf16 clips")
     ap.add_argument("--optimizer", action="store_true",
                     help="train mode: finish the step with the fused clip_grad_norm(1.0) + AdamW update "
                          "(svit_b200.optim, SOLVER settings of configs/ssv2.yaml)")
@@ -255,7 +258,13 @@ def main():
         # ---- end to end: pinned host clips -> H2D (copy stream, double buffered) -> forward -> D2H of the probabilities
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream()
-        staged = [torch.empty_like(dev_in[0]) for _ in range(2)]
+        model_e2e = model
+        if args.host_input == "uint8":  # frames as the decoder leaves them; the graph starts with the normalise kernel
+            host = [torch.randint(0, 256, (B, 16, 224, 224, 3), generator=gen, dtype=torch.uint8).pin_memory()
+                    for _ in range(2)]
+            if not args.no_graph:
+                model_e2e = svit_b200.GraphedForward(eager, host[0].to(dev))
+        staged = [torch.empty(host[0].shape, dtype=host[0].dtype, device=dev) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
 
@@ -267,7 +276,7 @@ def main():
                     staged[j].copy_(host[j], non_blocking=True)
                     ready[j].record(copy_stream)
                 main_stream.wait_event(ready[j])
-                out, _ = model([staged[j]] if args.no_graph else staged[j])
+                out, _ = model_e2e([staged[j]] if args.no_graph else staged[j])
                 freed[j].record(main_stream)
                 probs_host.copy_(out, non_blocking=True)
 
@@ -362,7 +371,7 @@ def main():
                                    f"batch {B} clips per GPU, random init",
                        "parallelism": f"dp{world}", "global_batch": B * world,
                        "l2_policy": "inputs larger than L2 (308 MB of bf16 clips per step, >1 GB activations)",
-                       "host_input_dtype": "bf16", "launch": "eager" if args.no_graph else "cuda graph replay"},
+                       "host_input_dtype": args.host_input, "launch": "eager" if args.no_graph else "cuda graph replay"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": "clips/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": host[0].numel() * host[0].element_size(),

@@ -198,6 +198,11 @@ int svit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, in
 int svit_match_haog(float* boxes, int64_t* contact, int64_t n, void* stream);
 int svit_zero_empty_boxes(float* boxes_cxcywh, int64_t n, float eps, void* stream);
 
+/* ---- input side: uint8 frames [B, T, H, W, 3] -> normalised [B, 3, T, H, W] (bf16 or fp32), the
+ * arithmetic of datasets/utils.py:287-303 (x / 255 - mean) / std in fp32.  T*H*W must be a multiple of 16. */
+int svit_normalize_u8(const void* frames, void* out, int B, int T, int H, int W, float mean0, float mean1, float mean2,
+                      float std0, float std1, float std2, int out_dtype, void* stream);
+
 /* ---- fused optimizer step: clip_grad_norm_ + torch.optim.AdamW over all parameter tensors
  * (tools/train_net.py:133-151, models/optimizer.py:89-104) in two launches.  `table` [ntensors] and the chunk map
  * (chunk c covers elements [chunk_start[c], chunk_start[c] + chunk) of tensor chunk_tensor[c]) live in device memory;

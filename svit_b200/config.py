@@ -51,6 +51,8 @@ _SSV2 = {
         "TRAIN_CROP_SIZE": 224,
         "TEST_CROP_SIZE": 224,
         "INPUT_CHANNEL_NUM": [3],
+        "MEAN": [0.45, 0.45, 0.45],   # config/defaults.py DATA.MEAN / DATA.STD (configs/ssv2.yaml does not override)
+        "STD": [0.225, 0.225, 0.225],
     },
     "MODEL": {
         "NUM_CLASSES": 174,

@@ -311,3 +311,70 @@ int svit_im2col_rows(const void* x, void* cols, int B, int Cin, int T, int H, in
   e = cudaGetLastError();
   return e == cudaSuccess ? 1 : 1000 + (int)e;
 }
+
+
+// ------------------------------------------------------------------------------------------------ uint8 frames
+// Input side of the path: decoded frames arrive as uint8 [B, T, H, W, 3]; the reference normalises on
+// the CPU (datasets/utils.py:287-303: x / 255, - mean, / std in fp32) and permutes to [B, 3, T, H, W] before the
+// host -> device copy of 4 bytes per value.  Here the uint8 frames are what crosses PCIe (1 byte per value) and one
+// streaming kernel does normalise + layout change + cast: thread = 16 consecutive pixels of a row (48 bytes in, 3 x 16
+// values out), same fp32 operation order as the reference so the fp32 output is bit-identical.
+template <typename OT>
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ in, OT* __restrict__ out, int64_t npix16,
+                                                           int64_t THW, float m0, float m1, float m2, float s0, float s1,
+                                                           float s2) {
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix16; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 16;          // first pixel (b, t, h, w) flattened; THW % 16 == 0 keeps a unit inside one sample
+    const int64_t b = pix / THW, r = pix - b * THW;
+    const uint4* src = reinterpret_cast<const uint4*>(in + pix * 3);
+    const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+    const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    float v[3][16];
+#pragma unroll
+    for (int k = 0; k < 48; ++k) {
+      const float f = (float)((w[k >> 2] >> ((k & 3) * 8)) & 255u);
+      const int c = k % 3;
+      v[c][k / 3] = __fdiv_rn(__fsub_rn(__fdiv_rn(f, 255.0f), mean[c]), sd[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      OT* dst = out + (b * 3 + c) * THW + r;
+      if (sizeof(OT) == 2) {
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[c][2 * k], v[c][2 * k + 1]);
+          o[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          reinterpret_cast<float4*>(dst)[k] = make_float4(v[c][4 * k], v[c][4 * k + 1], v[c][4 * k + 2], v[c][4 * k + 3]);
+      }
+    }
+  }
+}
+
+extern "C" int svit_normalize_u8(const void* frames, void* out, int B, int T, int H, int W, float mean0, float mean1,
+                                 float mean2, float std0, float std1, float std2, int out_dtype, void* stream) {
+  if (!frames || !out || B < 0 || T < 1 || H < 1 || W < 1) return SVIT_EINVAL;
+  const int64_t THW = (int64_t)T * H * W;
+  if (THW % 16 || (reinterpret_cast<uintptr_t>(frames) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return SVIT_ENOTSUP;
+  if (B == 0) return 0;
+  const int64_t n16 = (int64_t)B * THW / 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t grid = (n16 + 255) / 256;
+  const int64_t cap = (int64_t)svit_num_sms() * 16;
+  if (grid > cap) grid = cap;
+  if (out_dtype == SVIT_BF16)
+    normalize_u8_kernel<bf16><<<(unsigned)grid, 256, 0, st>>>((const uint8_t*)frames, (bf16*)out, n16, THW, mean0, mean1, mean2, std0, std1, std2);
+  else if (out_dtype == SVIT_F32)
+    normalize_u8_kernel<float><<<(unsigned)grid, 256, 0, st>>>((const uint8_t*)frames, (float*)out, n16, THW, mean0, mean1, mean2, std0, std1, std2);
+  else
+    return SVIT_EINVAL;
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}

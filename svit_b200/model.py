@@ -152,6 +152,9 @@ class SViT(nn.Module):
     def forward_tokens(self, clip):
         """clip [B,3,T,H,W] (or [B,3,H,W] frame mode) -> (normed tokens [B, N, C], thw, Tx)."""
         x = clip
+        if x.dtype == torch.uint8:  # decoded frames [B, T, H, W, 3]: normalise + CTHW layout on the device (8f N4)
+            x = clip = ops.normalize_u8(x, self.cfg.DATA.MEAN, self.cfg.DATA.STD,
+                                        torch.float32 if self.compute_dtype == torch.float32 else torch.bfloat16)
         if x.ndim == 4:
             x = x.unsqueeze(2)
         Tx = x.shape[2]

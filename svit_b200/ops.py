@@ -739,6 +739,20 @@ def roi_align_nhwc(feat_nhwc, rois, out_size, spatial_scale, sampling_ratio=0, a
     return out
 
 
+def normalize_u8(frames: torch.Tensor, mean, std, dtype=torch.bfloat16) -> torch.Tensor:
+    """uint8 frames [B, T, H, W, 3] -> normalised clip [B, 3, T, H, W] (datasets/utils.py:287-303 + the THWC -> CTHW
+    permute of the loaders) in one streaming kernel; the uint8 tensor is what crosses PCIe."""
+    if frames.dtype != torch.uint8 or frames.dim() != 5 or frames.shape[-1] != 3:
+        raise ValueError("normalize_u8 expects uint8 [B, T, H, W, 3]")
+    _chk(frames, "normalize_u8")
+    frames = frames.contiguous()
+    B, T, H, W, _ = frames.shape
+    out = torch.empty(B, 3, T, H, W, dtype=dtype, device=frames.device)
+    _call("svit_normalize_u8", frames.data_ptr(), out.data_ptr(), B, T, H, W, float(mean[0]), float(mean[1]), float(mean[2]),
+          float(std[0]), float(std[1]), float(std[2]), _dt(out), _stream())
+    return out
+
+
 def match_haog_device(boxes):
     """boxes [n,4,4] fp32 CUDA (modified in place) -> contact [n,2] int64 (utils/box_ops.py:140-194)."""
     _chk(boxes, "match_haog")

@@ -527,3 +527,27 @@ def test_fused_adamw_matches_torch():
         # second moments: (1 - beta2) g * g is rounded in a different order than addcmul_ and g carries the clip factor
         assert max_rel_err(cpu(ours.state[q]["exp_avg_sq"]), cpu(ref.state[p]["exp_avg_sq"])) < 5e-5
         assert max_rel_err(cpu(ours.state[q]["exp_avg"]), cpu(ref.state[p]["exp_avg"])) < 5e-6
+
+
+def test_normalize_u8_bit_exact_and_model_accepts_frames():
+    """uint8 frames [B,T,H,W,3] -> (x/255 - mean)/std, CTHW layout (datasets/utils.py:287-303): fp32 output
+    bit-identical to the reference expression, bf16 output = its rounding; SViT.forward takes the uint8 tensor directly."""
+    gen = torch.Generator().manual_seed(11)
+    frames = torch.randint(0, 256, (2, 4, 32, 32, 3), generator=gen, dtype=torch.uint8)
+    mean, std = [0.45, 0.40, 0.35], [0.225, 0.25, 0.2]
+    ref = ((frames.float() / 255.0 - torch.tensor(mean)) / torch.tensor(std)).permute(0, 4, 1, 2, 3).contiguous()
+    got32 = ops.normalize_u8(frames.to(DEV), mean, std, torch.float32)
+    assert torch.equal(cpu(got32), ref)
+    got16 = ops.normalize_u8(frames.to(DEV), mean, std, torch.bfloat16)
+    assert torch.equal(cpu(got16), ref.bfloat16().float())
+    cfg = tiny_cfg()
+    m = svit_b200.SViT(cfg, compute_dtype=torch.float32).to(DEV).eval()
+    ops.set_impl(gemm=ops.IMPL_SIMT, attn=ops.IMPL_SIMT)
+    try:
+        with torch.no_grad():
+            a, _ = m([frames.to(DEV)])
+            clip = ((frames.float() / 255.0 - torch.tensor(cfg.DATA.MEAN)) / torch.tensor(cfg.DATA.STD)).permute(0, 4, 1, 2, 3)
+            b, _ = m([clip.contiguous().to(DEV)])
+    finally:
+        ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+    assert torch.equal(a, b)
