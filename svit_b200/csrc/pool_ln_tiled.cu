@@ -273,7 +273,8 @@ struct CpDims {
   static constexpr int OFF_AFF = OFF_TOK + ((NTOK * 8 + 15) & ~15);   // int64 token index per staged token
   static constexpr int OFF_W = OFF_AFF + 3 * PD * 4;                   // gamma, beta, w_eff
   static constexpr int OFF_BAR = OFF_W + TAPS * (PD / 2) * 8;          // tap weights as float2 [27][48]
-  static constexpr int SMEM = OFF_BAR + 64;                            // one mbarrier per ring slot
+  static constexpr int OFF_RED = OFF_BAR + 64;                         // one mbarrier per ring slot, then
+  static constexpr int SMEM = OFF_RED + 2 * 24 * 16 * 4;               // LayerNorm partial sums [2][24 groups][16]
 };
 
 __device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
@@ -438,6 +439,64 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
     }
   };
 
+  // LayerNorm of a finished output plane straight from the accumulators (no staging tile, no CTA barrier): the 96
+  // channels of a token live in the 48 threads of its strip = three 16-lane groups.  Sum and sum of squares of the
+  // thread's SW tokens (padded to 16 values) go through a transposing butterfly (15 shuffles: lane l of a group ends
+  // with the group total of value l), the three groups of a strip meet in shared memory behind a 96-thread named
+  // barrier (two strips = three warps), and every thread normalises and stores its own channel pair.
+  float* red = reinterpret_cast<float*>(smem + D::OFF_RED);
+  const float2 gam = make_float2(__ldg(gamma + 2 * wd), __ldg(gamma + 2 * wd + 1));
+  const float2 bet = make_float2(__ldg(beta + 2 * wd), __ldg(beta + 2 * wd + 1));
+  auto ln_direct = [&](float2 (&set)[SW], int t, int buf) {
+    float v[16];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      if (o < SW) {
+        v[o] = set[o].x + set[o].y;
+        v[8 + o] = fmaf(set[o].x, set[o].x, set[o].y * set[o].y);
+      } else {
+        v[o] = v[8 + o] = 0.f;
+      }
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+      const bool up = (lane & w) != 0;
+#pragma unroll
+      for (int i = 0; i < w; ++i) {
+        const float send = up ? v[i] : v[i + w];
+        const float keep = up ? v[i + w] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+      }
+    }
+    const int g16 = threadIdx.x >> 4;
+    float* rb = red + buf * (24 * 16);
+    rb[g16 * 16 + (lane & 15)] = v[0];
+    asm volatile("bar.sync %0, 96;" ::"r"(1 + (strip >> 1)) : "memory");
+    const float4* r4 = reinterpret_cast<const float4*>(rb + strip * 48);
+    float tot[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 a = r4[k], b = r4[4 + k], c = r4[8 + k];
+      tot[4 * k] = a.x + b.x + c.x; tot[4 * k + 1] = a.y + b.y + c.y;
+      tot[4 * k + 2] = a.z + b.z + c.z; tot[4 * k + 3] = a.w + b.w + c.w;
+    }
+#pragma unroll
+    for (int o = 0; o < SW; ++o) {
+      const float mean = tot[o] * (1.f / PD);
+      const float var = fmaxf(tot[8 + o] * (1.f / PD) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      const int wo = wo0 + scol + o;
+      const bool ok = ho < g.Ho && scol + o < C::TW && wo < g.Wo;
+      if (ok) {
+        const int64_t tok = 1 + ((int64_t)t * g.Ho + ho) * g.Wo + wo;
+        const float y0 = fmaf((set[o].x - mean) * rstd, gam.x, bet.x), y1 = fmaf((set[o].y - mean) * rstd, gam.y, bet.y);
+        reinterpret_cast<uint32_t*>(obase + tok * PD)[wd] = pack2(y0, y1);
+      }
+      set[o] = make_float2(0.f, 0.f);
+    }
+  };
+
   int tl_n = 0;
   (void)tl_n;
   auto step = [&](auto rtag, int tp) {
@@ -473,10 +532,7 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
       }
     }
     PTL(400 + tp);
-    if (tp >= 1) stage_out(acc[(R + 2) % 3], tp - 1);  // output plane tp-1 has now seen planes tp-2, tp-1, tp
-    __syncthreads();
-    PTL(500 + tp);
-    if (tp >= 1) cp_ln_flush(stg, stg_tok, aff, D::NTOK, eps, obase);
+    if (tp >= 1) ln_direct(acc[(R + 2) % 3], tp - 1, tp & 1);  // output plane tp-1 has now seen planes tp-2, tp-1, tp
     PTL(600 + tp);
   };
   for (int tp0 = 0; tp0 < g.T; tp0 += 3) {
@@ -485,15 +541,12 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
     if (tp0 + 2 < g.T) step(std::integral_constant<int, 2>{}, tp0 + 2);
   }
   // last output plane T-1 (its t+1 neighbour is zero padding)
-  __syncthreads();
   {
     const int a = (g.T - 1) % 3;
-    if (a == 0) stage_out(acc[0], g.T - 1);
-    else if (a == 1) stage_out(acc[1], g.T - 1);
-    else stage_out(acc[2], g.T - 1);
+    if (a == 0) ln_direct(acc[0], g.T - 1, g.T & 1);
+    else if (a == 1) ln_direct(acc[1], g.T - 1, g.T & 1);
+    else ln_direct(acc[2], g.T - 1, g.T & 1);
   }
-  __syncthreads();
-  cp_ln_flush(stg, stg_tok, aff, D::NTOK, eps, obase);
   // cls + object tokens of this (batch, head): tile 0, through the same staging / LayerNorm path
   if (tile == 0) {
     float* sweff = aff + 2 * PD;
