@@ -156,7 +156,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc::tma_load_2d(smem + OFF_T + TP * 128, &tmap_t, &bars[BAR_T_FULL], 64, ps * TP);
       }
       tc::mbar_wait(&bars[BAR_E_EMPTY], (p.n_pass - 1) & 1);  // tables + staging alias the K/V buffers
-      for (int j = 0; j < p.n_tiles; ++j) {
+      // the K request of tile j+1 goes out before the V request of tile j (a V stage frees up late in a tile period;
+      // see attn_tc3.cu)
+      auto load_k = [&](int j) {
         const int ks = j & 1;
         const int n0 = key_start<KW>(p, j);
         tc::mbar_wait(&bars[BAR_K_EMPTY0 + ks], ((j >> 1) & 1) ^ 1);
@@ -165,12 +167,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc::mbar_arrive_expect_tx(&bars[BAR_K_FULL0 + ks], 16384);
         tc::tma_load_3d(kd, &tmap_k, &bars[BAR_K_FULL0 + ks], 0, n0, bh);
         tc::tma_load_3d(kd + 8192, &tmap_k, &bars[BAR_K_FULL0 + ks], 64, n0, bh);
+      };
+      auto load_v = [&](int j) {
+        const int ks = j & 1;
+        const int n0 = key_start<KW>(p, j);
         tc::mbar_wait(&bars[BAR_V_EMPTY0 + ks], ((j >> 1) & 1) ^ 1);
         TL(0, 200 + j);
         unsigned char* vd = smem + OFF_V + ks * 16384;
         tc::mbar_arrive_expect_tx(&bars[BAR_V_FULL0 + ks], 16384);
         tc::tma_load_3d(vd, &tmap_v, &bars[BAR_V_FULL0 + ks], 0, n0, bh);
         tc::tma_load_3d(vd + 8192, &tmap_v, &bars[BAR_V_FULL0 + ks], 64, n0, bh);
+      };
+      load_k(0);
+      for (int j = 0; j < p.n_tiles; ++j) {
+        if (j + 1 < p.n_tiles) load_k(j + 1);
+        load_v(j);
       }
     }
   } else if (warp == 1) {

@@ -161,7 +161,11 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       tc::mbar_arrive_expect_tx(&bars[BAR_Q_FULL], 16384 + 8192);
       tc::tma_load_3d(smem + OFF_Q0, &tmap_q0, &bars[BAR_Q_FULL], 0, r0, bh);
       tc::tma_load_3d(smem + OFF_Q1, &tmap_q1, &bars[BAR_Q_FULL], 64, r0, bh);
-      auto load_kv = [&](int j) {
+      // K (+ Sel) and V tiles are requested separately: the K tile of key tile j+1 goes out BEFORE the V tile of tile j.
+      // A V stage frees up only when the P.V MMA two tiles back has completed (late in a tile period); queueing the
+      // next K request behind that wait made every score MMA start ~800 cycles after its operands could have been
+      // there (TMA latency ~1.5k cycles; tools/attn_timeline.py).
+      auto load_k = [&](int j) {
         const int ks = j & 1;
         const int n0 = j * BN;
         tc::mbar_wait(&bars[BAR_K_EMPTY0 + ks], ((j >> 1) & 1) ^ 1);
@@ -172,12 +176,17 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
         tc::tma_load_3d(kd + K1_OFF, &tmap_k1, &bars[BAR_K_FULL0 + ks], 64, n0, bh);
         tc::tma_load_2d(kd + SEL_OFF, &tmap_sel, &bars[BAR_K_FULL0 + ks], 0, n0);
         if (X16) tc::tma_load_2d(kd + SEL2_OFF, &tmap_sel2, &bars[BAR_K_FULL0 + ks], EK, n0);
+      };
+      auto load_v = [&](int j) {
+        const int ks = j & 1;
+        const int n0 = j * BN;
         tc::mbar_wait(&bars[BAR_V_EMPTY0 + ks], ((j >> 1) & 1) ^ 1);
         unsigned char* vd = smem + (ks ? OFF_V1 : OFF_V0);
         tc::mbar_arrive_expect_tx(&bars[BAR_V_FULL0 + ks], V_STAGE);
         tc::tma_load_3d(vd, &tmap_v, &bars[BAR_V_FULL0 + ks], 0, n0, bh);
         tc::tma_load_3d(vd + 8192, &tmap_v, &bars[BAR_V_FULL0 + ks], 64, n0, bh);
       };
+      auto load_kv = [&](int j) { load_k(j); load_v(j); };
       tc::mbar_arrive_expect_tx(&bars[BAR_T_FULL], 2 * TP * 128);
       tc::tma_load_2d(smem + OFF_T, &tmap_t, &bars[BAR_T_FULL], 0, 0);
       tc::tma_load_2d(smem + OFF_T + TP * 128, &tmap_t, &bars[BAR_T_FULL], 64, 0);
@@ -189,7 +198,11 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
         tc::tma_load_2d(smem + OFF_T + TP * 128, &tmap_t, &bars[BAR_T_FULL], 64, ps * TP);
       }
       tc::mbar_wait(&bars[BAR_E_EMPTY], (p.n_pass - 1) & 1);  // tables + staging alias stage 1 of the K/V ring
-      for (int j = 1; j < p.n_tiles; ++j) load_kv(j);
+      if (p.n_tiles > 1) load_k(1);
+      for (int j = 1; j < p.n_tiles; ++j) {
+        if (j + 1 < p.n_tiles) load_k(j + 1);
+        load_v(j);
+      }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
