@@ -139,6 +139,11 @@ class FusedAdamW:
             _call("svit_adamw_step", t["dev"].data_ptr(), t["chunk_tensor"].data_ptr(), t["chunk_start"].data_ptr(),
                   t["nchunks"], CHUNK, float(g["lr"]), float(b1), float(b2), float(g["eps"]), self._step,
                   float(max_norm) if total is not None else 0.0, total.data_ptr() if total is not None else None, _stream())
+            # the kernel writes the parameters through raw pointers: tell autograd / the bf16 weight caches
+            # (ops.cast_weight keys on param._version) that they changed
+            for p, gp in zip(t["params"], t["grad_ptrs"]):
+                if gp:
+                    torch._C._increment_version(p)
 
     def grad_norm(self) -> torch.Tensor:
         """Total gradient norm seen by the last clipped step (device scalar)."""

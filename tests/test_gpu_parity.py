@@ -551,3 +551,20 @@ def test_normalize_u8_bit_exact_and_model_accepts_frames():
     finally:
         ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
     assert torch.equal(a, b)
+
+
+def test_fused_adamw_invalidates_weight_caches():
+    """The fused step writes parameters through raw pointers; the bf16 GEMM-weight cache (keyed on param._version)
+    must see the update: a linear layer evaluated after the step uses the new weights."""
+    from svit_b200.optim import FusedAdamW
+    gen = torch.Generator().manual_seed(9)
+    w = torch.nn.Parameter(torch.randn(96, 96, generator=gen).to(DEV))
+    x = torch.randn(128, 96, generator=gen).to(torch.bfloat16).to(DEV)
+    y0 = ops.linear(x, w)
+    opt = FusedAdamW([w], lr=0.5, weight_decay=0.0)
+    w.grad = torch.ones_like(w)
+    opt.step()
+    y1 = ops.linear(x, w)
+    ref = x.float() @ w.detach().float().bfloat16().float().t()
+    assert max_rel_err(cpu(y1), cpu(ref)) < 1e-2
+    assert max_rel_err(cpu(y0), cpu(ref)) > 1e-1  # the step really moved the weights
