@@ -248,6 +248,50 @@ def box_cases():
     save("boxes.pt", dict(match_haog=cases, zero_empty=zcases))
 
 
+# ---------------------------------------------------------------- N2 losses (models/losses.py:50-168)
+def loss_cases():
+    """boxes_loss_ and VideoImageLoss._haog_loss / forward of the unmodified reference on seeded predictions:
+    values and gradients w.r.t. the predictions, incl. the 'no valid target' branches and the 5-column soft-mask form."""
+    import importlib
+    import types
+    L = importlib.import_module("slowfast.models.losses")
+    rng = np.random.RandomState(77)
+    cases = []
+    for i in range(8):
+        B_, T_, O_ = 2 + i % 2, 1 + (i % 3), 4
+        pred = torch.from_numpy(rng.randn(B_, T_, O_, 5).astype(np.float32))
+        pred[..., 1:] = torch.sigmoid(pred[..., 1:])                      # (cx, cy, w, h) in (0, 1)
+        tar = torch.from_numpy(rng.rand(B_, T_, O_, 4).astype(np.float32)) * 0.5 + 0.2
+        drop = torch.from_numpy(rng.rand(B_, T_, O_) < (1.1 if i == 3 else 0.35))  # case 3: no valid target at all
+        tar[drop] = 0
+        if i % 4 == 2:                                                       # 5-column target with a soft mask
+            tar = torch.cat([torch.from_numpy(rng.rand(B_, T_, O_, 1).astype(np.float32)), tar], -1)
+        p = pred.clone().requires_grad_(True)
+        l1, bce, giou = L.boxes_loss_(p, tar)
+        (l1 + 2 * bce + 3 * giou).backward()
+        cases.append(dict(pred=pred, tar=tar, l1=l1.detach(), bce=bce.detach(), giou=giou.detach(), dpred=p.grad.clone()))
+    haog = []
+    cfg = ssv2_cfg()
+    for i in range(4):
+        B_ = 3
+        pb = torch.from_numpy(rng.randn(B_, 1, 4, 5).astype(np.float32)); pb[..., 1:] = torch.sigmoid(pb[..., 1:])
+        pc = torch.from_numpy(rng.randn(B_, 1, 2, 5).astype(np.float32))
+        tb = torch.from_numpy(rng.rand(B_, 1, 4, 4).astype(np.float32)) * 0.5 + 0.2
+        tb[torch.from_numpy(rng.rand(B_, 1, 4) < 0.3)] = 0
+        cs = torch.from_numpy(rng.randint(-1, 5, (B_, 2)).astype(np.int64))
+        if i == 2: cs[:] = -1                                               # no annotated hand at all
+        stub = types.SimpleNamespace(ce_loss=nn.CrossEntropyLoss(reduction="mean"), cfg=cfg,
+                                     get_default_val=lambda: torch.tensor(0., requires_grad=True))
+        a, c = pb.clone().requires_grad_(True), pc.clone().requires_grad_(True)
+        out = L.VideoImageLoss._haog_loss(stub, {"pred_bboxes": a, "pred_contact_state": c},
+                                          {"haog_bboxes": tb, "contact_state": cs})
+        sum(out.values()).backward()
+        haog.append(dict(pred_bboxes=pb, pred_contact_state=pc, haog_bboxes=tb, contact_state=cs,
+                         out={k: v.detach() for k, v in out.items()}, dboxes=a.grad.clone(),
+                         dcontact=c.grad.clone() if c.grad is not None else torch.zeros_like(pc)))
+    save("losses.pt", dict(boxes=cases, haog=haog))
+
+
 if __name__ == "__main__":
     relpos_tables()
     pool_cases()
@@ -255,3 +299,4 @@ if __name__ == "__main__":
     block_cases()
     model_cases()
     box_cases()
+    loss_cases()
