@@ -258,13 +258,18 @@ def main():
         # ---- end to end: pinned host clips -> H2D (copy stream, double buffered) -> forward -> D2H of the probabilities
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream()
-        model_e2e = model
-        if args.host_input == "uint8":  # frames as the decoder leaves them; the graph starts with the normalise kernel
+        u8 = args.host_input == "uint8"
+        if u8:  # frames as the decoder leaves them: one normalise kernel (svit_normalize_u8) in front of the same graph
             host = [torch.randint(0, 256, (B, 16, 224, 224, 3), generator=gen, dtype=torch.uint8).pin_memory()
                     for _ in range(2)]
-            if not args.no_graph:
-                model_e2e = svit_b200.GraphedForward(eager, host[0].to(dev))
         staged = [torch.empty(host[0].shape, dtype=host[0].dtype, device=dev) for _ in range(2)]
+        mean, std = cfg.DATA.MEAN, cfg.DATA.STD
+
+        def model_e2e(inp):
+            x = inp[0] if args.no_graph else inp
+            if u8:
+                x = ops.normalize_u8(x, mean, std, torch.bfloat16)
+            return model([x]) if args.no_graph else model(x)
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
 
