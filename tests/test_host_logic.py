@@ -94,3 +94,48 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_backward_key_selection_matrix():
+    """dS @ Sel (the GEMM form of the rel-pos bias gradient, attn_bwd_tc.cu) equals the direct sums
+    dE_h[r, i'] = sum over patch keys with row i' of dS[r, key] (likewise w, t); cls / object keys contribute nothing."""
+    import torch
+    from svit_b200.ops import key_select_table_bwd
+    kt, kh, kw, O = 3, 4, 5, 6
+    nep = (kt + kh + kw + 7) // 8 * 8
+    sel = key_select_table_bwd((kt, kh, kw), O, nep, "cpu").float()
+    Nk = 1 + kt * kh * kw + O
+    assert sel.shape == (Nk, nep)
+    g = torch.Generator().manual_seed(0)
+    dS = torch.randn(7, Nk, generator=g)
+    got = dS @ sel
+    patch = dS[:, 1:1 + kt * kh * kw].reshape(7, kt, kh, kw)
+    assert torch.allclose(got[:, :kh], patch.sum((1, 3)), atol=1e-5)
+    assert torch.allclose(got[:, kh:kh + kw], patch.sum((1, 2)), atol=1e-5)
+    assert torch.allclose(got[:, kh + kw:kh + kw + kt], patch.sum((2, 3)), atol=1e-5)
+    assert float(got[:, kh + kw + kt:].abs().max()) == 0.0
+    assert float(sel[0].abs().max()) == 0.0 and float(sel[1 + kt * kh * kw:].abs().max()) == 0.0
+
+
+def test_weight_decay_groups_match_reference_construct_optimizer():
+    """svit_b200.optim.split_weight_decay_groups against the unmodified reference's construct_optimizer
+    (models/optimizer.py:31-58) on the tiny SViT: same parameters in the decay / zero-decay groups."""
+    import importlib
+    import pytest
+    import torch
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not mounted (GPU box)")
+    ref_loader.load()
+    ref_opt = importlib.import_module("slowfast.models.optimizer")
+    import svit_b200
+    from svit_b200.config import tiny_cfg
+    from svit_b200.optim import split_weight_decay_groups
+    cfg = tiny_cfg()
+    cfg.BN = type(cfg)({"WEIGHT_DECAY": 0.0}) if not hasattr(cfg, "BN") else cfg.BN
+    model = svit_b200.SViT(cfg, compute_dtype=torch.float32)
+    want = ref_opt.construct_optimizer(model, cfg)
+    got = split_weight_decay_groups(model, cfg.SOLVER.WEIGHT_DECAY, cfg.SOLVER.ZERO_WD_1D_PARAM)
+    by_wd = lambda groups: {float(g["weight_decay"]): {id(p) for p in g["params"]} for g in groups}
+    assert by_wd(want.param_groups) == by_wd(got)
+    assert isinstance(want, torch.optim.AdamW) and want.defaults["lr"] == cfg.SOLVER.BASE_LR
