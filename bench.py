@@ -312,6 +312,7 @@ def main():
     e2e_val = world * B * K / (ms_e2e / 1e3)
     if rank != 0:
         if world > 1:
+            dist.barrier()  # stay alive until rank 0 has finished its instrumented pass: ordered NCCL teardown
             dist.destroy_process_group()
         return
 
@@ -393,8 +394,9 @@ def main():
     if args.profile_json:
         with open(args.profile_json, "w") as f:
             json.dump(prof, f, indent=1)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
