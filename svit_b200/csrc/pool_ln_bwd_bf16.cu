@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
   const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
   const bf16* dp = dpre + (int64_t)bh * Nout * PD + c0;
   bf16* dzb = dz + b * g.in_bs + head * g.in_hs + c0;
-  const int smask = (1 << LS) - 1;
+  const int smask = (1 << (LS >= 0 ? LS : 0)) - 1;  // unused by the generic (LS < 0) instantiation
   const int step = gridDim.x * wpb;
   const int step_w = step % g.W, step_h = (step / g.W) % g.H, step_t = step / (g.W * g.H);
   int ww, hh, t;
@@ -343,12 +343,6 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
       t += step_t;
     }
   }
-}
-
-inline int grid_for_tokens(int64_t tokens) {
-  int64_t gsz = ceil_div64(tokens, 8);
-  const int64_t cap = (int64_t)svit_num_sms() * 8;
-  return (int)(gsz < cap ? (gsz > 0 ? gsz : 1) : cap);
 }
 
 }  // namespace
