@@ -252,8 +252,10 @@ pool_ln_tiled_kernel(const bf16* __restrict__ in, Geom g, const float* __restric
 // weights of the pair live in registers for the whole CTA lifetime; the CTA marches over the T input planes and
 // every plane is read from shared memory exactly once per strip: its three input rows feed the accumulators of the
 // three output planes t-1, t, t+1 (three rotating register sets), so one LDS.32 + 2 conversions feed up to 27 FFMA2.
-// A finished output plane goes through an fp32 staging tile to the LayerNorm lanes (4 lanes per token, 24 channels
-// each).  384 threads = 8 strips x 48 pairs; input planes arrive through a 3-slot cp.async ring, two planes ahead.
+// A finished output plane is normalised straight from the accumulators (ln_direct below: transposing butterfly over the
+// three 16-lane groups of a strip + a 96-thread named barrier); only the cls / object rows still go through the fp32
+// staging tile and the 4-lanes-per-token LayerNorm.  384 threads = 8 strips x 48 pairs; input planes arrive as one TMA
+// box each through a 3-slot ring, two planes ahead.
 template <int S> struct CpCfg;
 template <> struct CpCfg<1> { static constexpr int ROWS = 4, TW = 14, SW = 7, IW = 16; };
 template <> struct CpCfg<2> { static constexpr int ROWS = 4, TW = 7, SW = 4, IW = 15; };  // strip 2 over-reads 2 tokens (masked output)
@@ -424,20 +426,6 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int o = 0; o < SW; ++o) acc[a][o] = make_float2(0.f, 0.f);
-
-  // stage output plane t (accumulator set a) for the LayerNorm lanes
-  auto stage_out = [&](float2 (&set)[SW], int t) {
-#pragma unroll
-    for (int o = 0; o < SW; ++o) {
-      stg[(strip * SW + o) * CP_PITCH + wd] = set[o];
-      set[o] = make_float2(0.f, 0.f);
-    }
-    if (wd < SW) {
-      const int o = wd, wo = wo0 + scol + o;
-      const bool ok = ho < g.Ho && scol + o < C::TW && wo < g.Wo;
-      stg_tok[strip * SW + o] = ok ? 1 + ((int64_t)t * g.Ho + ho) * g.Wo + wo : -1;
-    }
-  };
 
   // LayerNorm of a finished output plane straight from the accumulators (no staging tile, no CTA barrier): the 96
   // channels of a token live in the 48 threads of its strip = three 16-lane groups.  Sum and sum of squares of the
