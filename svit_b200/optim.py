@@ -150,6 +150,52 @@ class FusedAdamW:
         n = sum(1 for t in self._tables if t is not None)
         return self._sqnorm[n].sqrt()
 
+    # ---- checkpointing: the torch.optim.AdamW layout, so optimizer states saved by the reference's
+    # utils/checkpoint.py (`optimizer.state_dict()`) resume here and vice versa ----------------------------------------
+    def state_dict(self) -> dict:
+        index, groups = {}, []
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                index.setdefault(id(p), len(index))
+                ids.append(index[id(p)])
+            b1, b2 = g["betas"]
+            groups.append({"lr": g["lr"], "betas": (b1, b2), "eps": g["eps"], "weight_decay": g["weight_decay"],
+                           "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                           "differentiable": False, "fused": None, "params": ids})
+        state = {}
+        for g in self.param_groups:
+            for p in g["params"]:
+                st = self.state.get(p)
+                if st is not None:
+                    state[index[id(p)]] = {"step": torch.tensor(float(self._step)), "exp_avg": st["exp_avg"],
+                                           "exp_avg_sq": st["exp_avg_sq"]}
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: dict):
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups) or any(len(a["params"]) != len(b["params"])
+                                                         for a, b in zip(groups, self.param_groups)):
+            raise ValueError("loaded state dict has a different number of parameter groups / parameters")
+        by_index = {}
+        for saved, g in zip(groups, self.param_groups):
+            for k in ("lr", "eps", "weight_decay"):
+                g[k] = saved[k]
+            g["betas"] = tuple(saved["betas"])
+            for idx, p in zip(saved["params"], g["params"]):
+                by_index[idx] = p
+        steps = set()
+        for idx, st in sd["state"].items():
+            p = by_index[int(idx)]
+            mine = self.state.setdefault(p, {"exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)})
+            mine["exp_avg"].copy_(st["exp_avg"])     # in place: the device pointer table keeps pointing at these buffers
+            mine["exp_avg_sq"].copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): the fused step keeps one counter")
+        self._step = steps.pop() if steps else 0
+        self._tables = None  # weight decay / membership may have changed: rebuild the tables at the next step
+
     def zero_grad(self, set_to_none: bool = True):
         for g in self.param_groups:
             for p in g["params"]:

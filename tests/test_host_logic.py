@@ -139,3 +139,31 @@ def test_weight_decay_groups_match_reference_construct_optimizer():
     by_wd = lambda groups: {float(g["weight_decay"]): {id(p) for p in g["params"]} for g in groups}
     assert by_wd(want.param_groups) == by_wd(got)
     assert isinstance(want, torch.optim.AdamW) and want.defaults["lr"] == cfg.SOLVER.BASE_LR
+
+
+def test_fused_adamw_state_dict_round_trips_with_torch_adamw():
+    """Checkpoint resume (reference: utils/checkpoint.py saves optimizer.state_dict()): a torch.optim.AdamW state loads into
+    FusedAdamW and FusedAdamW's state loads back into torch.optim.AdamW (host logic only: no kernel is launched)."""
+    import torch
+    from svit_b200.optim import FusedAdamW
+    gen = torch.Generator().manual_seed(0)
+    def params():
+        return [torch.nn.Parameter(torch.randn(4, 3, generator=gen)), torch.nn.Parameter(torch.randn(5, generator=gen))]
+    p_ref = params()
+    ref = torch.optim.AdamW([{"params": [p_ref[0]], "weight_decay": 1e-2}, {"params": [p_ref[1]], "weight_decay": 0.0}],
+                            lr=3e-4, eps=1e-8)
+    for _ in range(2):
+        for p in p_ref:
+            p.grad = torch.randn(p.shape, generator=gen)
+        ref.step()
+    p_ours = params()
+    ours = FusedAdamW([{"params": [p_ours[0]], "weight_decay": 0.5}, {"params": [p_ours[1]], "weight_decay": 0.5}], lr=1.0)
+    ours.load_state_dict(ref.state_dict())
+    assert ours._step == 2 and ours.param_groups[0]["weight_decay"] == 1e-2 and ours.param_groups[1]["lr"] == 3e-4
+    for a, b in zip(p_ours, p_ref):
+        assert torch.equal(ours.state[a]["exp_avg"], ref.state[b]["exp_avg"])
+        assert torch.equal(ours.state[a]["exp_avg_sq"], ref.state[b]["exp_avg_sq"])
+    back = torch.optim.AdamW([{"params": [p_ref[0]]}, {"params": [p_ref[1]]}], lr=1.0)
+    back.load_state_dict(ours.state_dict())
+    assert back.param_groups[0]["weight_decay"] == 1e-2 and float(back.state[p_ref[0]]["step"]) == 2.0
+    assert torch.equal(back.state[p_ref[1]]["exp_avg_sq"], ref.state[p_ref[1]]["exp_avg_sq"])
