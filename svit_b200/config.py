@@ -106,7 +106,10 @@ _SSV2 = {
     "TRAIN": {"DATASET": "ssv2", "FORWARD_VIDEO_FRAMES": True, "BATCH_SIZE": 63},
     "TEST": {"BATCH_SIZE": 64},
     "SOLVER": {"CLIP_GRAD_L2NORM": 1.0, "BASE_LR": 2e-4, "WEIGHT_DECAY": 1e-4, "OPTIMIZING_METHOD": "adamw",
-               "ZERO_WD_1D_PARAM": True},
+               "ZERO_WD_1D_PARAM": True,
+               # configs/ssv2.yaml:169-182 (learning-rate policy, svit_b200/optim.py::get_epoch_lr)
+               "LR_POLICY": "cosine", "COSINE_END_LR": 2e-6, "COSINE_AFTER_WARMUP": True, "MAX_EPOCH": 50,
+               "WARMUP_EPOCHS": 0.0, "WARMUP_START_LR": 2e-6},
 }
 
 

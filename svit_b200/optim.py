@@ -13,6 +13,7 @@ weight_decay, `step()`, `zero_grad()`); results match torch.optim.AdamW to fp32 
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Iterable, List, Optional
 
 import torch
@@ -45,6 +46,40 @@ def construct_optimizer(model, cfg):
         raise NotImplementedError(f"Does not support {cfg.SOLVER.OPTIMIZING_METHOD} optimizer")
     groups = split_weight_decay_groups(model, cfg.SOLVER.WEIGHT_DECAY, cfg.SOLVER.ZERO_WD_1D_PARAM)
     return FusedAdamW(groups, lr=cfg.SOLVER.BASE_LR, eps=1e-8, weight_decay=cfg.SOLVER.WEIGHT_DECAY)
+
+
+def lr_func_cosine(cfg, cur_epoch: float, base_lr=None) -> float:
+    """utils/lr_policy.py:35-66: half-cosine from BASE_LR to COSINE_END_LR over MAX_EPOCH (offset by the warm-up when
+    COSINE_AFTER_WARMUP)."""
+    if base_lr is None:
+        base_lr, end_lr = cfg.SOLVER.BASE_LR, cfg.SOLVER.COSINE_END_LR
+    elif isinstance(base_lr, tuple):
+        base_lr, end_lr = base_lr
+    else:
+        end_lr = cfg.SOLVER.COSINE_END_LR
+    offset = cfg.SOLVER.WARMUP_EPOCHS if cfg.SOLVER.COSINE_AFTER_WARMUP else 0.0
+    assert end_lr < base_lr
+    return end_lr + (base_lr - end_lr) * (math.cos(math.pi * (cur_epoch - offset) / (cfg.SOLVER.MAX_EPOCH - offset)) + 1.0) * 0.5
+
+
+def get_epoch_lr(cur_epoch: float, cfg) -> dict:
+    """models/optimizer.py:115-125 -> utils/lr_policy.py:9-32 for LR_POLICY 'cosine' (what configs/ssv2.yaml uses):
+    the policy value, replaced by a linear ramp from WARMUP_START_LR during the first WARMUP_EPOCHS.  Returns
+    {'lr': value} like the reference."""
+    if cfg.SOLVER.LR_POLICY != "cosine":
+        raise NotImplementedError(f"Unknown LR policy: {cfg.SOLVER.LR_POLICY}")
+    lr = lr_func_cosine(cfg, cur_epoch, base_lr=cfg.SOLVER.BASE_LR)
+    if cur_epoch < cfg.SOLVER.WARMUP_EPOCHS:
+        lr_start = cfg.SOLVER.WARMUP_START_LR
+        lr_end = lr_func_cosine(cfg, cfg.SOLVER.WARMUP_EPOCHS)
+        lr = cur_epoch * (lr_end - lr_start) / cfg.SOLVER.WARMUP_EPOCHS + lr_start
+    return {"lr": lr}
+
+
+def set_lr(optimizer, new_lr: dict):
+    """models/optimizer.py:128-137."""
+    for g in optimizer.param_groups:
+        g["lr"] = new_lr["lr"]
 
 
 class FusedAdamW:

@@ -167,3 +167,25 @@ def test_fused_adamw_state_dict_round_trips_with_torch_adamw():
     back.load_state_dict(ours.state_dict())
     assert back.param_groups[0]["weight_decay"] == 1e-2 and float(back.state[p_ref[0]]["step"]) == 2.0
     assert torch.equal(back.state[p_ref[1]]["exp_avg_sq"], ref.state[p_ref[1]]["exp_avg_sq"])
+
+
+def test_lr_policy_matches_reference():
+    """svit_b200.optim.get_epoch_lr against the unmodified reference (utils/lr_policy.py:9-66 via models/optimizer.py:115-125):
+    the ssv2.yaml cosine schedule, and a variant with warm-up, bit for bit."""
+    import copy
+    import importlib
+    import pytest
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not mounted (GPU box)")
+    ref_loader.load()
+    ref_opt = importlib.import_module("slowfast.models.optimizer")
+    from svit_b200.config import ssv2_cfg
+    from svit_b200.optim import get_epoch_lr
+    cfg = ssv2_cfg()
+    warm = copy.deepcopy(cfg)
+    warm.SOLVER.WARMUP_EPOCHS = 5.0
+    for c in (cfg, warm):
+        for e in (0.0, 0.37, 4.99, 5.0, 12.5, 49.999):
+            assert get_epoch_lr(e, c) == ref_opt.get_epoch_lr(e, c), (e, c.SOLVER.WARMUP_EPOCHS)
+    assert get_epoch_lr(0.0, cfg)["lr"] == cfg.SOLVER.BASE_LR
