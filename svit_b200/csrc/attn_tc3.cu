@@ -87,6 +87,7 @@ struct Params {
 enum {  // barrier slots
   BAR_Q_FULL = 0, BAR_T_FULL, BAR_E_FULL, BAR_E_EMPTY, BAR_E_READY, BAR_K_FULL0, BAR_K_FULL1, BAR_K_EMPTY0, BAR_K_EMPTY1,
   BAR_V_FULL0, BAR_V_FULL1, BAR_V_EMPTY0, BAR_V_EMPTY1, BAR_S_FULL0, BAR_S_FULL1, BAR_P_FULL0, BAR_P_FULL1, BAR_O_DONE,
+  BAR_O_FINAL,  // completes exactly once, when the last P.V MMA has retired
   NUM_BARS
 };
 
@@ -270,6 +271,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
           }
           tc::umma_commit(&bars[BAR_V_EMPTY0 + (i & 1)]);
           tc::umma_commit(&bars[BAR_O_DONE]);
+          if (i == p.n_tiles - 1) tc::umma_commit(&bars[BAR_O_FINAL]);
         }
       }
     }
@@ -434,9 +436,11 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       TL(2, 600 + j);
     }
     // ---- phase O: normalise, residual pooling, store
-    // phases <= n_tiles-3 are known complete (S_FULL of the last tile was seen): observe the last two in order
-    if (p.n_tiles >= 2) tc::mbar_wait_hot(&bars[BAR_O_DONE], (p.n_tiles - 2) & 1);
-    tc::mbar_wait_hot(&bars[BAR_O_DONE], (p.n_tiles - 1) & 1);
+    // The last P.V product is observed through its own single-use barrier.  O_DONE cannot serve here: at this point
+    // between n_tiles-2 and n_tiles of its phases may be complete, and a parity wait only tells the current phase from
+    // the previous one -- a warp that got here after the last P.V had already retired would wait on parity
+    // (n_tiles-2)&1 = n_tiles&1, i.e. for a phase that never completes.
+    tc::mbar_wait_hot(&bars[BAR_O_FINAL], 0);
     tc::fence_after_sync();
     TL(2, 9003);
     xch[((p.n_tiles & 1) * 2 + half) * BM + rl] = l;  // partial row sums of the two halves
