@@ -275,10 +275,10 @@ int svit_attn_bwd_sdp(const svit_attn_args* a, cudaStream_t st) {
                               (uint64_t)p.Nq * a->h * HD, BM)))
     return rc;
   const size_t smem = smem_bytes(p.n_tiles, p.pitch);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static SvitDevOnce configured;
+  if (configured.need(smem)) {
     SVIT_CUDA(cudaFuncSetAttribute(attn_bwd_sdp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured.done(smem);
   }
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles * BH;
   const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());

@@ -251,10 +251,10 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
 
     {
       const size_t smem = (size_t)Nkp * 4 + 8 * (MAXE + 4) * 4;
-      static size_t configured = 0;
-      if (smem > 48 * 1024 && smem > configured) {
+      static SvitDevOnce configured;
+      if (smem > 48 * 1024 && configured.need(smem)) {
         SVIT_CUDA(cudaFuncSetAttribute(attn_bwd_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured.done(smem);
       }
       int64_t ctas = ceil_div64(rows, 8);
       const int64_t cap = (int64_t)svit_num_sms() * 8;

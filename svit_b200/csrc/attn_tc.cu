@@ -556,10 +556,10 @@ int svit_attn_fwd_tc(const svit_attn_args* a, cudaStream_t st) {
   dim3 grid((unsigned)((p.Nq + BM - 1) / BM), (unsigned)BH);
 #define ATTN_LAUNCH(KWV)                                                                                              \
   {                                                                                                                   \
-    static bool configured = false;                                                                                   \
-    if (!configured) {                                                                                                \
+    static SvitDevOnce configured;                                                                                   \
+    if (configured.need()) {                                                                                                \
       SVIT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<KWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      configured = true;                                                                                              \
+      configured.done();                                                                                              \
     }                                                                                                                 \
     attn_fwd_tc_kernel<KWV><<<grid, NTHREADS, smem, st>>>(tq, tk, tv, tt, p);                                         \
   }

@@ -583,11 +583,11 @@ int svit_attn_fwd_tc3(const svit_attn_args* a, cudaStream_t st) {
   if ((rc = svit_make_tmap_3d(&tv, a->v, BH, p.Nk, HD, HD, (uint64_t)p.Nk * HD, BN))) return rc;
   if ((rc = svit_make_tmap_2d(&tt, a->rel_tab, p.ntab, HD, HD, TP))) return rc;
   dim3 grid((unsigned)((p.Nq + BM - 1) / BM), (unsigned)BH);
-  static bool configured = false;
-  if (!configured) {
+  static SvitDevOnce configured;
+  if (configured.need()) {
     SVIT_CUDA(cudaFuncSetAttribute(attn_fwd_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     SVIT_CUDA(cudaFuncSetAttribute(attn_fwd_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    configured = true;
+    configured.done();
   }
   if (x16) attn_fwd_tc3_kernel<true><<<grid, NTHREADS, SMEM_TOTAL, st>>>(tq0, tq1, tk0, tk1, tsel, tsel2, tv, tt, p);
   else attn_fwd_tc3_kernel<false><<<grid, NTHREADS, SMEM_TOTAL, st>>>(tq0, tq1, tk0, tk1, tsel, tsel2, tv, tt, p);

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #define SVIT_F32 0
 #define SVIT_BF16 1
 
@@ -55,15 +57,41 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * kInvSqrt2Pi * __expf(-0.5f * x * x);
 }
 
-static inline int svit_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+#define SVIT_MAX_DEVICES 64
+
+static inline int svit_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < SVIT_MAX_DEVICES ? dev : 0;
 }
+
+// SM count of the CURRENT device (a process may drive several GPUs).
+static inline int svit_num_sms() {
+  static std::atomic<int> n[SVIT_MAX_DEVICES];
+  const int dev = svit_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+// One-time kernel configuration PER DEVICE.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current
+// device's context only, so a process-wide flag would leave the second GPU of a process unconfigured.
+//   static SvitDevOnce once;  if (once.need(bytes)) { cudaFuncSetAttribute(...); once.done(bytes); }
+// need(v): the current device has not been configured with a value >= v yet.  Threads racing on the same device may
+// both configure (the call is idempotent); the flag is published only after the attribute has been set.
+struct SvitDevOnce {
+  std::atomic<size_t> v[SVIT_MAX_DEVICES];
+  bool need(size_t want = 1) { return v[svit_device()].load(std::memory_order_acquire) < want; }
+  void done(size_t want = 1) {
+    std::atomic<size_t>& a = v[svit_device()];
+    size_t cur = a.load(std::memory_order_relaxed);
+    while (cur < want && !a.compare_exchange_weak(cur, want, std::memory_order_release)) {
+    }
+  }
+};
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

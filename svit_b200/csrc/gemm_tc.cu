@@ -382,10 +382,10 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
     }
   }
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
-  static bool configured = false;
-  if (!configured) {
+  static SvitDevOnce configured;
+  if (configured.need()) {
     SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
+    configured.done();
   }
   const int64_t tiles = ((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN) * e.splits * e.batch;
   const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());

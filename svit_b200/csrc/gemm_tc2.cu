@@ -502,10 +502,10 @@ int launch_g(const svit_gemm_args* a, cudaStream_t st) {
   else if (e.aux == AUX_GELU_PRE) rc = make_box_map(&tx, a->gelu_pre, (uint64_t)a->M, (uint64_t)a->N, (uint64_t)a->ldg);
   if (rc) return rc;
   auto kern = gemm_tc_tma_kernel<BN, B_MN, G, PAIR>;
-  static bool configured = false;
-  if (!configured) {
+  static SvitDevOnce configured;
+  if (configured.need()) {
     SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
+    configured.done();
   }
   constexpr int TM = PAIR ? 2 * BM : BM;
   const int64_t tiles = ((a->M + TM - 1) / TM) * ((a->N + BN - 1) / BN);

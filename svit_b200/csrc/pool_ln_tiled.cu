@@ -376,7 +376,8 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
                   const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ out, float eps) {
   using C = CpCfg<S>;
   using D = CpDims<S>;
-  constexpr int IH = D::IH, IW = D::IW, XN = D::XN, SW = C::SW;
+  constexpr int IW = D::IW, XN = D::XN, SW = C::SW;
+  constexpr int NV = SW > 4 ? 16 : 8;  // LayerNorm butterfly width: token sums in v[0, NV/2), sums of squares in v[NV/2, NV)
   extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* ring = reinterpret_cast<uint32_t*>(smem);
   float2* stg = reinterpret_cast<float2*>(smem + D::OFF_STG);
@@ -416,126 +417,169 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
 
   const int strip = threadIdx.x / 48, wd = threadIdx.x - strip * 48;   // strip, channel-pair word
   const int srow = strip >> 1, scol = (strip & 1) * SW;
-  const int ho = ho0 + srow;
+  const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < TAPS * 48; i += CP_THREADS) {
     const int tp = i / 48, pr = i - tp * 48;
     sw2[i] = make_float2(__ldg(w + (2 * pr) * TAPS + tp), __ldg(w + (2 * pr + 1) * TAPS + tp));
   }
-  float2 acc[3][SW];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int o = 0; o < SW; ++o) acc[a][o] = make_float2(0.f, 0.f);
-
-  // LayerNorm of a finished output plane straight from the accumulators (no staging tile, no CTA barrier): the 96
-  // channels of a token live in the 48 threads of its strip = three 16-lane groups.  Sum and sum of squares of the
-  // thread's SW tokens (padded to 16 values) go through a transposing butterfly (15 shuffles: lane l of a group ends
-  // with the group total of value l), the three groups of a strip meet in shared memory behind a 96-thread named
-  // barrier (two strips = three warps), and every thread normalises and stores its own channel pair.
-  float* red = reinterpret_cast<float*>(smem + D::OFF_RED);
+  // this thread's output tokens: row ho0 + srow, columns wo0 + scol + o for o < nvalid; optr walks over the output planes
+  int nvalid = min(SW, min(C::TW - scol, g.Wo - (wo0 + scol)));
+  if (ho0 + srow >= g.Ho || nvalid < 0) nvalid = 0;
+  uint32_t* optr = reinterpret_cast<uint32_t*>(obase + (1 + (int64_t)(ho0 + srow) * g.Wo + wo0 + scol) * PD) + wd;
+  const int plane_words = g.Ho * g.Wo * (PD / 2);
+  const uint32_t* xbase = ring + ((srow * S) * IW + scol * S) * 48 + wd;
+  const float2* wbase = sw2 + wd;
   const float2 gam = make_float2(__ldg(gamma + 2 * wd), __ldg(gamma + 2 * wd + 1));
   const float2 bet = make_float2(__ldg(beta + 2 * wd), __ldg(beta + 2 * wd + 1));
-  auto ln_direct = [&](float2 (&set)[SW], int t, int buf) {
-    float v[16];
+  // LayerNorm statistics meet here: red[plane parity][16-lane group (24)][16]; a strip = groups 3*strip .. 3*strip + 2
+  float* red = reinterpret_cast<float*>(smem + D::OFF_RED);
+  const int l16 = lane & 15;
+  const int my_tok = l16 & (NV / 2 - 1);                        // the token whose statistics this lane finishes
+  const int red_wr = (threadIdx.x >> 4) * 16 + l16;
+  const int red_rd = strip * 48 + (NV == 16 ? my_tok : 2 * my_tok);
+  const int bar_id = 1 + (strip >> 1);
+
+  float2 acc[3][SW];
+
+  // LayerNorm of a finished output plane straight from the accumulators.  The 96 channels of a token are the 48
+  // threads of its strip = three 16-lane groups.  Each thread contributes (x + y, x^2 + y^2) for its SW tokens; a
+  // transposing butterfly over the 16 lanes of a group (NV - 1 shuffles) leaves lane l with the group total of
+  // value l (NV = 16) or l / 2 (NV = 8); the three groups meet in shared memory behind a 96-thread named barrier
+  // (two strips = three warps); lane o of every group then finishes token o (mean, rstd) and the 16 lanes fetch the
+  // per-token scale / shift with two shuffles per token.  Stores: 4 bytes per thread and token, a warp writes
+  // 128 contiguous bytes; the token rows of a strip are consecutive in memory (immediate offsets from optr).
+  auto ln_plane = [&](float2 (&set)[SW], int buf) {
+    float v[NV];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
+    for (int o = 0; o < NV / 2; ++o) {
       if (o < SW) {
         v[o] = set[o].x + set[o].y;
-        v[8 + o] = fmaf(set[o].x, set[o].x, set[o].y * set[o].y);
+        v[NV / 2 + o] = fmaf(set[o].x, set[o].x, set[o].y * set[o].y);
       } else {
-        v[o] = v[8 + o] = 0.f;
+        v[o] = v[NV / 2 + o] = 0.f;
       }
     }
-    const int lane = threadIdx.x & 31;
+    {
+      int d = 8;
 #pragma unroll
-    for (int w = 8; w >= 1; w >>= 1) {
-      const bool up = (lane & w) != 0;
+      for (int hw = NV / 2; hw >= 1; hw >>= 1, d >>= 1) {
+        const bool up = (lane & d) != 0;
 #pragma unroll
-      for (int i = 0; i < w; ++i) {
-        const float send = up ? v[i] : v[i + w];
-        const float keep = up ? v[i + w] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        for (int i = 0; i < hw; ++i) {
+          const float send = up ? v[i] : v[i + hw];
+          const float keep = up ? v[i + hw] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
       }
+      if (NV == 8) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
     }
-    const int g16 = threadIdx.x >> 4;
     float* rb = red + buf * (24 * 16);
-    rb[g16 * 16 + (lane & 15)] = v[0];
-    asm volatile("bar.sync %0, 96;" ::"r"(1 + (strip >> 1)) : "memory");
-    const float4* r4 = reinterpret_cast<const float4*>(rb + strip * 48);
-    float tot[16];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 a = r4[k], b = r4[4 + k], c = r4[8 + k];
-      tot[4 * k] = a.x + b.x + c.x; tot[4 * k + 1] = a.y + b.y + c.y;
-      tot[4 * k + 2] = a.z + b.z + c.z; tot[4 * k + 3] = a.w + b.w + c.w;
-    }
+    rb[red_wr] = v[0];
+    asm volatile("bar.sync %0, 96;" ::"r"(bar_id) : "memory");
+    const float* rr = rb + red_rd;
+    const float sum = rr[0] + rr[16] + rr[32];
+    const float sq = rr[8] + rr[24] + rr[40];
+    const float mean = sum * (1.f / PD);
+    const float var = fmaxf(fmaf(sq, 1.f / PD, -mean * mean), 0.f);
+    const float sc = rsqrtf(var + eps);
+    const float sh = -mean * sc;
+    uint32_t pk[SW];
 #pragma unroll
     for (int o = 0; o < SW; ++o) {
-      const float mean = tot[o] * (1.f / PD);
-      const float var = fmaxf(tot[8 + o] * (1.f / PD) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + eps);
-      const int wo = wo0 + scol + o;
-      const bool ok = ho < g.Ho && scol + o < C::TW && wo < g.Wo;
-      if (ok) {
-        const int64_t tok = 1 + ((int64_t)t * g.Ho + ho) * g.Wo + wo;
-        const float y0 = fmaf((set[o].x - mean) * rstd, gam.x, bet.x), y1 = fmaf((set[o].y - mean) * rstd, gam.y, bet.y);
-        reinterpret_cast<uint32_t*>(obase + tok * PD)[wd] = pack2(y0, y1);
-      }
-      set[o] = make_float2(0.f, 0.f);
+      const float a = __shfl_sync(0xffffffffu, sc, (lane & 16) + o);
+      const float c = __shfl_sync(0xffffffffu, sh, (lane & 16) + o);
+      const float2 ag = make_float2(a * gam.x, a * gam.y);
+      const float2 cg = make_float2(fmaf(c, gam.x, bet.x), fmaf(c, gam.y, bet.y));
+      const float2 y = pfma2(set[o], ag, cg);
+      pk[o] = pack2(y.x, y.y);
     }
+    if (nvalid == SW) {
+#pragma unroll
+      for (int o = 0; o < SW; ++o) optr[o * (PD / 2)] = pk[o];
+    } else {
+#pragma unroll
+      for (int o = 0; o < SW; ++o)
+        if (o < nvalid) optr[o * (PD / 2)] = pk[o];
+    }
+    optr += plane_words;
   };
 
   int tl_n = 0;
   (void)tl_n;
-  auto step = [&](auto rtag, int tp) {
-    constexpr int R = decltype(rtag)::value;  // tp % 3
+  // One input plane tp: its three rows (kh) feed output planes tp+1 (kt = 0, a fresh accumulator set: the first tap
+  // is a multiply, so sets are never zeroed), tp (kt = 1) and tp-1 (kt = 2, which is complete afterwards).
+  // R = tp % 3 selects the rotating sets at compile time; E bit 0 = first plane (no plane tp-1), bit 1 = last plane
+  // (no plane tp+1; its own output plane is normalised here too).  No branches inside the tap loops.
+  auto step = [&](auto rtag, auto etag, int tp) {
+    constexpr int R = decltype(rtag)::value;
+    constexpr int E = decltype(etag)::value;
+    constexpr bool FIRST = (E & 1) != 0, LAST = (E & 2) != 0;
     PTL(100 + tp);
-    __syncthreads();
-    PTL(200 + tp);                                      // staging tile and ring slot (tp+2)%3 are free
+    __syncthreads();                                    // ring slot (tp+2)%3 is free
+    PTL(200 + tp);
     if (threadIdx.x == 0 && tp + 2 < g.T) load_plane(tp + 2);
-    tc::mbar_wait_hot(&full[tp % CP_SLOTS], (tp / CP_SLOTS) & 1);  // plane tp has landed
+    tc::mbar_wait_hot(&full[R], (tp / CP_SLOTS) & 1);   // plane tp has landed
     PTL(300 + tp);
-    const uint32_t* pl = ring + (tp % CP_SLOTS) * D::SLOT_WORDS;
+    const uint32_t* pl = xbase + R * D::SLOT_WORDS;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      const uint32_t* rowp = pl + ((srow * S + kh) * IW + scol * S) * 48 + wd;
       float2 x[XN];
 #pragma unroll
       for (int p = 0; p < XN; ++p) {
-        const uint32_t v = rowp[p * 48];
+        const uint32_t v = pl[(kh * IW + p) * 48];
         x[p] = make_float2(lo_f(v), hi_f(v));
       }
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
-        const int t_out = tp + 1 - kt;
-        if (t_out < 0 || t_out >= g.T) continue;  // temporal zero padding (uniform)
-        constexpr int dummy = 0; (void)dummy;
+        if ((kt == 0 && LAST) || (kt == 2 && FIRST)) continue;  // temporal zero padding (compile time)
         float2 (&set)[SW] = acc[(R + 4 - kt) % 3];
+        const bool fresh = kh == 0 && (kt == 0 || (kt == 1 && FIRST));
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const float2 wt = sw2[((kt * 3 + kh) * 3 + kw) * 48 + wd];
+          const float2 wt = wbase[((kt * 3 + kh) * 3 + kw) * 48];
 #pragma unroll
-          for (int o = 0; o < SW; ++o) fma2(set[o], x[o * S + kw], wt);
+          for (int o = 0; o < SW; ++o) {
+            if (fresh && kw == 0) set[o] = pmul2(x[o * S], wt);
+            else fma2(set[o], x[o * S + kw], wt);
+          }
         }
       }
     }
     PTL(400 + tp);
-    if (tp >= 1) ln_direct(acc[(R + 2) % 3], tp - 1, tp & 1);  // output plane tp-1 has now seen planes tp-2, tp-1, tp
+    if (!FIRST) ln_plane(acc[(R + 2) % 3], (tp - 1) & 1);  // output plane tp-1 has now seen planes tp-2, tp-1, tp
+    if (LAST) ln_plane(acc[R], tp & 1);                    // output plane T-1 (its t+1 neighbour is zero padding)
     PTL(600 + tp);
   };
-  for (int tp0 = 0; tp0 < g.T; tp0 += 3) {
-    step(std::integral_constant<int, 0>{}, tp0);
-    if (tp0 + 1 < g.T) step(std::integral_constant<int, 1>{}, tp0 + 1);
-    if (tp0 + 2 < g.T) step(std::integral_constant<int, 2>{}, tp0 + 2);
+  using R0 = std::integral_constant<int, 0>;
+  using R1 = std::integral_constant<int, 1>;
+  using R2 = std::integral_constant<int, 2>;
+  using EMID = std::integral_constant<int, 0>;
+  using EFIRST = std::integral_constant<int, 1>;
+  using ELAST = std::integral_constant<int, 2>;
+  using EONLY = std::integral_constant<int, 3>;
+  if (g.T == 1) {
+    step(R0{}, EONLY{}, 0);
+  } else {
+    step(R0{}, EFIRST{}, 0);
+    int tp = 1;
+    for (; tp + 3 <= g.T - 1; tp += 3) {
+      step(R1{}, EMID{}, tp);
+      step(R2{}, EMID{}, tp + 1);
+      step(R0{}, EMID{}, tp + 2);
+    }
+    const int rem = g.T - 1 - tp;  // middle planes left before the last one: 0, 1 or 2
+    if (rem == 0) {
+      step(R1{}, ELAST{}, tp);
+    } else if (rem == 1) {
+      step(R1{}, EMID{}, tp);
+      step(R2{}, ELAST{}, tp + 1);
+    } else {
+      step(R1{}, EMID{}, tp);
+      step(R2{}, EMID{}, tp + 1);
+      step(R0{}, ELAST{}, tp + 2);
+    }
   }
-  // last output plane T-1 (its t+1 neighbour is zero padding)
-  {
-    const int a = (g.T - 1) % 3;
-    if (a == 0) ln_direct(acc[0], g.T - 1, g.T & 1);
-    else if (a == 1) ln_direct(acc[1], g.T - 1, g.T & 1);
-    else ln_direct(acc[2], g.T - 1, g.T & 1);
-  }
-  // cls + object tokens of this (batch, head): tile 0, through the same staging / LayerNorm path
+  // cls + object tokens of this (batch, head): tile 0, through the fp32 staging tile and the 4-lanes-per-token LayerNorm
   if (tile == 0) {
     float* sweff = aff + 2 * PD;
     if (threadIdx.x < 48) {
@@ -685,19 +729,19 @@ int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
       return SVIT_EINVAL;
     if (s == 1) {
       using C = CpCfg<1>;
-      static bool configured = false;
-      if (!configured) {
+      static SvitDevOnce configured;
+      if (configured.need()) {
         SVIT_CUDA(cudaFuncSetAttribute(pool_ln_cp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CpDims<1>::SMEM));
-        configured = true;
+        configured.done();
       }
       dim3 grid((unsigned)(((g.Wo + C::TW - 1) / C::TW) * ((g.Ho + C::ROWS - 1) / C::ROWS)), (unsigned)h, (unsigned)B);
       pool_ln_cp_kernel<1><<<grid, CP_THREADS, CpDims<1>::SMEM, st>>>(tm, (const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
     } else {
       using C = CpCfg<2>;
-      static bool configured = false;
-      if (!configured) {
+      static SvitDevOnce configured;
+      if (configured.need()) {
         SVIT_CUDA(cudaFuncSetAttribute(pool_ln_cp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CpDims<2>::SMEM));
-        configured = true;
+        configured.done();
       }
       dim3 grid((unsigned)(((g.Wo + C::TW - 1) / C::TW) * ((g.Ho + C::ROWS - 1) / C::ROWS)), (unsigned)h, (unsigned)B);
       pool_ln_cp_kernel<2><<<grid, CP_THREADS, CpDims<2>::SMEM, st>>>(tm, (const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
@@ -707,10 +751,10 @@ int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   }
   if (tiled && s == 1) {
     using C = TileCfg<1>;
-    static bool configured = false;
-    if (!configured) {
+    static SvitDevOnce configured;
+    if (configured.need()) {
       SVIT_CUDA(cudaFuncSetAttribute(pool_ln_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileDims<1>::SMEM));
-      configured = true;
+      configured.done();
     }
     dim3 grid((unsigned)(((g.Wo + C::TWO - 1) / C::TWO) * ((g.Ho + C::THO - 1) / C::THO)), (unsigned)h, (unsigned)B);
     pool_ln_tiled_kernel<1><<<grid, 256, TileDims<1>::SMEM, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
@@ -719,10 +763,10 @@ int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   }
   if (tiled && s == 2) {
     using C = TileCfg<2>;
-    static bool configured = false;
-    if (!configured) {
+    static SvitDevOnce configured;
+    if (configured.need()) {
       SVIT_CUDA(cudaFuncSetAttribute(pool_ln_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileDims<2>::SMEM));
-      configured = true;
+      configured.done();
     }
     dim3 grid((unsigned)(((g.Wo + C::TWO - 1) / C::TWO) * ((g.Ho + C::THO - 1) / C::THO)), (unsigned)h, (unsigned)B);
     pool_ln_tiled_kernel<2><<<grid, 256, TileDims<2>::SMEM, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
