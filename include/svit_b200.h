@@ -224,6 +224,12 @@ int svit_grad_sqnorm(const svit_optim_tensor* table, const int32_t* chunk_tensor
 int svit_adamw_step(const svit_optim_tensor* table, const int32_t* chunk_tensor, const int64_t* chunk_start, int nchunks,
                     int chunk, float lr, float beta1, float beta2, float eps, int step, float max_norm, const float* sqnorm,
                     void* stream);
+/* Same update with the step-dependent scalars read from DEVICE memory: hyper = {lr, 1 - beta1^step, sqrt(1 - beta2^step)}.
+ * Nothing step-dependent is baked into the launch, so a CUDA graph of the training step (svit_b200.GraphedTrainStep)
+ * replays it; the caller refreshes `hyper` with a small H2D copy before each replay. */
+int svit_adamw_step_dev(const svit_optim_tensor* table, const int32_t* chunk_tensor, const int64_t* chunk_start, int nchunks,
+                        int chunk, const float* hyper, float beta1, float beta2, float eps, float max_norm,
+                        const float* sqnorm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsvit_sm100.so")
+# SVIT_LIB selects an instrumented build of the same library (tools/*_timeline.py); never a different implementation
+LIB_PATH = os.environ.get("SVIT_LIB") or os.path.join(HERE, "libsvit_sm100.so")
 
 F32, BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
@@ -77,6 +78,7 @@ PROTOTYPES = {
     "svit_normalize_u8": [vp, vp] + [C.c_int] * 4 + [f32] * 6 + [C.c_int, vp],
     "svit_grad_sqnorm": [vp, vp, vp, C.c_int, C.c_int, vp, vp],
     "svit_adamw_step": [vp, vp, vp, C.c_int, C.c_int, f32, f32, f32, f32, C.c_int, f32, vp, vp],
+    "svit_adamw_step_dev": [vp, vp, vp, C.c_int, C.c_int, vp, f32, f32, f32, f32, vp, vp],
 }
 
 _lib = None

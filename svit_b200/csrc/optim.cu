@@ -40,7 +40,13 @@ __global__ void __launch_bounds__(256) adamw_kernel(const svit_optim_tensor* __r
                                                     const int32_t* __restrict__ chunk_tensor,
                                                     const int64_t* __restrict__ chunk_start, int nchunks, int chunk, float lr,
                                                     float beta1, float beta2, float eps, float bc1, float sqrt_bc2,
-                                                    float max_norm, const float* __restrict__ sqnorm) {
+                                                    float max_norm, const float* __restrict__ sqnorm,
+                                                    const float* __restrict__ hyper) {
+  if (hyper) {  // step-dependent scalars from device memory: the launch can be replayed from a CUDA graph
+    lr = hyper[0];
+    bc1 = hyper[1];
+    sqrt_bc2 = hyper[2];
+  }
   float coef = 1.f;
   if (max_norm > 0.f && sqnorm) {  // torch.nn.utils.clip_grad_norm_: max_norm / (total_norm + 1e-6), clamped to 1
     coef = max_norm / (sqrtf(*sqnorm) + 1e-6f);
@@ -98,7 +104,20 @@ int svit_adamw_step(const svit_optim_tensor* table, const int32_t* chunk_tensor,
   const float sqrt_bc2 = sqrtf(1.f - powf(beta2, (float)step));
   const int grid = nchunks < svit_num_sms() * 8 ? nchunks : svit_num_sms() * 8;
   adamw_kernel<<<grid, 256, 0, st>>>(table, chunk_tensor, chunk_start, nchunks, chunk, lr, beta1, beta2, eps, bc1, sqrt_bc2,
-                                     max_norm, sqnorm);
+                                     max_norm, sqnorm, nullptr);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int svit_adamw_step_dev(const svit_optim_tensor* table, const int32_t* chunk_tensor, const int64_t* chunk_start, int nchunks,
+                        int chunk, const float* hyper, float beta1, float beta2, float eps, float max_norm,
+                        const float* sqnorm, void* stream) {
+  if (!table || !chunk_tensor || !chunk_start || !hyper || nchunks < 0 || chunk < 1) return SVIT_EINVAL;
+  if (nchunks == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = nchunks < svit_num_sms() * 8 ? nchunks : svit_num_sms() * 8;
+  adamw_kernel<<<grid, 256, 0, st>>>(table, chunk_tensor, chunk_start, nchunks, chunk, 0.f, beta1, beta2, eps, 1.f, 1.f,
+                                     max_norm, sqnorm, hyper);
   SVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -2,17 +2,11 @@
 // Reference: slowfast/models/attention.py:13-65.  HBM-bound: every input token slice is read once from
 // DRAM (halo re-reads are L2 hits) and every output token written once.
 //
-// Mapping shared by both kernels: a HALF-WARP owns one output token; lane l16 owns the six channels
-// {2w, 2w+1 : w = l16, l16+16, l16+32} as three bf16x2 words, so a token slice (192 B) is three conflict-free
-// 64-byte half-warp accesses and LayerNorm(96) is a 4-step xor-shuffle inside the half-warp.
-//
-//   pool_ln_tiled_kernel<S>   stride (1,S,S), S = 1 or 2: CTA = one output tile marched over T through a 5-slot
-//                             ring of input planes in shared memory (cp.async two planes ahead, zero fill for the
-//                             spatial padding); each half-warp produces a strip of outputs with a 3x9 register
-//                             window and FFMA2, so one shared-memory word feeds up to 3 x 6 FMAs; tile 0 of each
-//                             (batch, head) also emits the cls and object-token rows.
-//   pool_ln_direct_kernel     stride >= 4 (windows do not overlap) or unaligned input: taps straight from
-//                             global / L2.
+//   pool_ln_march_kernel<S, SPR>  stride (1,S,S), S = 1 or 2: persistent CTAs; thread = (strip of outputs along W, one
+//                                 bf16x2 channel pair); the CTA marches over T through a TMA ring of input planes.
+//   pool_ln_direct_kernel         stride >= 4 (windows do not overlap) or unaligned input: a half-warp per output token
+//                                 (lane l16 owns channel words l16, l16+16, l16+32), taps straight from global / L2.
+#include <cstdlib>
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -74,32 +68,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// ------------------------------------------------------------------------------------------------ tiled
-// Geometry per pooling stride S (kernel 3x3x3, pad 1, temporal stride 1):
-//   S = 1: CTA tile 8 x 14 outputs, input tile 10 x 16 tokens; warp w = output row w, its half-warps take the
-//          7-output strips at columns 0 and 7 (token positions of opposite parity -> disjoint bank halves).
-//   S = 2: CTA tile 7 x 7 outputs, input tile 15 x 15 tokens; a warp's half-warps take the same 4-output strip on
-//          two consecutive output rows; input rows r with (r >> 1) odd are stored rotated by 16 words so the two
-//          half-warps again hit disjoint bank halves.
-// A strip needs XN = (STRIP-1)*S + 3 = 9 input positions per (kt, kh): 27 LDS.32 feed 3 x STRIP x 6 FMAs.
-// The CTA marches over T through a ring of NS = 5 input planes filled by cp.async two planes ahead of the
-// plane being computed; temporal padding planes are skipped (uniform branch), spatial padding is zero-filled.
-template <int S> struct TileCfg;
-template <> struct TileCfg<1> { static constexpr int THO = 8, TWO = 14, STRIP = 7; };
-template <> struct TileCfg<2> { static constexpr int THO = 7, TWO = 7, STRIP = 4; };
-constexpr int NS = 5;
-
-template <int S>
-struct TileDims {
-  using C = TileCfg<S>;
-  static constexpr int IH = (C::THO - 1) * S + 3, IW = (C::TWO - 1) * S + 3;
-  static constexpr int XN = (C::STRIP - 1) * S + 3;
-  static constexpr int SLOT_WORDS = IH * IW * (PD / 2);
-  // the last strip of a row may read up to XN positions from a start that leaves fewer in the row: the reads run
-  // into the next row / the weight block (values only reach masked outputs), so the weights sit behind the ring
-  static constexpr int SMEM = NS * SLOT_WORDS * 4 + TAPS * PD * 4 + PD * 4;
-};
-
 // two fp32 FMAs per instruction (sm_100 FFMA2): acc = x * w + acc on both halves of a 64-bit register pair
 __device__ __forceinline__ void fma2(float2& acc, const float2 x, const float2 w) {
 #ifdef POOL_SCALAR_FMA
@@ -113,171 +81,6 @@ __device__ __forceinline__ void fma2(float2& acc, const float2 x, const float2 w
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(xx), "l"(ww));
   acc = *reinterpret_cast<float2*>(&a);
 }
-
-template <int S>
-__global__ void __launch_bounds__(256, 1)
-pool_ln_tiled_kernel(const bf16* __restrict__ in, Geom g, const float* __restrict__ w, const float* __restrict__ frac,
-                     const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ out, float eps) {
-  using C = TileCfg<S>;
-  using D = TileDims<S>;
-  constexpr int IH = D::IH, IW = D::IW, XN = D::XN, STRIP = C::STRIP;
-  extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t* ring = reinterpret_cast<uint32_t*>(smem);                          // [NS][IH][IW][48]
-  float* sw = reinterpret_cast<float*>(smem + NS * D::SLOT_WORDS * 4);         // [27][96]
-  float* sweff = sw + TAPS * PD;                                               // [96]
-  const int tiles_w = (g.Wo + C::TWO - 1) / C::TWO;
-  const int tile = blockIdx.x;
-  const int wo0 = (tile % tiles_w) * C::TWO, ho0 = (tile / tiles_w) * C::THO;
-  const int iw0 = wo0 * S - 1, ih0 = ho0 * S - 1;
-  const int head = blockIdx.y, b = blockIdx.z;
-  const bf16* zin = in + (int64_t)b * g.in_bs + (int64_t)head * g.in_hs;
-  const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
-  const int64_t Nout = 1 + Lo + g.O;
-  bf16* obase = out + ((int64_t)b * g.h + head) * Nout * PD;
-
-  auto load_plane = [&](int t) {
-    uint32_t* dst = ring + (t % NS) * D::SLOT_WORDS;
-    const bf16* src_t = zin + (1 + (int64_t)t * g.H * g.W) * g.in_ts;
-    for (int i = threadIdx.x; i < IH * IW * 12; i += 256) {
-      const int chunk = i % 12, pos = i / 12;
-      const int pw = pos % IW, ph = pos / IW;
-      const int hh = ih0 + ph, ww = iw0 + pw;
-      const bool ok = hh >= 0 && hh < g.H && ww >= 0 && ww < g.W;
-      const bf16* src = ok ? src_t + ((int64_t)hh * g.W + ww) * g.in_ts + chunk * 8 : zin;
-      const int pchunk = (S == 2 && ((ph >> 1) & 1)) ? (chunk + 4 >= 12 ? chunk - 8 : chunk + 4) : chunk;
-      cp_async16(dst + pos * 48 + pchunk * 4, src, ok);
-    }
-  };
-  // prologue: planes 0..2 in flight while the weights are staged
-  for (int t = 0; t < 3; ++t) {
-    if (t < g.T) load_plane(t);
-    cp_async_commit();
-  }
-  for (int i = threadIdx.x; i < PD * TAPS; i += 256) sw[(i % TAPS) * PD + i / TAPS] = w[i];
-
-  const int lane = threadIdx.x & 31, l16 = lane & 15;
-  const int warp = threadIdx.x >> 5, hb = (threadIdx.x >> 4) & 1;
-  const int srow = S == 1 ? warp : (warp >> 1) * 2 + hb;       // output row inside the tile
-  const int scol = S == 1 ? hb * STRIP : (warp & 1) * STRIP;   // first output column inside the tile
-  const int ho = ho0 + srow;
-  const bool row_ok = srow < C::THO && ho < g.Ho;
-  float gm[6], bt[6];
-  load_affine(gamma, beta, l16, gm, bt);
-
-  for (int t = 0; t < g.T; ++t) {
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // planes <= t+1 have landed (t+2 may be in flight)
-    __syncthreads();                                      // ... for every thread; compute(t-1) is finished
-    if (t + 3 < g.T) load_plane(t + 3);                   // slot of plane t-2
-    cp_async_commit();
-    if (row_ok) {
-      float2 acc[STRIP][3];
-#pragma unroll
-      for (int o = 0; o < STRIP; ++o)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) acc[o][j] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int kt = 0; kt < 3; ++kt) {
-        const int tp = t - 1 + kt;
-        if (tp < 0 || tp >= g.T) continue;  // temporal zero padding
-        const uint32_t* pl = ring + (tp % NS) * D::SLOT_WORDS;
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const int rin = srow * S + kh;
-          const uint32_t* rowp = pl + (rin * IW + scol * S) * 48 + l16;
-          int off[3];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            int jj = j;
-            if (S == 2 && ((rin >> 1) & 1)) jj = j + 1 >= 3 ? j - 2 : j + 1;
-            off[j] = jj * 16;
-          }
-          float2 x[XN][3];
-#pragma unroll
-          for (int p = 0; p < XN; ++p)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const uint32_t wd = rowp[p * 48 + off[j]];
-              x[p][j] = make_float2(lo_f(wd), hi_f(wd));
-            }
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const float* wr = sw + ((kt * 3 + kh) * 3 + kw) * PD;
-            float2 wt[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) wt[j] = *reinterpret_cast<const float2*>(wr + 2 * (l16 + 16 * j));
-#pragma unroll
-            for (int o = 0; o < STRIP; ++o)
-#pragma unroll
-              for (int j = 0; j < 3; ++j) fma2(acc[o][j], x[o * S + kw][j], wt[j]);
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 0; o < STRIP; ++o) {
-        const int wo = wo0 + scol + o;
-        if (scol + o < C::TWO && wo < g.Wo) {  // uniform across the half-warp
-          uint32_t* dst = reinterpret_cast<uint32_t*>(obase + (1 + ((int64_t)t * g.Ho + ho) * g.Wo + wo) * PD);
-          const float v[6] = {acc[o][0].x, acc[o][0].y, acc[o][1].x, acc[o][1].y, acc[o][2].x, acc[o][2].y};
-          ln_store(v, gm, bt, eps, dst, l16);
-        }
-      }
-    }
-  }
-  // cls + object tokens of this (batch, head): done by the CTA of tile 0
-  if (tile == 0) {
-    for (int c = threadIdx.x; c < PD; c += 256) {
-      float a = 0.f;
-      for (int tp = 0; tp < TAPS; ++tp) a += sw[tp * PD + c] * frac[tp];
-      sweff[c] = a;
-    }
-    __syncthreads();
-    for (int r = threadIdx.x >> 4; r < 1 + g.O; r += 16) {
-      const int64_t tok_in = r == 0 ? 0 : L + r, tok_out = r == 0 ? 0 : Lo + r;
-      const uint32_t* p = reinterpret_cast<const uint32_t*>(zin + tok_in * g.in_ts);
-      float v[6];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const uint32_t wd = p[l16 + 16 * j];
-        const int c = 2 * (l16 + 16 * j);
-        v[2 * j] = lo_f(wd) * (r == 0 ? 1.f : sweff[c]);
-        v[2 * j + 1] = hi_f(wd) * (r == 0 ? 1.f : sweff[c + 1]);
-      }
-      ln_store(v, gm, bt, eps, reinterpret_cast<uint32_t*>(obase + tok_out * PD), l16);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ channel-pair
-// pool_ln_cp_kernel<S>: thread = (strip of SW consecutive outputs along W, one bf16x2 channel pair).  The 27 tap
-// weights of the pair live in registers for the whole CTA lifetime; the CTA marches over the T input planes and
-// every plane is read from shared memory exactly once per strip: its three input rows feed the accumulators of the
-// three output planes t-1, t, t+1 (three rotating register sets), so one LDS.32 + 2 conversions feed up to 27 FFMA2.
-// A finished output plane is normalised straight from the accumulators (ln_direct below: transposing butterfly over the
-// three 16-lane groups of a strip + a 96-thread named barrier); only the cls / object rows still go through the fp32
-// staging tile and the 4-lanes-per-token LayerNorm.  384 threads = 8 strips x 48 pairs; input planes arrive as one TMA
-// box each through a 3-slot ring, two planes ahead.
-template <int S> struct CpCfg;
-template <> struct CpCfg<1> { static constexpr int ROWS = 4, TW = 14, SW = 7, IW = 16; };
-template <> struct CpCfg<2> { static constexpr int ROWS = 4, TW = 7, SW = 4, IW = 15; };  // strip 2 over-reads 2 tokens (masked output)
-constexpr int CP_THREADS = 384, CP_STRIPS = 8, CP_SLOTS = 3;
-constexpr int CP_PITCH = 50;  // staging token pitch in float2: conflict-free 16-byte reads by the LN lanes
-
-template <int S>
-struct CpDims {
-  using C = CpCfg<S>;
-  static constexpr int IH = (C::ROWS - 1) * S + 3, IW = C::IW;
-  static constexpr int XN = (C::SW - 1) * S + 3;
-  static constexpr int PLANE_BYTES = IH * IW * PD * 2;                  // one TMA box
-  static constexpr int SLOT_WORDS = ((PLANE_BYTES + 127) / 128) * 32;   // ring slots stay 128-byte aligned
-  static constexpr int NTOK = CP_STRIPS * C::SW;
-  static constexpr int OFF_STG = CP_SLOTS * SLOT_WORDS * 4;
-  static constexpr int OFF_TOK = OFF_STG + NTOK * CP_PITCH * 8;
-  static constexpr int OFF_AFF = OFF_TOK + ((NTOK * 8 + 15) & ~15);   // int64 token index per staged token
-  static constexpr int OFF_W = OFF_AFF + 3 * PD * 4;                   // gamma, beta, w_eff
-  static constexpr int OFF_BAR = OFF_W + TAPS * (PD / 2) * 8;          // tap weights as float2 [27][48]
-  static constexpr int OFF_RED = OFF_BAR + 64;                         // one mbarrier per ring slot, then
-  static constexpr int SMEM = OFF_RED + 2 * 24 * 16 * 4;               // LayerNorm partial sums [2][24 groups][16]
-};
 
 __device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
   return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
@@ -303,14 +106,16 @@ __device__ __forceinline__ float2 pfma2(const float2 a, const float2 b, const fl
   return *reinterpret_cast<float2*>(&d);
 }
 
-// LayerNorm + store of the first `ntok` staged tokens (pre-LN fp32, CP_PITCH float2 per token); four lanes per token,
+constexpr int MK_PITCH = 50;  // staging token pitch in float2: conflict-free 16-byte reads by the LN lanes
+
+// LayerNorm + store of the first `ntok` staged tokens (pre-LN fp32, MK_PITCH float2 per token); four lanes per token,
 // 24 channels per lane, packed fp32x2 arithmetic.
-__device__ __forceinline__ void cp_ln_flush(const float2* stg, const long long* stg_tok, const float* aff, int ntok, float eps,
-                                            bf16* __restrict__ obase) {
-  const int tok = threadIdx.x >> 2, q = threadIdx.x & 3;
-  if ((threadIdx.x & ~31) >= ntok * 4) return;  // whole warp idle
+__device__ __forceinline__ void mk_ln_flush(const float2* stg, const long long* stg_tok, const float* aff, int ntok, float eps,
+                                            bf16* __restrict__ obase, int tid) {
+  const int tok = tid >> 2, q = tid & 3;
+  if ((tid & ~31) >= ntok * 4) return;  // whole warp idle
   const bool live = tok < ntok;
-  const float2* src = stg + (live ? tok : 0) * CP_PITCH + q * 12;
+  const float2* src = stg + (live ? tok : 0) * MK_PITCH + q * 12;
   float2 x[12];
 #pragma unroll
   for (int i = 0; i < 12; i += 2) {
@@ -356,6 +161,7 @@ __device__ __forceinline__ void cp_ln_flush(const float2* stg, const long long* 
   dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
 }
 
+
 #ifdef SVIT_TIMELINE
 __device__ unsigned long long* g_pool_dbg = nullptr;
 #define PTL(tag)                                                              \
@@ -370,74 +176,134 @@ __device__ unsigned long long* g_pool_dbg = nullptr;
 #define PTL(tag) do { } while (0)
 #endif
 
-template <int S>
-__global__ void __launch_bounds__(CP_THREADS, 2)
-pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ in, Geom g, const float* __restrict__ w, const float* __restrict__ frac,
-                  const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ out, float eps) {
-  using C = CpCfg<S>;
-  using D = CpDims<S>;
-  constexpr int IW = D::IW, XN = D::XN, SW = C::SW;
+// ------------------------------------------------------------------------------------------------ march
+// pool_ln_march_kernel<S, SPR>: thread = (strip of SW consecutive outputs along W, one bf16x2 channel pair); 384 threads =
+// 8 strips x 48 pairs; 2 CTAs per SM.  A work item ("column") is one output tile of one (batch, head) over all T planes:
+// the CTA marches over the input planes and every plane is read from shared memory exactly once per strip: its three
+// input rows feed the accumulators of the three output planes t-1, t, t+1 (three rotating register sets), so one LDS.32 +
+// 2 conversions feed up to 27 FFMA2.  A finished output plane is normalised straight from the accumulators (ln_plane).
+// CTAs are PERSISTENT: grid = min(columns, 2 x SMs), the tap weights are staged once per CTA, and the TMA plane ring
+// (one box per plane, two planes ahead) runs across column boundaries, so the next column's first planes are in flight
+// while the current column finishes (a per-column prologue costs ~20 % of a column at T = 8: measured by merging two
+// columns into one CTA).  The cls / object rows of every (batch, head) are separate, cheap items done after the columns.
+// SPR = strips per output row: 2 (tile 4 rows x 2 strips) or 1 (8 rows x 1 strip: 7-wide grids waste no strips).
+constexpr int MK_THREADS = 384, MK_STRIPS = 8, MK_SLOTS = 3;
+template <int S, int SPR> struct MkCfg {
+  static_assert(S == 1 || SPR == 2, "stride 2 uses two strips per row");
+  static constexpr int SW = S == 1 ? 7 : 4;
+  static constexpr int ROWS = MK_STRIPS / SPR;
+  static constexpr int TW = S == 1 ? SPR * SW : 7;      // S = 2: the second strip's 4th output is masked
+  static constexpr int IW = S == 1 ? TW + 2 : 15;       // S = 2: strip 2 over-reads 2 tokens (they only reach the masked output)
+  static constexpr int IH = (ROWS - 1) * S + 3;
+  static constexpr int XN = (SW - 1) * S + 3;
+  static constexpr int PLANE_BYTES = IH * IW * PD * 2;  // one TMA box
+  static constexpr int SLOT_WORDS = ((PLANE_BYTES + 127) / 128) * 32 + (S == 2 ? 128 : 0);  // 128-byte aligned (+ over-read room)
+  static constexpr int RING_BYTES = MK_SLOTS * SLOT_WORDS * 4;
+  static constexpr int NTOK = MK_STRIPS * SW;           // cls / object rows staged per flush (aliases the idle ring)
+  static_assert(NTOK * MK_PITCH * 8 + NTOK * 8 <= RING_BYTES, "staging tile must fit into the plane ring");
+  static constexpr int OFF_AFF = RING_BYTES;                    // gamma | beta | w_eff
+  static constexpr int OFF_W = OFF_AFF + 3 * PD * 4;            // tap weights as float2 [27][48]
+  static constexpr int OFF_BAR = OFF_W + TAPS * (PD / 2) * 8;   // one mbarrier per ring slot
+  static constexpr int OFF_RED = OFF_BAR + 64;                  // LayerNorm partial sums [2][24 groups][16]
+  static constexpr int SMEM = OFF_RED + 2 * 24 * 16 * 4;
+};
+
+template <int S, int SPR, bool PERSIST>
+__global__ void __launch_bounds__(MK_THREADS, 2)
+pool_ln_march_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ in, Geom g, const float* __restrict__ w,
+                     const float* __restrict__ frac, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     bf16* __restrict__ out, float eps, int tiles, int ncols) {
+  using C = MkCfg<S, SPR>;
+  constexpr int IW = C::IW, XN = C::XN, SW = C::SW;
   constexpr int NV = SW > 4 ? 16 : 8;  // LayerNorm butterfly width: token sums in v[0, NV/2), sums of squares in v[NV/2, NV)
   extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* ring = reinterpret_cast<uint32_t*>(smem);
-  float2* stg = reinterpret_cast<float2*>(smem + D::OFF_STG);
-  long long* stg_tok = reinterpret_cast<long long*>(smem + D::OFF_TOK);
-  float* aff = reinterpret_cast<float*>(smem + D::OFF_AFF);  // gamma[96] | beta[96] | w_eff[96]
-  float2* sw2 = reinterpret_cast<float2*>(smem + D::OFF_W);  // [27][48]: tap weights of channel pair wd
+  float* aff = reinterpret_cast<float*>(smem + C::OFF_AFF);
+  float2* sw2 = reinterpret_cast<float2*>(smem + C::OFF_W);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  float* red = reinterpret_cast<float*>(smem + C::OFF_RED);
   const int tiles_w = (g.Wo + C::TW - 1) / C::TW;
-  const int tile = blockIdx.x;
-  const int wo0 = (tile % tiles_w) * C::TW, ho0 = (tile / tiles_w) * C::ROWS;
-  const int iw0 = wo0 * S - 1, ih0 = ho0 * S - 1;
-  const int head = blockIdx.y, b = blockIdx.z;
-  const bf16* zin = in + (int64_t)b * g.in_bs + (int64_t)head * g.in_hs;
   const int64_t Lo = (int64_t)g.T * g.Ho * g.Wo, L = (int64_t)g.T * g.H * g.W;
   const int64_t Nout = 1 + Lo + g.O;
-  bf16* obase = out + ((int64_t)b * g.h + head) * Nout * PD;
 
-  // one TMA box per plane: (96 channels of this head, IW tokens, IH rows) with zero fill outside the H x W grid
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + D::OFF_BAR);
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmap);
-    for (int i = 0; i < CP_SLOTS; ++i) tc::mbar_init(&full[i], 1);
+    for (int i = 0; i < MK_SLOTS; ++i) tc::mbar_init(&full[i], 1);
     tc::fence_barrier_init();
   }
   __syncthreads();
-  auto load_plane = [&](int t) {  // thread 0 only
-    const int slot = t % CP_SLOTS;
-    tc::mbar_arrive_expect_tx(&full[slot], D::PLANE_BYTES);
-    tc::tma_load_5d(ring + slot * D::SLOT_WORDS, &tmap, &full[slot], head * PD, iw0, ih0, t, b);
+  // plane m of this CTA's sequence = plane (m % T) of its (m / T)-th column; thread 0 walks (column, plane, slot) two planes
+  // ahead; the walker lives in shared memory (registers are the scarce resource of this kernel)
+  int* pf = reinterpret_cast<int*>(smem + C::OFF_BAR + 32);  // {column, plane, slot, c0 = head*96, c1 = iw0, c2 = ih0, c4 = b}
+  auto pf_column = [&](int col) {  // TMA coordinates of a column: once per column, not per plane
+    const int tile = col % tiles, bh = col / tiles;
+    pf[0] = col;
+    pf[3] = (bh % g.h) * PD;
+    pf[4] = (tile % tiles_w) * C::TW * S - 1;
+    pf[5] = (tile / tiles_w) * C::ROWS * S - 1;
+    pf[6] = bh / g.h;
+  };
+  // !PERSIST (one column per CTA): the coordinates stay in registers and the ring slot is the compile-time R of step()
+  const int c_tile = blockIdx.x % tiles, c_bh = blockIdx.x / tiles;
+  const int c_w = (c_tile % tiles_w) * C::TW * S - 1, c_h = (c_tile / tiles_w) * C::ROWS * S - 1;
+  auto load_plane = [&](int t) {  // thread 0 only, !PERSIST
+    const int sl = t % MK_SLOTS;
+    tc::mbar_arrive_expect_tx(&full[sl], C::PLANE_BYTES);
+    tc::tma_load_5d(ring + sl * C::SLOT_WORDS, &tmap, &full[sl], (c_bh % g.h) * PD, c_w, c_h, t, c_bh / g.h);
+  };
+  auto load_next = [&]() {  // thread 0 only, PERSIST
+    const int pf_col = pf[0], pf_t = pf[1], pf_slot = pf[2];
+    if (pf_col < ncols) {
+      tc::mbar_arrive_expect_tx(&full[pf_slot], C::PLANE_BYTES);
+      tc::tma_load_5d(ring + pf_slot * C::SLOT_WORDS, &tmap, &full[pf_slot], pf[3], pf[4], pf[5], pf_t, pf[6]);
+      pf[2] = pf_slot == MK_SLOTS - 1 ? 0 : pf_slot + 1;
+      if (pf_t + 1 == g.T) {
+        pf[1] = 0;
+        if (pf_col + (int)gridDim.x < ncols) pf_column(pf_col + gridDim.x);
+        else pf[0] = ncols;
+      } else {
+        pf[1] = pf_t + 1;
+      }
+    }
   };
   if (threadIdx.x == 0) {
-    for (int t = 0; t < 2 && t < g.T; ++t) load_plane(t);
+    if (PERSIST) {
+      pf_column(blockIdx.x);
+      pf[1] = 0;
+      pf[2] = 0;
+      load_next();
+      load_next();
+    } else {
+      for (int t = 0; t < 2 && t < g.T; ++t) load_plane(t);
+    }
   }
-  for (int i = threadIdx.x; i < PD; i += CP_THREADS) {
+  for (int i = threadIdx.x; i < PD; i += MK_THREADS) {
     aff[i] = gamma[i];
     aff[PD + i] = beta[i];
   }
-
-  const int strip = threadIdx.x / 48, wd = threadIdx.x - strip * 48;   // strip, channel-pair word
-  const int srow = strip >> 1, scol = (strip & 1) * SW;
-  const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < TAPS * 48; i += CP_THREADS) {
+  for (int i = threadIdx.x; i < TAPS * 48; i += MK_THREADS) {
     const int tp = i / 48, pr = i - tp * 48;
     sw2[i] = make_float2(__ldg(w + (2 * pr) * TAPS + tp), __ldg(w + (2 * pr + 1) * TAPS + tp));
   }
-  // this thread's output tokens: row ho0 + srow, columns wo0 + scol + o for o < nvalid; optr walks over the output planes
-  int nvalid = min(SW, min(C::TW - scol, g.Wo - (wo0 + scol)));
-  if (ho0 + srow >= g.Ho || nvalid < 0) nvalid = 0;
-  uint32_t* optr = reinterpret_cast<uint32_t*>(obase + (1 + (int64_t)(ho0 + srow) * g.Wo + wo0 + scol) * PD) + wd;
+
+  const int strip = threadIdx.x / 48, wd = threadIdx.x - strip * 48;   // strip, channel-pair word
+  const int srow = strip / SPR, scol = (strip % SPR) * SW;
+  const int lane = threadIdx.x & 31;
   const int plane_words = g.Ho * g.Wo * (PD / 2);
   const uint32_t* xbase = ring + ((srow * S) * IW + scol * S) * 48 + wd;
   const float2* wbase = sw2 + wd;
   const float2 gam = make_float2(__ldg(gamma + 2 * wd), __ldg(gamma + 2 * wd + 1));
   const float2 bet = make_float2(__ldg(beta + 2 * wd), __ldg(beta + 2 * wd + 1));
-  // LayerNorm statistics meet here: red[plane parity][16-lane group (24)][16]; a strip = groups 3*strip .. 3*strip + 2
-  float* red = reinterpret_cast<float*>(smem + D::OFF_RED);
+  // LayerNorm statistics meet in red[plane parity][16-lane group (24)][16]; a strip = groups 3*strip .. 3*strip + 2
   const int l16 = lane & 15;
   const int my_tok = l16 & (NV / 2 - 1);                        // the token whose statistics this lane finishes
   const int red_wr = (threadIdx.x >> 4) * 16 + l16;
   const int red_rd = strip * 48 + (NV == 16 ? my_tok : 2 * my_tok);
   const int bar_id = 1 + (strip >> 1);
+  // per column: this thread's output tokens are row ho0 + srow, columns wo0 + scol + o for o < nvalid; optr walks the planes
+  int nvalid = 0;
+  uint32_t* optr = nullptr;
+  int slot = 0, parity = 0;  // ring position of the plane being consumed
 
   float2 acc[3][SW];
 
@@ -506,21 +372,32 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
 
   int tl_n = 0;
   (void)tl_n;
-  // One input plane tp: its three rows (kh) feed output planes tp+1 (kt = 0, a fresh accumulator set: the first tap
-  // is a multiply, so sets are never zeroed), tp (kt = 1) and tp-1 (kt = 2, which is complete afterwards).
-  // R = tp % 3 selects the rotating sets at compile time; E bit 0 = first plane (no plane tp-1), bit 1 = last plane
-  // (no plane tp+1; its own output plane is normalised here too).  No branches inside the tap loops.
+  // One input plane tp of the current column: its three rows (kh) feed output planes tp+1 (kt = 0, a fresh accumulator
+  // set: the first tap is a multiply, so sets are never zeroed), tp (kt = 1) and tp-1 (kt = 2, complete afterwards).
+  // R = tp % 3 selects the rotating sets at compile time; E bit 0 = first plane of the column (no plane tp-1), bit 1 =
+  // last plane (no plane tp+1; its own output plane is normalised here too).  No branches inside the tap loops.
   auto step = [&](auto rtag, auto etag, int tp) {
     constexpr int R = decltype(rtag)::value;
     constexpr int E = decltype(etag)::value;
     constexpr bool FIRST = (E & 1) != 0, LAST = (E & 2) != 0;
     PTL(100 + tp);
-    __syncthreads();                                    // ring slot (tp+2)%3 is free
+    __syncthreads();                           // every thread is done with the slot that the next load overwrites
     PTL(200 + tp);
-    if (threadIdx.x == 0 && tp + 2 < g.T) load_plane(tp + 2);
-    tc::mbar_wait_hot(&full[R], (tp / CP_SLOTS) & 1);   // plane tp has landed
+    const uint32_t* pl;
+    if (PERSIST) {
+      if (threadIdx.x == 0) load_next();         // two planes ahead (possibly the next column's)
+      tc::mbar_wait_hot(&full[slot], parity);    // this plane has landed
+      pl = xbase + slot * C::SLOT_WORDS;
+      if (++slot == MK_SLOTS) {
+        slot = 0;
+        parity ^= 1;
+      }
+    } else {
+      if (threadIdx.x == 0 && tp + 2 < g.T) load_plane(tp + 2);
+      tc::mbar_wait_hot(&full[R], (tp / MK_SLOTS) & 1);
+      pl = xbase + R * C::SLOT_WORDS;
+    }
     PTL(300 + tp);
-    const uint32_t* pl = xbase + R * D::SLOT_WORDS;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       float2 x[XN];
@@ -557,56 +434,80 @@ pool_ln_cp_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restri
   using EFIRST = std::integral_constant<int, 1>;
   using ELAST = std::integral_constant<int, 2>;
   using EONLY = std::integral_constant<int, 3>;
-  if (g.T == 1) {
-    step(R0{}, EONLY{}, 0);
-  } else {
-    step(R0{}, EFIRST{}, 0);
-    int tp = 1;
-    for (; tp + 3 <= g.T - 1; tp += 3) {
-      step(R1{}, EMID{}, tp);
-      step(R2{}, EMID{}, tp + 1);
-      step(R0{}, EMID{}, tp + 2);
+
+  for (int col = blockIdx.x; col < ncols; col += gridDim.x) {  // !PERSIST: exactly one iteration (grid = ncols)
+    {
+      const int tile = col % tiles, bh = col / tiles;
+      const int wo0 = (tile % tiles_w) * C::TW, ho0 = (tile / tiles_w) * C::ROWS;
+      nvalid = min(SW, min(C::TW - scol, g.Wo - (wo0 + scol)));
+      if (ho0 + srow >= g.Ho || nvalid < 0) nvalid = 0;
+      optr = reinterpret_cast<uint32_t*>(out + ((int64_t)bh * Nout + 1 + (int64_t)(ho0 + srow) * g.Wo + wo0 + scol) * PD) + wd;
     }
-    const int rem = g.T - 1 - tp;  // middle planes left before the last one: 0, 1 or 2
-    if (rem == 0) {
-      step(R1{}, ELAST{}, tp);
-    } else if (rem == 1) {
-      step(R1{}, EMID{}, tp);
-      step(R2{}, ELAST{}, tp + 1);
+    if (g.T == 1) {
+      step(R0{}, EONLY{}, 0);
     } else {
-      step(R1{}, EMID{}, tp);
-      step(R2{}, EMID{}, tp + 1);
-      step(R0{}, ELAST{}, tp + 2);
+      step(R0{}, EFIRST{}, 0);
+      int tp = 1;
+      for (; tp + 3 <= g.T - 1; tp += 3) {
+        step(R1{}, EMID{}, tp);
+        step(R2{}, EMID{}, tp + 1);
+        step(R0{}, EMID{}, tp + 2);
+      }
+      const int rem = g.T - 1 - tp;  // middle planes left before the last one: 0, 1 or 2
+      if (rem == 0) {
+        step(R1{}, ELAST{}, tp);
+      } else if (rem == 1) {
+        step(R1{}, EMID{}, tp);
+        step(R2{}, ELAST{}, tp + 1);
+      } else {
+        step(R1{}, EMID{}, tp);
+        step(R2{}, EMID{}, tp + 1);
+        step(R0{}, ELAST{}, tp + 2);
+      }
     }
   }
-  // cls + object tokens of this (batch, head): tile 0, through the fp32 staging tile and the 4-lanes-per-token LayerNorm
-  if (tile == 0) {
+
+  // cls + object rows: item = one (batch, head), through an fp32 staging tile (aliases the idle ring) and the
+  // 4-lanes-per-token LayerNorm.  Items are dealt from the last CTA backwards: those CTAs have the fewest columns.
+  {
+    float2* stg = reinterpret_cast<float2*>(ring);
+    long long* stg_tok = reinterpret_cast<long long*>(smem + C::NTOK * MK_PITCH * 8);
     float* sweff = aff + 2 * PD;
-    if (threadIdx.x < 48) {
-      float2 a = make_float2(0.f, 0.f);
+    const int nbh = g.B * g.h;
+    bool have_weff = false;
+    for (int item = gridDim.x - 1 - blockIdx.x; item < nbh; item += gridDim.x) {
+      if (!have_weff) {
+        if (threadIdx.x < 48) {
+          float2 a = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int tp = 0; tp < TAPS; ++tp) {
-        const float f = __ldg(frac + tp);
-        a.x = fmaf(sw2[tp * 48 + wd].x, f, a.x);
-        a.y = fmaf(sw2[tp * 48 + wd].y, f, a.y);
+          for (int tp = 0; tp < TAPS; ++tp) {
+            const float f = __ldg(frac + tp);
+            a.x = fmaf(sw2[tp * 48 + wd].x, f, a.x);
+            a.y = fmaf(sw2[tp * 48 + wd].y, f, a.y);
+          }
+          sweff[2 * wd] = a.x;
+          sweff[2 * wd + 1] = a.y;
+        }
+        have_weff = true;
       }
-      sweff[2 * wd] = a.x;
-      sweff[2 * wd + 1] = a.y;
-    }
-    for (int base = 0; base < 1 + g.O; base += D::NTOK) {
-      __syncthreads();  // previous flush finished with the staging tile; w_eff visible
-      const int n = min(D::NTOK, 1 + g.O - base);
-      for (int i = threadIdx.x; i < n * 48; i += CP_THREADS) {
-        const int k = i / 48, ww = i - k * 48;
-        const int r = base + k;  // 0 = cls, r >= 1: object token r-1
-        const int64_t tok_in = r == 0 ? 0 : L + r;
-        const uint32_t v = reinterpret_cast<const uint32_t*>(zin + tok_in * g.in_ts)[ww];
-        const float sx = r == 0 ? 1.f : sweff[2 * ww], sy = r == 0 ? 1.f : sweff[2 * ww + 1];
-        stg[k * CP_PITCH + ww] = make_float2(lo_f(v) * sx, hi_f(v) * sy);
-        if (ww == 0) stg_tok[k] = r == 0 ? 0 : Lo + r;
+      const int head = item % g.h, b = item / g.h;
+      const bf16* zin = in + (int64_t)b * g.in_bs + (int64_t)head * g.in_hs;
+      bf16* obase = out + (int64_t)item * Nout * PD;
+      for (int base = 0; base < 1 + g.O; base += C::NTOK) {
+        __syncthreads();  // ring reads / previous flush finished with the staging tile; w_eff visible
+        const int n = min(C::NTOK, 1 + g.O - base);
+        for (int i = threadIdx.x; i < n * 48; i += MK_THREADS) {
+          const int k = i / 48, ww = i - k * 48;
+          const int r = base + k;  // 0 = cls, r >= 1: object token r-1
+          const int64_t tok_in = r == 0 ? 0 : L + r;
+          const uint32_t v = reinterpret_cast<const uint32_t*>(zin + tok_in * g.in_ts)[ww];
+          const float sx = r == 0 ? 1.f : sweff[2 * ww], sy = r == 0 ? 1.f : sweff[2 * ww + 1];
+          stg[k * MK_PITCH + ww] = make_float2(lo_f(v) * sx, hi_f(v) * sy);
+          if (ww == 0) stg_tok[k] = r == 0 ? 0 : Lo + r;
+        }
+        __syncthreads();
+        mk_ln_flush(stg, stg_tok, aff, n, eps, obase, threadIdx.x);
       }
-      __syncthreads();
-      cp_ln_flush(stg, stg_tok, aff, n, eps, obase);
     }
   }
 }
@@ -701,6 +602,42 @@ extern "C" int svit_debug_pool_timeline(void* device_buffer) {
 }
 #endif
 
+namespace {
+template <int SV, int SPRV, bool PERSIST>
+int launch_march(const void* in, int64_t in_bs, int64_t in_ts, const Geom& g, const float* conv_w, const float* tap_frac,
+                 const float* gamma, const float* beta, void* out, float eps, cudaStream_t st) {
+  using C = MkCfg<SV, SPRV>;
+  // 5-D view of the patch tokens: (head*96 + c, w, h, t, b); the box of a CTA is (96, IW, IH, 1, 1), zero fill outside
+  svit_tmap_encode_fn enc = svit_get_tmap_encode();
+  if (!enc) return SVIT_ENOTSUP;
+  CUtensorMap tm;
+  cuuint64_t dims[5] = {(cuuint64_t)g.h * PD, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.T, (cuuint64_t)g.B};
+  cuuint64_t strides[4] = {(cuuint64_t)in_ts * 2, (cuuint64_t)g.W * in_ts * 2, (cuuint64_t)g.H * g.W * in_ts * 2, (cuuint64_t)in_bs * 2};
+  cuuint32_t box[5] = {PD, (cuuint32_t)C::IW, (cuuint32_t)C::IH, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const bf16* base = (const bf16*)in + in_ts;  // token 0 is the cls token
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return SVIT_EINVAL;
+  auto kern = pool_ln_march_kernel<SV, SPRV, PERSIST>;
+  static SvitDevOnce configured;
+  if (configured.need()) {
+    SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured.done();
+  }
+  const int tiles = ((g.Wo + C::TW - 1) / C::TW) * ((g.Ho + C::ROWS - 1) / C::ROWS);
+  const int64_t ncols = (int64_t)tiles * g.h * g.B;
+  if (ncols > (1ll << 30)) return SVIT_EINVAL;
+  int64_t grid = PERSIST ? (int64_t)svit_num_sms() * 2 : ncols;
+  if (grid > ncols) grid = ncols;
+  kern<<<(unsigned)grid, MK_THREADS, C::SMEM, st>>>(tm, (const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps,
+                                                    tiles, (int)ncols);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+}  // namespace
+
 // bf16 fast path of svit_pool_ln_fwd (pool_ln.cu dispatches here).  Requires 4-byte aligned token slices.
 int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const float* conv_w,
                           const float* tap_frac, const float* gamma, const float* beta, void* out, int B, int h, int T,
@@ -710,68 +647,23 @@ int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   g.Ho = (H - 1) / s + 1; g.Wo = (W - 1) / s + 1;
   g.in_bs = in_bs; g.in_ts = in_ts; g.in_hs = in_hs;
   const int sms = svit_num_sms();
-  const bool tiled = (s == 1 || s == 2) && (T <= 64) && (in_ts % 8 == 0) && (in_hs % 8 == 0) && (in_bs % 8 == 0) &&
-                     ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (tiled && in_hs == PD && (T * H * W) > 0) {
-    // 5-D view of the patch tokens: (head*96 + c, w, h, t, b); the box of a CTA is (96, IW, IH, 1, 1)
-    svit_tmap_encode_fn enc = svit_get_tmap_encode();
-    if (!enc) return SVIT_ENOTSUP;
-    const int IWb = s == 1 ? CpDims<1>::IW : CpDims<2>::IW, IHb = s == 1 ? CpDims<1>::IH : CpDims<2>::IH;
-    CUtensorMap tm;
-    cuuint64_t dims[5] = {(cuuint64_t)h * PD, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
-    cuuint64_t strides[4] = {(cuuint64_t)in_ts * 2, (cuuint64_t)W * in_ts * 2, (cuuint64_t)H * W * in_ts * 2, (cuuint64_t)in_bs * 2};
-    cuuint32_t box[5] = {PD, (cuuint32_t)IWb, (cuuint32_t)IHb, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const bf16* base = (const bf16*)in + in_ts;  // token 0 is the cls token
-    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return SVIT_EINVAL;
-    if (s == 1) {
-      using C = CpCfg<1>;
-      static SvitDevOnce configured;
-      if (configured.need()) {
-        SVIT_CUDA(cudaFuncSetAttribute(pool_ln_cp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CpDims<1>::SMEM));
-        configured.done();
-      }
-      dim3 grid((unsigned)(((g.Wo + C::TW - 1) / C::TW) * ((g.Ho + C::ROWS - 1) / C::ROWS)), (unsigned)h, (unsigned)B);
-      pool_ln_cp_kernel<1><<<grid, CP_THREADS, CpDims<1>::SMEM, st>>>(tm, (const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
-    } else {
-      using C = CpCfg<2>;
-      static SvitDevOnce configured;
-      if (configured.need()) {
-        SVIT_CUDA(cudaFuncSetAttribute(pool_ln_cp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CpDims<2>::SMEM));
-        configured.done();
-      }
-      dim3 grid((unsigned)(((g.Wo + C::TW - 1) / C::TW) * ((g.Ho + C::ROWS - 1) / C::ROWS)), (unsigned)h, (unsigned)B);
-      pool_ln_cp_kernel<2><<<grid, CP_THREADS, CpDims<2>::SMEM, st>>>(tm, (const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
-    }
-    SVIT_CHECK_LAUNCH();
-    return 0;
-  }
-  if (tiled && s == 1) {
-    using C = TileCfg<1>;
-    static SvitDevOnce configured;
-    if (configured.need()) {
-      SVIT_CUDA(cudaFuncSetAttribute(pool_ln_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileDims<1>::SMEM));
-      configured.done();
-    }
-    dim3 grid((unsigned)(((g.Wo + C::TWO - 1) / C::TWO) * ((g.Ho + C::THO - 1) / C::THO)), (unsigned)h, (unsigned)B);
-    pool_ln_tiled_kernel<1><<<grid, 256, TileDims<1>::SMEM, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
-    SVIT_CHECK_LAUNCH();
-    return 0;
-  }
-  if (tiled && s == 2) {
-    using C = TileCfg<2>;
-    static SvitDevOnce configured;
-    if (configured.need()) {
-      SVIT_CUDA(cudaFuncSetAttribute(pool_ln_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileDims<2>::SMEM));
-      configured.done();
-    }
-    dim3 grid((unsigned)(((g.Wo + C::TWO - 1) / C::TWO) * ((g.Ho + C::THO - 1) / C::THO)), (unsigned)h, (unsigned)B);
-    pool_ln_tiled_kernel<2><<<grid, 256, TileDims<2>::SMEM, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps);
-    SVIT_CHECK_LAUNCH();
-    return 0;
+  const bool tma_ok = (s == 1 || s == 2) && (in_ts % 8 == 0) && (in_bs % 8 == 0) && in_hs == PD && (T * H * W) > 0 &&
+                      ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (tma_ok) {
+    // Persistent CTAs (static column lists) pay off only where columns are short and many: stride 2 on the large grids
+    // (B64 h1 56x56 s2: 112 us against 119 us).  Everywhere else one column per CTA wins: the hardware scheduler
+    // balances the uneven tail (3.46 columns per CTA slot at B64 h4 14x14 s1: 95 us against 114 us persistent).
+    static const int mode = []() { const char* e = getenv("SVIT_POOL_PERSIST"); return e ? atoi(e) : -1; }();  // -1 auto, 0 never, 1 always
+    const bool wide = s == 1 && g.Wo > 7;
+    const int64_t cols_s2 = (int64_t)((g.Wo + 6) / 7) * ((g.Ho + 3) / 4) * h * B;
+    const bool persist = mode < 0 ? (s == 2 && cols_s2 >= (int64_t)sms * 12) : mode != 0;
+#define MARCH(SV, SPRV) \
+  (persist ? launch_march<SV, SPRV, true>(in, in_bs, in_ts, g, conv_w, tap_frac, gamma, beta, out, eps, st) \
+           : launch_march<SV, SPRV, false>(in, in_bs, in_ts, g, conv_w, tap_frac, gamma, beta, out, eps, st))
+    if (s == 2) return MARCH(2, 2);
+    if (!wide) return MARCH(1, 1);
+    return MARCH(1, 2);
+#undef MARCH
   }
   const int64_t total = (int64_t)B * h * (1 + (int64_t)T * g.Ho * g.Wo + O);
   int64_t blocks = (total + 15) / 16;

@@ -52,9 +52,10 @@ class GradAllReducer:
     Parameters that received no gradient are reduced as zeros, which mirrors find_unused_parameters=False
     plus the reference's `+ sum(p) * 0` tricks (video_model_builder.py:359, 514)."""
 
-    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
+    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None, overlap: bool = True):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.overlap = overlap  # False: one pass after backward (no NCCL CTAs next to the persistent GEMM kernels)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         order = list(reversed(self.params))  # backward completion order ~ reverse registration order
         self.buckets: List[List[torch.nn.Parameter]] = []
@@ -87,6 +88,9 @@ class GradAllReducer:
         self._op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
         self._pending = [0] * len(self.buckets)
         self._works = [None] * len(self.buckets)
+        self._launched = [0] * len(self.buckets)
+        self._next = 0
+        self._prepared = False
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self.bytes_per_step = sum(f.numel() * 4 for f in self.flat)
 
@@ -94,6 +98,9 @@ class GradAllReducer:
         for i, b in enumerate(self.buckets):
             self._pending[i] = len(b)
             self._works[i] = None
+            self._launched[i] = 0
+        self._next = 0
+        self._prepared = True
 
     def _launch(self, bi: int):
         """Pack the bucket with ONE multi-tensor copy (torch._foreach_copy_), then start its all-reduce."""
@@ -105,22 +112,39 @@ class GradAllReducer:
         have = [(v, p.grad) for v, p in zip(views, b) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
         if have:
             torch._foreach_copy_([v for v, _ in have], [g.view_as(v) for v, g in have])
+        self._launched[bi] += 1
         if self.world > 1:
             self._works[bi] = dist.all_reduce(self.flat[bi], op=self._op, group=self.group, async_op=True)
 
+    def _drain_ready(self):
+        """Launch, IN BUCKET ORDER, every bucket whose gradients are complete.  A complete bucket behind an incomplete
+        one waits (as DDP does): ranks whose sets of gradient-less parameters differ (video ranks never touch the box /
+        contact heads, image ranks never touch pos_embed_temporal or head.projection) would otherwise issue the same
+        collectives in different orders -- mismatched sizes, a hang or a wrong reduction."""
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
+
     def _on_grad(self, p: torch.nn.Parameter):
+        if not self._prepared:
+            return  # backward outside prepare()/finish(): nothing is reduced, finish() will say so
         bi = self._where[p][0]
         self._pending[bi] -= 1
-        if self._pending[bi] == 0:
-            self._launch(bi)
+        if self._pending[bi] == 0 and self.overlap:
+            self._drain_ready()
 
     def finish(self):
-        """Launch the buckets whose parameters got no gradient, wait, average; .grad becomes a view of the bucket
-        (no copy back: 405 attribute assignments instead of 405 kernels)."""
-        for bi in range(len(self.buckets)):
-            if self._pending[bi] > 0:
-                self._pending[bi] = 0
-                self._launch(bi)
+        """Launch what is left (buckets with gradient-less parameters, or everything when overlap is off) in bucket
+        order, wait, average; .grad becomes a view of the bucket (no copy back: 405 attribute assignments instead of
+        405 kernels)."""
+        if not self._prepared:
+            raise RuntimeError("GradAllReducer.finish() without prepare(): call prepare() before backward()")
+        while self._next < len(self.buckets):
+            self._pending[self._next] = 0
+            self._launch(self._next)
+            self._next += 1
+        if any(n != 1 for n in self._launched):
+            raise RuntimeError(f"GradAllReducer: every bucket must be reduced exactly once per step, got {self._launched}")
         for bi, b in enumerate(self.buckets):
             if self._works[bi] is not None:
                 self._works[bi].wait()
@@ -128,6 +152,7 @@ class GradAllReducer:
                 self.flat[bi].div_(self.world)
             for p, v in zip(b, self._views[bi]):
                 p.grad = v
+        self._prepared = False
 
     def remove(self):
         for h in self._hooks:

@@ -100,6 +100,7 @@ class FusedAdamW:
         self._step = 0
         self._tables = None
         self._sqnorm = None
+        self._hyper_dev = None
 
     # ---- table construction -----------------------------------------------------------------------------------
     def _build(self):
@@ -136,29 +137,75 @@ class FusedAdamW:
         self._sqnorm = torch.zeros(len(self._tables) + 1, dtype=torch.float32, device=dev)
 
     def _refresh(self, t):
-        """Gradient pointers change whenever autograd allocates fresh .grad tensors: re-upload the table when they did."""
+        """Gradient pointers change whenever autograd allocates fresh .grad tensors: re-upload the table when they did.
+
+        A parameter without a gradient gets a persistent ZERO gradient: the reference keeps every parameter in the graph
+        (`+ sum(p) * 0` terms, video_model_builder.py:359, 514), so torch.optim.AdamW still applies decoupled weight
+        decay and moment decay to it every step -- with or without the gradient all-reducer in front."""
         ptrs = []
         for p in t["params"]:
             g = p.grad
-            if g is None:  # torch.optim skips parameters without a gradient: a zero-length table entry does the same
-                ptrs.append(0)
-                continue
+            if g is None:
+                g = p.grad = torch.zeros_like(p)
             if g.dtype != torch.float32 or not g.is_contiguous():
                 raise RuntimeError("FusedAdamW: gradients must be contiguous fp32 tensors")
             ptrs.append(g.data_ptr())
         if ptrs != t["grad_ptrs"]:
+            # the pinned table is the source of an asynchronous copy: the previous upload must have executed before the
+            # host rewrites it (the step never synchronises otherwise, so the host may run a full step ahead)
+            capturing = t["dev"].is_cuda and torch.cuda.is_current_stream_capturing()
+            if t.get("uploaded") is not None and not capturing:
+                t["uploaded"].synchronize()
             t["host"][:, 1] = torch.tensor(ptrs, dtype=torch.int64)
-            t["host"][:, 4] = torch.tensor([p.numel() if a else 0 for p, a in zip(t["params"], ptrs)], dtype=torch.int64)
             t["dev"].copy_(t["host"], non_blocking=True)
+            if t["dev"].is_cuda and not capturing:
+                t["uploaded"] = torch.cuda.Event()
+                t["uploaded"].record()
             t["grad_ptrs"] = ptrs
+
+    # ---- CUDA-graph mode: step-dependent scalars live in device memory -------------------------------------------
+    def _hyper_row(self, g) -> list:
+        import numpy as np
+        b1, b2 = g["betas"]
+        st = np.float32(self._step)
+        bc1 = np.float32(1.0) - np.power(np.float32(b1), st)
+        sqrt_bc2 = np.sqrt(np.float32(1.0) - np.power(np.float32(b2), st))
+        return [float(g["lr"]), float(bc1), float(sqrt_bc2), 0.0]
+
+    def upload_hyper(self):
+        """Graph mode, OUTSIDE the graph and before each replay: advance the step counter and refresh
+        {lr, 1 - beta1^step, sqrt(1 - beta2^step)} per group in device memory (one small H2D copy from a ring of pinned
+        rows, so the host never rewrites a row whose copy may still be pending)."""
+        if self._tables is None:
+            self._build()
+        live = [g for g, t in zip(self.param_groups, self._tables) if t is not None]
+        if self._hyper_dev is None:
+            dev = self._sqnorm.device
+            self._hyper_dev = torch.zeros(len(live), 4, dtype=torch.float32, device=dev)
+            self._hyper_host = torch.zeros(8, len(live), 4, dtype=torch.float32).pin_memory()
+            self._hyper_events = [None] * 8
+        self._step += 1
+        slot = self._step % 8
+        if self._hyper_events[slot] is not None:
+            self._hyper_events[slot].synchronize()
+        self._hyper_host[slot] = torch.tensor([self._hyper_row(g) for g in live], dtype=torch.float32)
+        self._hyper_dev.copy_(self._hyper_host[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_events[slot] = ev
 
     # ---- public API -------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, max_norm: Optional[float] = None):
-        """One AdamW step over every group; `max_norm` fuses torch.nn.utils.clip_grad_norm_(all params, max_norm)."""
+    def step(self, max_norm: Optional[float] = None, captured: bool = False):
+        """One AdamW step over every group; `max_norm` fuses torch.nn.utils.clip_grad_norm_(all params, max_norm).
+        captured=True (inside a CUDA graph capture / GraphedTrainStep): lr and the bias corrections are read from the
+        device row written by upload_hyper(), and the step counter is not touched here."""
         if self._tables is None:
             self._build()
-        self._step += 1
+        if captured and self._hyper_dev is None:
+            raise RuntimeError("FusedAdamW.step(captured=True) needs upload_hyper() first")
+        if not captured:
+            self._step += 1
         live = [(g, t) for g, t in zip(self.param_groups, self._tables) if t is not None]
         for _, t in live:
             self._refresh(t)
@@ -169,16 +216,22 @@ class FusedAdamW:
                       t["nchunks"], CHUNK, self._sqnorm[i:].data_ptr(), _stream())
             total = self._sqnorm[len(live):len(live) + 1]
             torch.sum(self._sqnorm[:len(live)], dim=0, keepdim=True, out=total)  # norm over all groups
-        for g, t in live:
+        for i, (g, t) in enumerate(live):
             b1, b2 = g["betas"]
-            _call("svit_adamw_step", t["dev"].data_ptr(), t["chunk_tensor"].data_ptr(), t["chunk_start"].data_ptr(),
-                  t["nchunks"], CHUNK, float(g["lr"]), float(b1), float(b2), float(g["eps"]), self._step,
-                  float(max_norm) if total is not None else 0.0, total.data_ptr() if total is not None else None, _stream())
+            mn = float(max_norm) if total is not None else 0.0
+            tp = total.data_ptr() if total is not None else None
+            if captured:
+                _call("svit_adamw_step_dev", t["dev"].data_ptr(), t["chunk_tensor"].data_ptr(), t["chunk_start"].data_ptr(),
+                      t["nchunks"], CHUNK, self._hyper_dev[i].data_ptr(), float(b1), float(b2), float(g["eps"]), mn, tp,
+                      _stream())
+            else:
+                _call("svit_adamw_step", t["dev"].data_ptr(), t["chunk_tensor"].data_ptr(), t["chunk_start"].data_ptr(),
+                      t["nchunks"], CHUNK, float(g["lr"]), float(b1), float(b2), float(g["eps"]), self._step, mn, tp,
+                      _stream())
             # the kernel writes the parameters through raw pointers: tell autograd / the bf16 weight caches
             # (ops.cast_weight keys on param._version) that they changed
-            for p, gp in zip(t["params"], t["grad_ptrs"]):
-                if gp:
-                    torch._C._increment_version(p)
+            for p in t["params"]:
+                torch._C._increment_version(p)
 
     def grad_norm(self) -> torch.Tensor:
         """Total gradient norm seen by the last clipped step (device scalar)."""

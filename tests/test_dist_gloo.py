@@ -83,3 +83,64 @@ def test_single_process_reducer_is_identity():
     red.finish()
     for p, b in zip(net.parameters(), before):
         assert torch.equal(p.grad, b if b is not None else torch.zeros_like(p))
+
+
+class _TwoHeads(nn.Module):
+    """Trunk with two heads: video ranks use one, image ranks the other (losses.VideoImageLoss(is_video=...))."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.trunk = nn.Sequential(nn.Linear(12, 24), nn.GELU(), nn.Linear(24, 24))
+        self.head_video = nn.Linear(24, 7)
+        self.head_image = nn.Linear(24, 4)
+
+
+def _hetero_worker(rank, world, port, overlap, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        net = _TwoHeads()
+        red = GradAllReducer(net.parameters(), bucket_bytes=64, overlap=overlap)  # tiny buckets: heads in different buckets
+        assert len(red.buckets) >= 4
+        x = torch.randn(6, 12, generator=torch.Generator().manual_seed(10 + rank))
+        for _ in range(2):
+            for p in net.parameters():
+                p.grad = None
+            red.prepare()
+            feat = net.trunk(x)
+            loss = net.head_video(feat).square().mean() if rank == 0 else net.head_image(feat).square().mean()
+            loss.backward()
+            red.finish()
+        torch.save({n: p.grad.clone() for n, p in net.named_parameters()}, out + f".{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_ranks_with_different_unused_parameters(tmp_path, overlap):
+    """ranks whose gradient-less parameter sets differ must still issue the bucket all-reduces in the
+    same order (fixed bucket order); the result is the mean over ranks with zeros for the unused heads."""
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_hetero_worker, args=(2, _free_port(), overlap, out), nprocs=2, join=True)
+    got0, got1 = torch.load(out + ".0"), torch.load(out + ".1")
+    want = {}
+    for rank in range(2):
+        net = _TwoHeads()
+        x = torch.randn(6, 12, generator=torch.Generator().manual_seed(10 + rank))
+        feat = net.trunk(x)
+        (net.head_video(feat).square().mean() if rank == 0 else net.head_image(feat).square().mean()).backward()
+        for n, p in net.named_parameters():
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            want[n] = want.get(n, 0) + g / 2
+    for n in want:
+        assert torch.allclose(got0[n], want[n], rtol=1e-5, atol=1e-7), n
+        assert torch.equal(got0[n], got1[n]), n
+
+
+def test_finish_without_prepare_raises():
+    net = _net()
+    red = GradAllReducer(net.parameters(), bucket_bytes=256)
+    net[:5](torch.randn(4, 16)).sum().backward()
+    with pytest.raises(RuntimeError, match="prepare"):
+        red.finish()
