@@ -18,7 +18,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("SVIT_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """SVIT_REFERENCE_ROOT, then /root/reference (build container), then <repo>/baseline/_ref (a driver-side install of
+    the unmodified reference package, git-ignored) -- the first that holds slowfast/models."""
+    cands = [os.environ.get("SVIT_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "slowfast", "models")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

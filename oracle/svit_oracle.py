@@ -75,7 +75,7 @@ def conv_obj_scale(w: torch.Tensor, stride: Sequence[int]) -> torch.Tensor:
     averaged.  Equivalent to mean over output positions of the sum of in-bounds taps."""
     C = w.shape[0]
     k = w.shape[-3:]
-    ones = torch.ones(1, C, *k, dtype=w.dtype)
+    ones = torch.ones(1, C, *k, dtype=w.dtype, device=w.device)
     out = F.conv3d(ones, w, stride=tuple(stride), padding=tuple(x // 2 for x in k), groups=C)
     return out.mean(dim=(-1, -2, -3)).reshape(C)
 

@@ -144,6 +144,5 @@ class GraphedTrainStep:
         self.graph.replay()
         ops._state["launches"] += self.launches_per_replay
         if self.optimizer is not None:
-            for p in self.params:  # the replayed kernels wrote the parameters through raw pointers
-                torch._C._increment_version(p)
+            torch._C._increment_version(self.params)  # the replayed kernels wrote the parameters through raw pointers
         return self.loss

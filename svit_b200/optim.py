@@ -230,8 +230,7 @@ class FusedAdamW:
                       _stream())
             # the kernel writes the parameters through raw pointers: tell autograd / the bf16 weight caches
             # (ops.cast_weight keys on param._version) that they changed
-            for p in t["params"]:
-                torch._C._increment_version(p)
+            torch._C._increment_version(t["params"])  # takes an iterable of tensors: one call, not one per tensor
 
     def grad_norm(self) -> torch.Tensor:
         """Total gradient norm seen by the last clipped step (device scalar)."""

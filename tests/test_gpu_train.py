@@ -1,0 +1,106 @@
+"""GPU tests of the training-step plumbing: the CUDA-graph replay of a whole step (GraphedTrainStep) must follow the
+eager step (forward, CE loss, backward, clip, fused AdamW) bit for bit when nothing random is left in the model, and
+keep drawing fresh DropPath / dropout masks when there is."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+import svit_b200
+from svit_b200 import ops
+from svit_b200.config import tiny_cfg
+from svit_b200.optim import construct_optimizer
+from tests.golden.recipe import synth_input
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _tiny(seed=0, stochastic=False):
+    cfg = tiny_cfg()
+    torch.manual_seed(seed)
+    m = svit_b200.SViT(cfg, compute_dtype=torch.bfloat16).to(DEV).train()
+    if not stochastic:
+        for mod in m.modules():
+            if isinstance(mod, svit_b200.DropPath):
+                mod.drop_prob = 0.0
+            if isinstance(mod, nn.Dropout):
+                mod.p = 0.0
+    return cfg, m
+
+
+def _eager_step(m, opt, clip, labels, max_norm):
+    for p in m.parameters():
+        p.grad = None
+    _, extra = m([clip])
+    loss = torch.nn.functional.cross_entropy(extra["logits"].float(), labels)
+    loss.backward()
+    opt.step(max_norm=max_norm)
+    return loss.detach()
+
+
+def test_graphed_train_step_matches_eager_steps():
+    """Same start, same clips: the replayed graph and the eager loop must follow the same trajectory.  The backward
+    uses fp32 atomics (split-K weight gradients, pooling-weight gradients), so two runs differ in the last bits and
+    Adam turns the sign of a noise-level gradient into a full +-lr move of that element: the comparison is therefore on
+    the loss values (2 %) and on the direction / size of the total parameter movement, not element by element."""
+    cfg, m_e = _tiny()
+    m_g = copy.deepcopy(m_e)
+    init = [p.detach().clone() for p in m_e.parameters()]
+    clips = [synth_input(f"train.clip{i}", (2, 3, 4, 32, 32), 7 + i).to(DEV).bfloat16() for i in range(3)]
+    labels = [torch.tensor([1, 3], device=DEV), torch.tensor([0, 9], device=DEV), torch.tensor([4, 4], device=DEV)]
+    opt_e, opt_g = construct_optimizer(m_e, cfg), construct_optimizer(m_g, cfg)
+    for o in (opt_e, opt_g):
+        for g in o.param_groups:
+            g["lr"] = 2e-3
+    warm = 2
+    step = svit_b200.GraphedTrainStep(m_g, opt_g, clips[0], labels[0], max_norm=1.0, warmup=warm)
+    # the constructor ran `warm` eager steps on (clips[0], labels[0]); do the same on the eager twin
+    for _ in range(warm):
+        _eager_step(m_e, opt_e, clips[0], labels[0], 1.0)
+    losses_e, losses_g = [], []
+    for i in range(6):
+        if i == 3:  # the learning-rate schedule keeps working between replays
+            for o in (opt_e, opt_g):
+                for g in o.param_groups:
+                    g["lr"] = 5e-4
+        losses_e.append(float(_eager_step(m_e, opt_e, clips[i % 3], labels[i % 3], 1.0)))
+        losses_g.append(float(step(clips[i % 3], labels[i % 3])))
+    assert losses_e == pytest.approx(losses_g, rel=2e-2), (losses_e, losses_g)
+    assert losses_e[3] < losses_e[0]  # clip 0 again after three more steps: the optimizer is learning
+    assert opt_e._step == opt_g._step == warm + 6
+    de = torch.cat([(p.detach() - q).flatten() for p, q in zip(m_e.parameters(), init)])
+    dg = torch.cat([(p.detach() - q).flatten() for p, q in zip(m_g.parameters(), init)])
+    assert de.norm() > 0 and abs(float(dg.norm() / de.norm()) - 1.0) < 0.05
+    assert float(torch.dot(de, dg) / (de.norm() * dg.norm())) > 0.9
+    # an eager forward after the replays must see the updated weights (weight caches are invalidated per replay)
+    m_g.eval()
+    with torch.no_grad():
+        _, ex = m_g([clips[0]])
+    got = float(torch.nn.functional.cross_entropy(ex["logits"].float(), labels[0]))
+    stale = copy.deepcopy(m_g)
+    for p, q in zip(stale.parameters(), init):
+        p.data.copy_(q)
+    with torch.no_grad():
+        _, ex0 = stale.eval()([clips[0]])
+    first = float(torch.nn.functional.cross_entropy(ex0["logits"].float(), labels[0]))
+    assert got < first  # trained weights, not the capture-time copies
+
+
+def test_graphed_train_step_draws_fresh_droppath_masks():
+    """DropPath / head dropout inside the graph use torch's graph-safe generator: replays on the same input give
+    different losses (fresh masks), as the eager loop does."""
+    cfg, m = _tiny(stochastic=True)
+    for mod in m.modules():
+        if isinstance(mod, svit_b200.DropPath):
+            mod.drop_prob = 0.5
+    opt = construct_optimizer(m, cfg)
+    for g in opt.param_groups:
+        g["lr"] = 0.0  # freeze the weights: only the masks change between replays
+        g["weight_decay"] = 0.0
+    clip = synth_input("train.clip0", (2, 3, 4, 32, 32), 7).to(DEV).bfloat16()
+    labels = torch.tensor([1, 3], device=DEV)
+    step = svit_b200.GraphedTrainStep(m, opt, clip, labels, max_norm=None, warmup=1)
+    vals = {round(float(step(clip, labels)), 6) for _ in range(8)}
+    assert len(vals) > 1
