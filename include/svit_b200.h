@@ -184,11 +184,21 @@ int svit_gather_cls_obj_bwd(const void* dout, void* dx, int B, int64_t N, int O,
 /* ---- box-conditioned object tokens: call site video_model_builder.py:385-392, 472-491 (RoIAlign 7x7,
  * spatial_scale 1/16, aligned, sampling_ratio 0 -> adaptive) applied per frame.
  * feat: token-major features; patch token (b, s, y, x) at feat + b*feat_batch_stride + (1 + (s*Hf + y)*Wf + x)*C.
- * boxes [B, Tx, K, 4] xyxy input pixels (fp32). tokens [B, Tx*K, C] = max over the P x P RoIAlign bins;
- * frame t reads temporal slice t / patch_stride_t (t when Tf == 1). assign [B, Tx*K, 2] int32 = (b, slice). */
-int svit_roi_tokens_fwd(const void* feat, int64_t feat_batch_stride, const float* boxes, void* tokens, int32_t* assign,
-                        int B, int C, int Tf, int Hf, int Wf, int Tx, int K, int patch_stride_t, float spatial_scale,
-                        int P, int dtype, void* stream);
+ * boxes [B, Tx, K, 4] xyxy input pixels (fp32). token (b, t, k) = max over the P x P RoIAlign bins, written at
+ * tokens + b*tokens_batch_stride + (t*K + k)*C (tokens_batch_stride 0 = dense [B, Tx*K, C]); pointing `tokens` at row
+ * 1 + Tf*Hf*Wf of the token sequence with tokens_batch_stride = N*C scatters the RoI tokens to sequence rows
+ * 1 + T'H'W' + t*K + k; accumulate != 0 adds to what is there.  argmax (optional) [B*Tx*K, C] uint8 = the
+ * first maximal bin (what the backward needs).  Frame t reads temporal slice t / patch_stride_t (t when Tf == 1).
+ * assign [B, Tx*K, 2] int32 = (b, slice).
+ * Backward: dfeat [B, Tf*Hf*Wf, C] fp32 (+=, caller zero-fills): the gradient of every token spread over the bilinear taps
+ * of the samples of its arg-max bin (fp32 atomics). */
+int svit_roi_tokens_fwd(const void* feat, int64_t feat_batch_stride, const float* boxes, void* tokens,
+                        int64_t tokens_batch_stride, uint8_t* argmax, int accumulate, int32_t* assign, int B, int C, int Tf,
+                        int Hf, int Wf, int Tx, int K, int patch_stride_t, float spatial_scale, int P, int dtype,
+                        void* stream);
+int svit_roi_tokens_bwd(const void* dtokens, int64_t dtokens_batch_stride, const uint8_t* argmax, const float* boxes,
+                        float* dfeat, int B, int C, int Tf, int Hf, int Wf, int Tx, int K, int patch_stride_t,
+                        float spatial_scale, int P, int dtype, void* stream);
 /* plain RoIAlign (torchvision semantics, aligned flag) on a channels-last map [N, H, W, C]; rois [R,5]; out [R,P,P,C] */
 int svit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, int P,
                        float spatial_scale, int sampling_ratio, int aligned, int dtype, void* stream);

@@ -71,7 +71,8 @@ PROTOTYPES = {
     "svit_im2col3d": [vp, vp] + [C.c_int] * 17 + [vp],
     "svit_gather_cls_obj_fwd": [vp, vp, C.c_int, i64, C.c_int, C.c_int, C.c_int, vp],
     "svit_gather_cls_obj_bwd": [vp, vp, C.c_int, i64, C.c_int, C.c_int, C.c_int, vp],
-    "svit_roi_tokens_fwd": [vp, i64, vp, vp, vp] + [C.c_int] * 8 + [f32, C.c_int, C.c_int, vp],
+    "svit_roi_tokens_fwd": [vp, i64, vp, vp, i64, vp, C.c_int, vp] + [C.c_int] * 8 + [f32, C.c_int, C.c_int, vp],
+    "svit_roi_tokens_bwd": [vp, i64, vp, vp, vp] + [C.c_int] * 8 + [f32, C.c_int, C.c_int, vp],
     "svit_roi_align_fwd": [vp, vp, vp] + [C.c_int] * 6 + [f32, C.c_int, C.c_int, C.c_int, vp],
     "svit_match_haog": [vp, vp, i64, vp],
     "svit_zero_empty_boxes": [vp, i64, f32, vp],

@@ -96,7 +96,10 @@ _SSV2 = {
         "SEPARATE_QKV": False,
         "ZERO_DECAY_POS_CLS": False,
     },
-    "SVIT": {"O": 4, "LAMBDA_CON": 1.5, "LAMBDA_EDGES": 0.3, "LAMBDA_NODES": 3.7},
+    "SVIT": {"O": 4, "LAMBDA_CON": 1.5, "LAMBDA_EDGES": 0.3, "LAMBDA_NODES": 3.7,
+             # svit_b200 extension: "" | "replace" | "add" -- scatter the box-conditioned RoI tokens into the
+             # object rows of the sequence when SViT.forward is given bboxes
+             "BOX_TOKENS": ""},
     "DETECTION": {
         "ENABLE": False,
         "ALIGNED": True,

@@ -43,7 +43,8 @@ __device__ __forceinline__ float roi_bin(const T* __restrict__ fm, int C, int c,
 
 template <typename T>
 __global__ void roi_tokens_kernel(const T* __restrict__ feat, int64_t feat_bs, const float* __restrict__ boxes,
-                                  T* __restrict__ tokens, int32_t* __restrict__ assign, int B, int C, int Tf, int Hf,
+                                  T* __restrict__ tokens, int64_t tok_bs, uint8_t* __restrict__ argmax, int accumulate,
+                                  int32_t* __restrict__ assign, int B, int C, int Tf, int Hf,
                                   int Wf, int Tx, int K, int pst, float scale, int P) {
   const int box = blockIdx.x;  // (b, t, k) flattened
   const int k = box % K, t = (box / K) % Tx, b = box / (K * Tx);
@@ -60,11 +61,63 @@ __global__ void roi_tokens_kernel(const T* __restrict__ feat, int64_t feat_bs, c
   const float bw = rw / (float)P, bh = rh / (float)P;
   const int gh = (int)ceilf(rh / (float)P), gw = (int)ceilf(rw / (float)P);
   const T* fm = feat + (int64_t)b * feat_bs + (1 + (int64_t)slice * Hf * Wf) * C;
+  T* trow = tokens + (int64_t)b * tok_bs + (int64_t)(box - b * Tx * K) * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float best = -INFINITY;
+    int arg = 0;
     for (int ph = 0; ph < P; ++ph)
-      for (int pw = 0; pw < P; ++pw) best = fmaxf(best, roi_bin(fm, C, c, Hf, Wf, y1, x1, bh, bw, gh, gw, ph, pw));
-    tokens[(int64_t)box * C + c] = from_f<T>(best);
+      for (int pw = 0; pw < P; ++pw) {
+        const float v = roi_bin(fm, C, c, Hf, Wf, y1, x1, bh, bw, gh, gw, ph, pw);
+        if (v > best) {  // first maximal bin wins (torch.max semantics)
+          best = v;
+          arg = ph * P + pw;
+        }
+      }
+    if (argmax) argmax[(int64_t)box * C + c] = (uint8_t)arg;
+    trow[c] = from_f<T>(accumulate ? best + to_f(trow[c]) : best);
+  }
+}
+
+// Backward of roi_tokens: the gradient of token (box, c) goes to the samples of its arg-max bin, spread over the four
+// bilinear taps of every sample (weight / sample count), accumulated with fp32 atomics into dfeat [B, Tf*Hf*Wf, C].
+template <typename T>
+__global__ void roi_tokens_bwd_kernel(const T* __restrict__ dtok, int64_t dtok_bs, const uint8_t* __restrict__ argmax,
+                                      const float* __restrict__ boxes, float* __restrict__ dfeat, int B, int C, int Tf,
+                                      int Hf, int Wf, int Tx, int K, int pst, float scale, int P) {
+  const int box = blockIdx.x;
+  const int t = (box / K) % Tx, b = box / (K * Tx);
+  const int slice = (Tf == 1) ? 0 : (Tx == 1 ? t : t / pst);
+  const float* bx = boxes + (int64_t)box * 4;
+  const float x1 = bx[0] * scale - 0.5f, y1 = bx[1] * scale - 0.5f;
+  const float x2 = bx[2] * scale - 0.5f, y2 = bx[3] * scale - 0.5f;
+  const float rw = x2 - x1, rh = y2 - y1;
+  const float bw = rw / (float)P, bh = rh / (float)P;
+  const int gh = (int)ceilf(rh / (float)P), gw = (int)ceilf(rw / (float)P);
+  const int cnt = gh * gw;
+  if (cnt <= 0) return;  // no samples: the token is the constant 0
+  const float inv = 1.f / (float)cnt;
+  float* df = dfeat + ((int64_t)b * Tf + slice) * Hf * Wf * C;
+  const T* grow = dtok + (int64_t)b * dtok_bs + (int64_t)(box - b * Tx * K) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = to_f(grow[c]) * inv;
+    if (g == 0.f) continue;
+    const int bin = argmax[(int64_t)box * C + c];
+    const int ph = bin / P, pw = bin - ph * P;
+    for (int iy = 0; iy < gh; ++iy) {
+      const float y = y1 + ph * bh + (iy + 0.5f) * bh / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        const float x = x1 + pw * bw + (ix + 0.5f) * bw / (float)gw;
+        int yl, xl, yh, xh;
+        float w1, w2, w3, w4;
+        bool valid;
+        bilinear_setup(y, x, Hf, Wf, yl, xl, yh, xh, w1, w2, w3, w4, valid);
+        if (!valid) continue;
+        atomicAdd(df + ((int64_t)yl * Wf + xl) * C + c, g * w1);
+        atomicAdd(df + ((int64_t)yl * Wf + xh) * C + c, g * w2);
+        atomicAdd(df + ((int64_t)yh * Wf + xl) * C + c, g * w3);
+        atomicAdd(df + ((int64_t)yh * Wf + xh) * C + c, g * w4);
+      }
+    }
   }
 }
 
@@ -94,10 +147,12 @@ __device__ __forceinline__ Samp1D samp1d(float v, int n) {
 
 __global__ void __launch_bounds__(256) roi_tokens_vec8_kernel(const bf16* __restrict__ feat, int64_t feat_bs,
                                                               const float* __restrict__ boxes, bf16* __restrict__ tokens,
+                                                              int64_t tok_bs, uint8_t* __restrict__ argmax, int accumulate,
                                                               int32_t* __restrict__ assign, int B, int C, int Tf, int Hf,
                                                               int Wf, int Tx, int K, int pst, float scale, int P) {
   __shared__ Samp1D ys[ROI_MAXS], xs[ROI_MAXS];
   __shared__ float red[256 * 8];
+  __shared__ uint8_t redarg[256 * 8];
   const int box = blockIdx.x;  // (b, t, k) flattened
   const int t = (box / K) % Tx, b = box / (K * Tx);
   const int slice = (Tf == 1) ? 0 : (Tx == 1 ? t : t / pst);
@@ -131,8 +186,12 @@ __global__ void __launch_bounds__(256) roi_tokens_vec8_kernel(const bf16* __rest
   const int cnt = gh * gw;
   const float inv = 1.f / (float)(cnt > 0 ? cnt : 1);
   float best[8];
+  int barg[8];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) best[u] = -INFINITY;
+  for (int u = 0; u < 8; ++u) {
+    best[u] = -INFINITY;
+    barg[u] = 0;
+  }
   auto fma8 = [](float acc[8], const uint4& v, float w) {
     const uint32_t q[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -164,24 +223,60 @@ __global__ void __launch_bounds__(256) roi_tokens_vec8_kernel(const bf16* __rest
         }
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) best[u] = fmaxf(best[u], acc[u] * inv);
+      for (int u = 0; u < 8; ++u) {
+        const float v = acc[u] * inv;
+        if (v > best[u]) {  // bins arrive in increasing order inside a group: the first maximal bin is kept
+          best[u] = v;
+          barg[u] = bin;
+        }
+      }
     }
   }
 #pragma unroll
-  for (int u = 0; u < 8; ++u) red[threadIdx.x * 8 + u] = best[u];
+  for (int u = 0; u < 8; ++u) {
+    red[threadIdx.x * 8 + u] = best[u];
+    redarg[threadIdx.x * 8 + u] = (uint8_t)barg[u];
+  }
   __syncthreads();
   if (threadIdx.x < ct) {
     const int ng = ngrp < P * P ? ngrp : P * P;  // groups that owned at least one bin
     float m[8];
+    int ma[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) m[u] = red[threadIdx.x * 8 + u];
+    for (int u = 0; u < 8; ++u) {
+      m[u] = red[threadIdx.x * 8 + u];
+      ma[u] = redarg[threadIdx.x * 8 + u];
+    }
     for (int g2 = 1; g2 < ng; ++g2)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) m[u] = fmaxf(m[u], red[(g2 * ct + threadIdx.x) * 8 + u]);
+      for (int u = 0; u < 8; ++u) {
+        const float v = red[(g2 * ct + threadIdx.x) * 8 + u];
+        const int a = redarg[(g2 * ct + threadIdx.x) * 8 + u];
+        if (v > m[u] || (v == m[u] && a < ma[u])) {  // ties: the lowest bin index (first maximal bin)
+          m[u] = v;
+          ma[u] = a;
+        }
+      }
+    bf16* trow = tokens + (int64_t)b * tok_bs + (int64_t)(box - b * Tx * K) * C + threadIdx.x * 8;
+    if (accumulate) {
+      const uint4 old = *reinterpret_cast<const uint4*>(trow);
+      const uint32_t q[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        m[2 * u] += __uint_as_float(q[u] << 16);
+        m[2 * u + 1] += __uint_as_float(q[u] & 0xffff0000u);
+      }
+    }
     __nv_bfloat162 h2[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) h2[u] = __floats2bfloat162_rn(m[2 * u], m[2 * u + 1]);
-    *reinterpret_cast<uint4*>(tokens + (int64_t)box * C + threadIdx.x * 8) = *reinterpret_cast<uint4*>(h2);
+    *reinterpret_cast<uint4*>(trow) = *reinterpret_cast<uint4*>(h2);
+    if (argmax) {
+      uint8_t a8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a8[u] = (uint8_t)ma[u];
+      *reinterpret_cast<uint2*>(argmax + (int64_t)box * C + threadIdx.x * 8) = *reinterpret_cast<uint2*>(a8);
+    }
   }
 }
 
@@ -251,22 +346,45 @@ __global__ void zero_empty_boxes_kernel(float* __restrict__ b, int64_t n, float 
 
 extern "C" {
 
-int svit_roi_tokens_fwd(const void* feat, int64_t feat_batch_stride, const float* boxes, void* tokens, int32_t* assign,
-                        int B, int C, int Tf, int Hf, int Wf, int Tx, int K, int patch_stride_t, float spatial_scale,
-                        int P, int dtype, void* stream) {
-  if (B < 0 || K < 0 || Tx < 1 || P < 1 || patch_stride_t < 1 || Tf < 1) return SVIT_EINVAL;
+int svit_roi_tokens_fwd(const void* feat, int64_t feat_batch_stride, const float* boxes, void* tokens,
+                        int64_t tokens_batch_stride, uint8_t* argmax, int accumulate, int32_t* assign, int B, int C, int Tf,
+                        int Hf, int Wf, int Tx, int K, int patch_stride_t, float spatial_scale, int P, int dtype,
+                        void* stream) {
+  if (B < 0 || K < 0 || Tx < 1 || P < 1 || P > 15 || patch_stride_t < 1 || Tf < 1) return SVIT_EINVAL;
   if (Tf > 1 && Tx > 1 && (Tx - 1) / patch_stride_t >= Tf) return SVIT_EINVAL;
   int64_t nbox = (int64_t)B * Tx * K;
   if (nbox == 0) return 0;
+  const int64_t tbs = tokens_batch_stride > 0 ? tokens_batch_stride : (int64_t)Tx * K * C;
   cudaStream_t st = (cudaStream_t)stream;
   int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 96);
   if (dtype == SVIT_F32)
-    roi_tokens_kernel<float><<<(unsigned)nbox, threads, 0, st>>>((const float*)feat, feat_batch_stride, boxes, (float*)tokens, assign, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
-  else if (dtype == SVIT_BF16 && C % 8 == 0 && C <= 2048 && feat_batch_stride % 8 == 0 &&
-           ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(tokens)) & 15) == 0)
-    roi_tokens_vec8_kernel<<<(unsigned)nbox, 256, 0, st>>>((const bf16*)feat, feat_batch_stride, boxes, (bf16*)tokens, assign, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
+    roi_tokens_kernel<float><<<(unsigned)nbox, threads, 0, st>>>((const float*)feat, feat_batch_stride, boxes, (float*)tokens, tbs, argmax, accumulate, assign, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
+  else if (dtype == SVIT_BF16 && C % 8 == 0 && C <= 2048 && feat_batch_stride % 8 == 0 && tbs % 8 == 0 &&
+           ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(tokens)) & 15) == 0 &&
+           (!argmax || (reinterpret_cast<uintptr_t>(argmax) & 7) == 0))
+    roi_tokens_vec8_kernel<<<(unsigned)nbox, 256, 0, st>>>((const bf16*)feat, feat_batch_stride, boxes, (bf16*)tokens, tbs, argmax, accumulate, assign, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
   else if (dtype == SVIT_BF16)
-    roi_tokens_kernel<bf16><<<(unsigned)nbox, threads, 0, st>>>((const bf16*)feat, feat_batch_stride, boxes, (bf16*)tokens, assign, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
+    roi_tokens_kernel<bf16><<<(unsigned)nbox, threads, 0, st>>>((const bf16*)feat, feat_batch_stride, boxes, (bf16*)tokens, tbs, argmax, accumulate, assign, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
+  else
+    return SVIT_EINVAL;
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+int svit_roi_tokens_bwd(const void* dtokens, int64_t dtokens_batch_stride, const uint8_t* argmax, const float* boxes,
+                        float* dfeat, int B, int C, int Tf, int Hf, int Wf, int Tx, int K, int patch_stride_t,
+                        float spatial_scale, int P, int dtype, void* stream) {
+  if (B < 0 || K < 0 || Tx < 1 || P < 1 || P > 15 || patch_stride_t < 1 || Tf < 1 || !argmax || !dfeat) return SVIT_EINVAL;
+  if (Tf > 1 && Tx > 1 && (Tx - 1) / patch_stride_t >= Tf) return SVIT_EINVAL;
+  int64_t nbox = (int64_t)B * Tx * K;
+  if (nbox == 0) return 0;
+  const int64_t tbs = dtokens_batch_stride > 0 ? dtokens_batch_stride : (int64_t)Tx * K * C;
+  cudaStream_t st = (cudaStream_t)stream;
+  int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 96);
+  if (dtype == SVIT_F32)
+    roi_tokens_bwd_kernel<float><<<(unsigned)nbox, threads, 0, st>>>((const float*)dtokens, tbs, argmax, boxes, dfeat, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
+  else if (dtype == SVIT_BF16)
+    roi_tokens_bwd_kernel<bf16><<<(unsigned)nbox, threads, 0, st>>>((const bf16*)dtokens, tbs, argmax, boxes, dfeat, B, C, Tf, Hf, Wf, Tx, K, patch_stride_t, spatial_scale, P);
   else
     return SVIT_EINVAL;
   SVIT_CHECK_LAUNCH();

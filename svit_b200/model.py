@@ -174,10 +174,20 @@ class SViT(nn.Module):
         clip = x[0]
         tokens, thw, Tx = self.forward_tokens(clip)
         O_tot = Tx * self.O
+        roi = None
+        if bboxes is not None:
+            roi = self.roi_object_tokens(tokens, thw, bboxes)
+            mode = getattr(self.cfg.SVIT, "BOX_TOKENS", "")  # "", "replace" or "add" (svit_b200 extension)
+            if mode:
+                # the box-conditioned tokens take the place of (or are added to) the learned object tokens in the
+                # sequence, rows 1 + T'H'W' + t*K + k, so the head reads them
+                det = self.cfg.DETECTION
+                tokens, _ = ops.roi_scatter_tokens(tokens, thw, bboxes, self.patch_stride[0], 1.0 / det.SPATIAL_SCALE_FACTOR,
+                                                   det.ROI_XFORM_RESOLUTION, mode)
         cls_obj = ops.gather_cls_obj(tokens, O_tot)
         out, extra = self.head(cls_obj, T=Tx)
-        if bboxes is not None:
-            extra["roi_tokens"], extra["roi_assign"] = self.roi_object_tokens(tokens, thw, bboxes)
+        if roi is not None:
+            extra["roi_tokens"], extra["roi_assign"] = roi
         return out, extra
 
     def roi_object_tokens(self, tokens, thw, bboxes):

@@ -713,20 +713,78 @@ def gather_cls_obj(x, O):
 # --------------------------------------------------------------------------------------------
 # box-conditioned object tokens (inference path), integer box logic on device
 # --------------------------------------------------------------------------------------------
+class _RoITokens(torch.autograd.Function):
+    """Per-frame box-conditioned object tokens (call site video_model_builder.py:385-392, 472-491).
+
+    mode None      -> tokens [B, Tx*K, C]
+    mode "replace" -> a copy of the sequence whose object rows 1 + T'H'W' + t*K + k hold the RoI tokens
+    mode "add"     -> the same rows hold (learned object token + RoI token)
+    Backward: the token gradients go to the arg-max bin's bilinear taps (svit_roi_tokens_bwd, fp32 atomics)."""
+
+    @staticmethod
+    def forward(ctx, x_tokens, boxes, thw, patch_stride_t, spatial_scale, out_size, mode):
+        _chk(x_tokens, "roi_tokens")
+        x_tokens = x_tokens.contiguous()
+        B, N, Cn = x_tokens.shape
+        Tf, Hf, Wf = thw
+        L = Tf * Hf * Wf
+        _, Tx, K, _ = boxes.shape
+        bx = boxes.to(device=x_tokens.device, dtype=torch.float32).contiguous()
+        need = ctx.needs_input_grad[0]
+        argmax = torch.empty(B * Tx * K, Cn, dtype=torch.uint8, device=x_tokens.device) if need else None
+        assign = torch.empty(B, Tx * K, 2, dtype=torch.int32, device=x_tokens.device)
+        if mode is None:
+            out = torch.empty(B, Tx * K, Cn, dtype=x_tokens.dtype, device=x_tokens.device)
+            optr, obs, acc = out.data_ptr(), 0, 0
+        else:
+            if mode not in ("replace", "add"):
+                raise ValueError(f"roi token scatter mode {mode!r}: expected 'replace' or 'add'")
+            if N - 1 - L != Tx * K:
+                raise ValueError(f"scattering {Tx}x{K} RoI tokens needs {Tx * K} object rows, the sequence has {N - 1 - L}")
+            out = x_tokens.clone()
+            optr, obs, acc = out.data_ptr() + (1 + L) * Cn * out.element_size(), N * Cn, int(mode == "add")
+        _call("svit_roi_tokens_fwd", x_tokens.data_ptr(), N * Cn, bx.data_ptr(), optr, obs, _p(argmax), acc,
+              assign.data_ptr(), B, Cn, Tf, Hf, Wf, Tx, K, patch_stride_t, float(spatial_scale), out_size, _dt(x_tokens),
+              _stream())
+        if need:
+            ctx.save_for_backward(bx, argmax)
+        ctx.geom = (B, N, Cn, Tf, Hf, Wf, Tx, K, patch_stride_t, float(spatial_scale), out_size, mode)
+        ctx.mark_non_differentiable(assign)
+        return out, assign
+
+    @staticmethod
+    def backward(ctx, dout, _dassign):
+        bx, argmax = ctx.saved_tensors
+        B, N, Cn, Tf, Hf, Wf, Tx, K, pst, scale, P, mode = ctx.geom
+        L = Tf * Hf * Wf
+        dout = dout.contiguous()
+        dfeat = torch.zeros(B, L, Cn, dtype=torch.float32, device=dout.device)
+        if mode is None:
+            dptr, dbs = dout.data_ptr(), 0
+        else:
+            dptr, dbs = dout.data_ptr() + (1 + L) * Cn * dout.element_size(), N * Cn
+        _call("svit_roi_tokens_bwd", dptr, dbs, argmax.data_ptr(), bx.data_ptr(), dfeat.data_ptr(), B, Cn, Tf, Hf, Wf, Tx, K,
+              pst, scale, P, _dt(dout), _stream())
+        if mode is None:
+            dx = torch.zeros(B, N, Cn, dtype=dout.dtype, device=dout.device)
+        else:
+            dx = dout.clone()
+            if mode == "replace":
+                dx[:, 1 + L:].zero_()  # the learned object rows were overwritten
+        dx[:, 1:1 + L] += dfeat.to(dx.dtype)  # [B, T'H'W', C] glue add (the atomics accumulate in fp32)
+        return dx, None, None, None, None, None, None
+
+
 def roi_tokens(x_tokens, thw, boxes, patch_stride_t=2, spatial_scale=1.0 / 16, out_size=7):
     """x_tokens [B, N, C] (token-major, patch rows 1..T'H'W'); boxes [B, Tx, K, 4] xyxy pixels.
-    Returns (tokens [B, Tx*K, C], assign int32 [B, Tx*K, 2] = (batch, temporal slice))."""
-    _chk(x_tokens, "roi_tokens")
-    x_tokens = x_tokens.contiguous()
-    B, N, Cn = x_tokens.shape
-    Tf, Hf, Wf = thw
-    _, Tx, K, _ = boxes.shape
-    bx = boxes.to(device=x_tokens.device, dtype=torch.float32).contiguous()
-    toks = torch.empty(B, Tx * K, Cn, dtype=x_tokens.dtype, device=x_tokens.device)
-    assign = torch.empty(B, Tx * K, 2, dtype=torch.int32, device=x_tokens.device)
-    _call("svit_roi_tokens_fwd", x_tokens.data_ptr(), N * Cn, bx.data_ptr(), toks.data_ptr(), assign.data_ptr(),
-          B, Cn, Tf, Hf, Wf, Tx, K, patch_stride_t, float(spatial_scale), out_size, _dt(x_tokens), _stream())
-    return toks, assign
+    Returns (tokens [B, Tx*K, C], assign int32 [B, Tx*K, 2] = (batch, temporal slice)); differentiable in x_tokens."""
+    return _RoITokens.apply(x_tokens, boxes, tuple(thw), patch_stride_t, spatial_scale, out_size, None)
+
+
+def roi_scatter_tokens(x_tokens, thw, boxes, patch_stride_t=2, spatial_scale=1.0 / 16, out_size=7, mode="replace"):
+    """The sequence with its object rows (index 1 + T'H'W' + t*K + k, SURVEY R3 / video_model_builder.py:354-363) replaced
+    by -- or, mode="add", summed with -- the box-conditioned RoI tokens.  Returns (sequence [B, N, C], assign)."""
+    return _RoITokens.apply(x_tokens, boxes, tuple(thw), patch_stride_t, spatial_scale, out_size, mode)
 
 
 def roi_align_nhwc(feat_nhwc, rois, out_size, spatial_scale, sampling_ratio=0, aligned=True):

@@ -568,3 +568,92 @@ def test_fused_adamw_invalidates_weight_caches():
     ref = x.float() @ w.detach().float().bfloat16().float().t()
     assert max_rel_err(cpu(y1), cpu(ref)) < 1e-2
     assert max_rel_err(cpu(y0), cpu(ref)) > 1e-1  # the step really moved the weights
+
+
+def _roi_reference_tokens(feat, boxes, pst, scale, P=7):
+    """Differentiable CPU reference of roi_object_tokens: torchvision roi_align per (b, t) and torch.max over the bins
+    flattened row-major (gradient to the FIRST maximal bin, the kernel's rule)."""
+    from torchvision.ops import roi_align as tv_roi
+    B, C, Tp, H, W = feat.shape
+    _, Tx, K, _ = boxes.shape
+    rows = []
+    for b in range(B):
+        for t in range(Tx):
+            s = 0 if Tp == 1 else (t if Tx == 1 else t // pst)
+            rois = torch.cat([torch.zeros(K, 1), boxes[b, t]], dim=1)
+            r = tv_roi(feat[b:b + 1, :, s], rois, output_size=P, spatial_scale=scale, sampling_ratio=0, aligned=True)
+            rows.append(r.flatten(-2).max(dim=-1).values)
+    return torch.stack(rows).reshape(B, Tx * K, C)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_roi_tokens_backward_vs_torchvision(dtype):
+    """SURVEY R3 backward (VERDICT r1 missing #1): d tokens / d features through the arg-max bin's bilinear taps."""
+    gen = torch.Generator().manual_seed(5)
+    for (B, C, Tp, Hf, Tx, K, scale) in ((2, 96, 2, 7, 4, 4, 1 / 16), (1, 192, 4, 14, 8, 3, 1 / 8), (1, 96, 1, 7, 1, 2, 1 / 16)):
+        feat = torch.randn(B, C, Tp, Hf, Hf, generator=gen).to(dtype).float()
+        size = Hf / scale
+        boxes = torch.rand(B, Tx, K, 4, generator=gen) * size * 0.7
+        boxes[..., 2:] = boxes[..., :2] + 8 + torch.rand(B, Tx, K, 2, generator=gen) * size * 0.5
+        gy = torch.randn(B, Tx * K, C, generator=gen).to(dtype).float()
+        fr = feat.clone().requires_grad_(True)
+        want = _roi_reference_tokens(fr, boxes, 2, scale)
+        want.backward(gy)
+        L = Tp * Hf * Hf
+        seq = torch.zeros(B, 1 + L + 5, C)
+        seq[:, 1:1 + L] = feat.permute(0, 2, 3, 4, 1).reshape(B, L, C)
+        x = seq.to(DEV, dtype).requires_grad_(True)
+        got, _ = ops.roi_tokens(x, [Tp, Hf, Hf], boxes, 2, scale, 7)
+        assert max_rel_err(cpu(got), want.detach()) < (1e-5 if dtype == torch.float32 else 6e-3)
+        got.backward(gy.to(DEV, dtype))
+        dx = cpu(x.grad)
+        assert dx[:, 0].abs().max() == 0 and dx[:, 1 + L:].abs().max() == 0
+        dwant = fr.grad.permute(0, 2, 3, 4, 1).reshape(B, L, C)
+        # bf16: an arg-max decided on bf16-rounded bin values can differ from the fp32 reference's on near ties
+        tol = 1e-5 if dtype == torch.float32 else 3e-2
+        err = max_rel_err(dx[:, 1:1 + L], dwant)
+        if dtype == torch.float32:
+            assert err < tol, err
+        else:
+            bad = ((dx[:, 1:1 + L] - dwant).abs() > tol * dwant.abs().max()).float().mean().item()
+            assert bad < 5e-3, (err, bad)
+
+
+def test_roi_scatter_into_sequence_and_model_option():
+    """RoI tokens land at sequence rows 1 + T'H'W' + t*K + k (bit-exact index rule), 'add' keeps the learned object token,
+    and SViT.forward(bboxes=...) with cfg.SVIT.BOX_TOKENS routes them into the head with gradients to the backbone."""
+    gen = torch.Generator().manual_seed(9)
+    B, C, Tp, Hf, Tx, K = 2, 96, 2, 7, 4, 4
+    L = Tp * Hf * Hf
+    seq = torch.randn(B, 1 + L + Tx * K, C, generator=gen).to(DEV)
+    boxes = torch.rand(B, Tx, K, 4, generator=gen) * 60
+    boxes[..., 2:] = boxes[..., :2] + 10 + torch.rand(B, Tx, K, 2, generator=gen) * 40
+    toks, _ = ops.roi_tokens(seq, [Tp, Hf, Hf], boxes, 2, 1 / 16, 7)
+    rep, _ = ops.roi_scatter_tokens(seq, [Tp, Hf, Hf], boxes, 2, 1 / 16, 7, "replace")
+    add, _ = ops.roi_scatter_tokens(seq, [Tp, Hf, Hf], boxes, 2, 1 / 16, 7, "add")
+    assert torch.equal(rep[:, :1 + L], seq[:, :1 + L]) and torch.equal(add[:, :1 + L], seq[:, :1 + L])
+    for t in range(Tx):
+        for k in range(K):
+            row = 1 + L + t * K + k
+            assert torch.equal(rep[:, row], toks[:, t * K + k])
+    assert torch.allclose(add[:, 1 + L:], seq[:, 1 + L:] + toks, rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        ops.roi_scatter_tokens(seq[:, :-1], [Tp, Hf, Hf], boxes, 2, 1 / 16, 7, "replace")
+    # model option
+    cfg = tiny_cfg()
+    cfg.SVIT.BOX_TOKENS = "add"
+    ops.set_impl(gemm=ops.IMPL_SIMT, attn=ops.IMPL_SIMT)
+    try:
+        m = svit_b200.SViT(cfg, compute_dtype=torch.float32).to(DEV).eval()
+        clip = synth_input("tiny.clip", (2, 3, 4, 32, 32), 5).to(DEV)
+        bx = torch.tensor([[4.0, 4.0, 20.0, 24.0], [0.0, 0.0, 32.0, 32.0], [8.0, 2.0, 30.0, 12.0], [1.0, 16.0, 14.0, 31.0]]).repeat(2, 4, 1, 1)
+        _, e0 = m([clip])
+        _, e1 = m([clip], bboxes=bx)
+        assert e1["obj_desc"].shape == e0["obj_desc"].shape
+        assert torch.allclose(e1["obj_desc"].reshape(2, 16, -1), e0["obj_desc"].reshape(2, 16, -1) + e1["roi_tokens"].float(),
+                              rtol=1e-5, atol=1e-5)
+        m.zero_grad()
+        e1["obj_desc"].square().sum().backward()
+        assert m.patch_embed.proj.weight.grad is not None and m.patch_embed.proj.weight.grad.abs().max() > 0
+    finally:
+        ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
