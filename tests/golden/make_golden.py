@@ -224,6 +224,40 @@ def model_cases():
     save("svit_full.pt", res)
 
 
+# ---------------------------------------------------------------- training-mode parity with DropPath ON
+def droppath_case():
+    """Tiny SViT in train() with every DropPath at p = 0.5 and head dropout off.  The reference draws, in block order,
+    two torch.rand((B, 1, 1)) masks per block with a DropPath (attention branch attention.py:565, MLP branch :570) from
+    the global CPU generator: the test re-draws them with the same seed and injects them into the B200 modules."""
+    tc = tiny_cfg()
+    B = 4
+    clip = synth_input("tiny.clip.dp", (B, 3, 4, 32, 32), 15)
+    m = ns.builder.SViT(tc.clone())
+    load_state(m, 300, w_std=0.06)
+    m.train()
+    n_dp = 0
+    for mod in m.modules():
+        if isinstance(mod, ns.common.DropPath):
+            mod.drop_prob = 0.5
+            n_dp += 1
+        if isinstance(mod, nn.Dropout):
+            mod.p = 0.0
+    torch.manual_seed(777)
+    logits, extra = m([clip])
+    tgt = torch.arange(B) % logits.shape[1]
+    loss = torch.nn.functional.cross_entropy(logits, tgt) + 0.1 * extra["pred_bboxes"].square().mean()
+    loss.backward()
+    torch.manual_seed(777)
+    masks = [torch.rand((B, 1, 1)) for _ in range(2 * n_dp)]  # each DropPath module is applied twice per forward
+    keep = ["cls_token", "blocks.0.attn.qkv.weight", "blocks.1.attn.pool_q.weight", "blocks.1.mlp.fc1.bias",
+            "blocks.2.attn.rel_pos_h", "blocks.3.norm2.weight", "patch_embed.proj.bias", "head.projection.weight"]
+    named = dict(m.named_parameters())
+    save("svit_tiny_droppath.pt", dict(seed=300, w_std=0.06, rng_seed=777, drop_prob=0.5, n_droppath_modules=n_dp,
+                                       rand=torch.stack(masks).reshape(2 * n_dp, B), logits=logits.detach(), loss=loss.detach(),
+                                       grad_norms={k: p.grad.norm().double() for k, p in named.items()},
+                                       grads={k: named[k].grad.clone() for k in keep}))
+
+
 # ---------------------------------------------------------------- R4 integer box logic
 def box_cases():
     rng = np.random.RandomState(1234)
@@ -298,5 +332,6 @@ if __name__ == "__main__":
     msa_cases()
     block_cases()
     model_cases()
+    droppath_case()
     box_cases()
     loss_cases()

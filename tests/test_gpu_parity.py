@@ -204,7 +204,9 @@ def test_msa_bf16_golden_forward(golden):
         with torch.no_grad():
             y, qs = m(c["x"].to(DEV, torch.bfloat16), c["thw"])
         assert list(qs) == c["q_shape"]
-        assert max_rel_err(cpu(y), c["y"]) < 3e-2, i
+        err = max_rel_err(cpu(y), c["y"])
+        print(f"msa golden case {i}: bf16 max-rel-err {err:.2e}")
+        assert err < 2e-2, i  # north_star bf16 tolerance
 
 
 def _make_block(c):
@@ -237,7 +239,9 @@ def test_block_bf16_golden_forward(golden):
         m = _make_block(c)
         with torch.no_grad():
             y, _ = m(c["x"].to(DEV, torch.bfloat16), c["input_size"])
-        assert max_rel_err(cpu(y), c["y"]) < 3e-2, i
+        err = max_rel_err(cpu(y), c["y"])
+        print(f"block golden case {i}: bf16 max-rel-err {err:.2e}")
+        assert err < 2e-2, i  # north_star bf16 tolerance
 
 
 # ------------------------------------------------------------------------------------------------ models
@@ -657,3 +661,186 @@ def test_roi_scatter_into_sequence_and_model_option():
         assert m.patch_embed.proj.weight.grad is not None and m.patch_embed.proj.weight.grad.abs().max() > 0
     finally:
         ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+
+
+# ------------------------------------------------------------------------------------------------ round-2 parity holes
+def _norm_rel(got, want):
+    """||got - want|| / ||want||: the gradient metric for bf16 (element-wise max ratios are dominated by near-zero entries)."""
+    return float((got.double() - want.double()).norm() / want.double().norm().clamp_min(1e-30))
+
+
+def test_svit_tiny_bf16_training_gradients(golden):
+    """the bf16 training path (tcgen05 GEMMs, attention forward / backward, vectorised pooling backward)
+    against the gradients of the UNMODIFIED reference (fp32, tests/golden/svit_tiny.pt).  Stated tolerance: 3e-2 on the
+    loss, on every parameter's gradient norm and on ||g - g_ref|| / ||g_ref|| of the stored gradients (5e-2 for the rel-pos
+    tables)."""
+    g = golden("svit_tiny.pt")["video"]
+    cfg = tiny_cfg()
+    m = _model(cfg, g, torch.bfloat16)
+    m.train()
+    for mod in m.modules():
+        if isinstance(mod, svit_b200.DropPath):
+            mod.drop_prob = 0.0
+        if isinstance(mod, nn.Dropout):
+            mod.p = 0.0
+    clip = synth_input("tiny.clip", (2, 3, 4, 32, 32), 5).to(DEV)
+    logits, extra = m([clip])
+    assert max_rel_err(cpu(logits), g["train_logits"]) < 2e-2
+    tgt = (torch.arange(2) % logits.shape[1]).to(DEV)
+    loss = torch.nn.functional.cross_entropy(logits.float(), tgt) + 0.1 * extra["pred_bboxes"].float().square().mean() \
+        + 0.1 * extra["pred_contact_state"].float().square().mean()
+    assert abs(loss.item() - g["loss"].item()) < 3e-2 * abs(g["loss"].item())
+    loss.backward()
+    named = dict(m.named_parameters())
+    worst_norm, worst = 0.0, 0.0
+    total = sum(float(n) ** 2 for n in g["grad_norms"].values()) ** 0.5
+    for k, n in g["grad_norms"].items():
+        if n.item() < 1e-3 * total:  # gradients at noise level relative to the model's total: covered by the total below
+            continue
+        e = abs(named[k].grad.double().norm().item() - n.item()) / n.item()
+        worst_norm = max(worst_norm, e)
+        assert e < 3e-2, (k, e)
+    got_total = sum(float(p.grad.double().norm()) ** 2 for p in named.values()) ** 0.5
+    assert abs(got_total - total) < 3e-2 * total
+    errs = {}
+    for k, w in g["grads"].items():
+        if w.norm() < 1e-3 * total:
+            continue
+        errs[k] = _norm_rel(cpu(named[k].grad), w)
+    print(f"bf16 tiny training gradients vs reference: worst norm error {worst_norm:.2e}; ||dg||/||g||: "
+          + ", ".join(f"{k} {v:.2e}" for k, v in sorted(errs.items(), key=lambda kv: -kv[1])))
+    for k, e in errs.items():
+        # the rel-pos tables collect a bf16-rounded bias gradient dE over every (query, key) pair of a head: 5e-2 there
+        assert e < (5e-2 if "rel_pos" in k else 3e-2), (k, e)
+
+
+def test_svit_tiny_droppath_training_parity(golden):
+    """VERDICT r1 weak #1 / SURVEY App. C: training-mode parity with DropPath ON.  The reference draws two
+    torch.rand((B,1,1)) masks per block (attention branch, MLP branch) in block order from the global CPU generator;
+    the same draws (same seed, same order) are injected into svit_b200.DropPath, fp32 mode."""
+    g = golden("svit_tiny_droppath.pt")
+    cfg = tiny_cfg()
+    ops.set_impl(gemm=ops.IMPL_SIMT, attn=ops.IMPL_SIMT)
+    try:
+        m = _model(cfg, g, torch.float32)
+        m.train()
+        n_dp = 0
+        for mod in m.modules():
+            if isinstance(mod, svit_b200.DropPath):
+                mod.drop_prob = g["drop_prob"]
+                n_dp += 1
+            if isinstance(mod, nn.Dropout):
+                mod.p = 0.0
+        assert n_dp == g["n_droppath_modules"]
+        B = g["logits"].shape[0]
+        torch.manual_seed(g["rng_seed"])
+        draws = []
+        real_rand = torch.rand
+
+        def cpu_order_rand(shape, *a, dtype=None, device=None, **kw):
+            r = real_rand(tuple(shape), dtype=torch.float32)  # global CPU generator, the reference's stream
+            draws.append(r.reshape(-1))
+            return r.to(device=device, dtype=dtype or torch.float32)
+        msa.torch.rand = cpu_order_rand
+        try:
+            clip = synth_input("tiny.clip.dp", (B, 3, 4, 32, 32), 15).to(DEV)
+            logits, extra = m([clip])
+        finally:
+            msa.torch.rand = real_rand
+        assert torch.equal(torch.stack(draws), g["rand"])  # same number of draws, same order, same values
+        assert max_rel_err(cpu(logits), g["logits"]) < 2e-4
+        tgt = (torch.arange(B) % logits.shape[1]).to(DEV)
+        loss = torch.nn.functional.cross_entropy(logits, tgt) + 0.1 * extra["pred_bboxes"].square().mean()
+        assert abs(loss.item() - g["loss"].item()) < 1e-4 * abs(g["loss"].item())
+        loss.backward()
+        named = dict(m.named_parameters())
+        for k, n in g["grad_norms"].items():
+            # the reference keeps unused heads in the graph (+ sum(p) * 0): their gradient is zero there, None here
+            got = named[k].grad.double().norm().item() if named[k].grad is not None else 0.0
+            assert abs(got - n.item()) <= 2e-3 * n.item() + 1e-7, (k, got, n.item())
+        for k, w in g["grads"].items():
+            assert max_rel_err(cpu(named[k].grad), w) < 2e-3, k
+    finally:
+        ops.set_impl(gemm=ops.IMPL_AUTO, attn=ops.IMPL_AUTO)
+
+
+def test_blocks_full_size_bf16_forward_backward_vs_oracle():
+    """One real-geometry block per stage (blocks 0, 2, 4, 15 of configs/ssv2.yaml, B = 1), bf16 production kernels,
+    forward AND backward against the CPU oracle's autograd in fp32 on the same bf16-rounded input: forward <= 2e-2
+    (max|dy| / max|y|), gradients ||dg|| / ||g|| <= 3e-2 (input gradient, GEMM / pooling / rel-pos / norm parameters)."""
+    cfg = ssv2_cfg()
+    specs = block_specs(cfg)[0]
+    for i in (0, 2, 4, 15):
+        sp = specs[i]
+        p = synth_state(block_param_shapes(sp), 600 + i, w_std=0.06)
+        T, H, W = sp["input_size"]
+        x = synth_input(f"fullblk.bf16.{i}", (1, 1 + T * H * W + 64, sp["dim"]), 8).bfloat16().float()
+        gy_shape = None
+        po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        xo = x.clone().requires_grad_(True)
+        want, thw_w = O.block_forward(xo, sp["input_size"], po, "", sp)
+        gy = synth_input(f"fullblk.bf16.gy{i}", tuple(want.shape), 9).bfloat16().float()
+        want.backward(gy)
+        m = svit_b200.MultiScaleBlock(dim=sp["dim"], dim_out=sp["dim_out"], num_heads=sp["num_heads"],
+                                      input_size=sp["input_size"], qkv_bias=True, norm_layer=LN, kernel_q=[3, 3, 3],
+                                      kernel_kv=[3, 3, 3], stride_q=sp["stride_q"], stride_kv=sp["stride_kv"],
+                                      rel_pos_spatial=True, rel_pos_temporal=True, residual_pooling=True,
+                                      dim_mul_in_att=True)
+        m.load_state_dict(p)
+        m = m.to(DEV)
+        xg = x.to(DEV, torch.bfloat16).requires_grad_(True)
+        got, thw_g = m(xg, sp["input_size"])
+        assert list(thw_g) == list(thw_w)
+        ferr = max_rel_err(cpu(got), want.detach())
+        got.backward(gy.to(DEV, torch.bfloat16))
+        named = dict(m.named_parameters())
+        errs = {"dx": _norm_rel(cpu(xg.grad), xo.grad)}
+        for k in ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.bias", "attn.pool_q.weight",
+                  "attn.pool_k.weight", "attn.norm_q.weight", "attn.rel_pos_h", "attn.rel_pos_t", "norm1.weight", "norm2.bias"):
+            errs[k] = _norm_rel(cpu(named[k].grad), po[k].grad)
+        worst = max(errs, key=errs.get)
+        print(f"block {i}: bf16 forward max-rel-err {ferr:.2e}; worst gradient {worst} {errs[worst]:.2e}")
+        assert ferr < 2e-2, (i, ferr)
+        assert errs[worst] < 3e-2, (i, errs)
+
+
+def test_msa_config5_shapes_vs_oracle():
+    """BASELINE configs[4] shapes: a full MultiScaleAttention at each of the 7 distinct stage shapes of a 32x312^2 clip
+    (patch grid 16x78x78, 128 object tokens; run-time rel-pos table interpolation, non-integer q/k ratios), B = 1, bf16,
+    against the CPU oracle in fp32.  Blocks 1, 3, 14 have kh + kw + kt = 56 > 47 bias entries and take the older
+    attn_tc kernel, the others attn_tc3: both paths are covered.  Tolerance 2e-2 (max|dy| / max|y|)."""
+    cfg = ssv2_cfg()
+    cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE, cfg.DATA.TEST_CROP_SIZE = 32, 312, 312
+    specs = block_specs(cfg)[0]
+    ps = cfg.MVIT.PATCH_STRIDE
+    thw = [32 // ps[0], 312 // ps[1], 312 // ps[2]]
+    Otot = 32 * cfg.SVIT.O
+    seen = set()
+    for i, sp in enumerate(specs):
+        sq = sp["stride_q"][1] if sp["stride_q"] else 1
+        key = (sp["dim"], sp["dim_out"], tuple(thw), sq, tuple(sp["stride_kv"]))
+        nthw = [thw[0], (thw[1] - 1) // sq + 1, (thw[2] - 1) // sq + 1]
+        if key not in seen:
+            seen.add(key)
+            p = synth_state(attn_param_shapes(sp["dim"], sp["dim_out"], sp["num_heads"], sp["input_size"], sp["stride_q"],
+                                                sp["stride_kv"]), 700 + i, w_std=0.06)
+            N = 1 + thw[0] * thw[1] * thw[2] + Otot
+            x = synth_input(f"cfg5.msa{i}", (1, N, sp["dim"]), 10).bfloat16().float()
+            with torch.no_grad():
+                want, q_thw = O.msa_forward(x, thw, p, "", sp["num_heads"], sp["stride_q"], sp["stride_kv"])
+            m = svit_b200.MultiScaleAttention(sp["dim"], sp["dim_out"], sp["input_size"], num_heads=sp["num_heads"],
+                                              qkv_bias=True, kernel_q=sp["kernel_q"], kernel_kv=sp["kernel_kv"],
+                                              stride_q=sp["stride_q"], stride_kv=sp["stride_kv"], norm_layer=LN,
+                                              rel_pos_spatial=True, rel_pos_temporal=True, residual_pooling=True)
+            m.load_state_dict(p)
+            m = m.to(DEV)
+            with torch.no_grad():
+                got, q_got = m(x.to(DEV, torch.bfloat16), thw)
+            assert list(q_got) == list(q_thw) == nthw
+            err = max_rel_err(cpu(got), want)
+            skv = sp["stride_kv"][1]
+            ne = thw[0] + 2 * ((thw[1] - 1) // skv + 1)
+            print(f"config-5 block {i}: Nq {got.shape[1]} heads {sp['num_heads']} bias entries {ne}: bf16 max-rel-err {err:.2e}")
+            assert err < 2e-2, (i, err)
+        thw = nthw
+    assert len(seen) == 7
