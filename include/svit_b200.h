@@ -213,6 +213,25 @@ int svit_zero_empty_boxes(float* boxes_cxcywh, int64_t n, float eps, void* strea
 int svit_normalize_u8(const void* frames, void* out, int B, int T, int H, int W, float mean0, float mean1, float mean2,
                       float std0, float std1, float std2, int out_dtype, void* stream);
 
+/* ---- head + losses.
+ * svit_head_fwd: SViTHead.forward without autograd (video_model_builder.py:507-546) in one launch.  x [B, 1 + Tx*O, C]
+ * = [cls ; object tokens] (fp32 or bf16); weights fp32: projection [num_classes, C], boxes_mlp.0 [4, C], boxes_bce_mlp
+ * [1, C], contact_mlp [5, C] and their biases.  Outputs fp32: logits [B, num_classes]; probs (optional; softmax, or
+ * sigmoid when act_sigmoid) ; obj_desc [B, Tx, O, C]; pred_bboxes [B, Tx, O, 5] = (score | sigmoid(box)) with the score
+ * passed through a sigmoid when eval_mode; pred_contact [B, Tx, 2, 5] (softmax when eval_mode) for object slots 0, 1.
+ * svit_haog_loss: boxes_loss_ + contact-state cross entropy (models/losses.py:50-92, 138-155; utils/box_ops.py:41-77) as
+ * masked means over paired boxes.  pred_bboxes [n_boxes, 5] = (score logit, cx, cy, w, h); target_boxes
+ * [n_boxes, target_cols] (4: all-zero row = no box; 5: leading soft mask); pred_contact [n_contact, 5] logits,
+ * target_contact [n_contact] int64 (-1 = ignore).  losses[4] = (l1, bce, giou, contact ce); d_l1 / d_giou [n_boxes, 4],
+ * d_bce [n_boxes], d_ce [n_contact, 5] = the gradient of each term w.r.t. its prediction columns. */
+int svit_head_fwd(const void* x, const float* w_proj, const float* b_proj, const float* w_box, const float* b_box,
+                  const float* w_score, const float* b_score, const float* w_contact, const float* b_contact, float* logits,
+                  float* probs, float* obj_desc, float* pred_bboxes, float* pred_contact, int B, int Tx, int O, int C,
+                  int num_classes, int act_sigmoid, int eval_mode, int dtype, void* stream);
+int svit_haog_loss(const float* pred_bboxes, const float* target_boxes, int target_cols, int64_t n_boxes,
+                   const float* pred_contact, const int64_t* target_contact, int64_t n_contact, float* losses, float* d_l1,
+                   float* d_bce, float* d_giou, float* d_ce, void* stream);
+
 /* ---- fused optimizer step: clip_grad_norm_ + torch.optim.AdamW over all parameter tensors
  * (tools/train_net.py:133-151, models/optimizer.py:89-104) in two launches.  `table` [ntensors] and the chunk map
  * (chunk c covers elements [chunk_start[c], chunk_start[c] + chunk) of tensor chunk_tensor[c]) live in device memory;

@@ -4,8 +4,9 @@ Reference: slowfast/models/losses.py:50-168 (`boxes_loss_`, `VideoImageLoss`) an
 slowfast/utils/box_ops.py:41-77.  The reference branches on `tar_mask.sum() > 0` / `mask.sum() > 0` (a device -> host
 round trip per step) and builds the full N x N GIoU matrix only to take its diagonal; here every term is a masked mean
 over paired boxes, which has the same value and the same gradients -- including the "no valid target" case, where the
-reference substitutes a fresh zero and these give zero with zero gradient.  Pure tensor glue on tiny tensors
-([B, T, O, 5]); runs on whatever device the predictions live on.
+reference substitutes a fresh zero and these give zero with zero gradient.  On CUDA tensors `haog_loss` is ONE kernel
+launch (svit_haog_loss: values and gradients of the four terms); the tensor expressions below are the host-side statement
+of the same definition, pinned to the reference by tests/test_losses.py and used to check the kernel.
 """
 from __future__ import annotations
 
@@ -64,6 +65,12 @@ def boxes_loss(pred, tar):
 def haog_loss(extra_preds, metadata):
     """VideoImageLoss._haog_loss (losses.py:138-155): box L1 / BCE / GIoU + contact-state cross entropy over the
     annotated hands (target >= 0)."""
+    if extra_preds["pred_bboxes"].is_cuda:  # one launch: values and gradients of the four terms (csrc/head_loss.cu)
+        from . import ops
+        l1, bce, giou, ce = ops.haog_loss(extra_preds["pred_bboxes"], metadata["haog_bboxes"],
+                                          extra_preds["pred_contact_state"], metadata["contact_state"])
+        return {"boxes_l1_loss": l1, "boxes_bce_loss": bce, "boxes_giou_loss": giou, "loss_contact_state": ce}
+    # CPU tensors (host-side unit tests of the loss definition): the same masked means as plain tensor expressions
     l1, bce, giou = boxes_loss(extra_preds["pred_bboxes"], metadata["haog_bboxes"])
     pred = extra_preds["pred_contact_state"].flatten(0, 2)
     tar = metadata["contact_state"].flatten()

@@ -72,6 +72,15 @@ class SViTHead(nn.Module):
         if hasattr(self, "dropout") and self.training:
             x = self.dropout(x)
         B = x.size(0)
+        if not torch.is_grad_enabled():
+            # no autograd (inference, the no-grad frames pass): the whole head is one launch (csrc/head_loss.cu)
+            O = (x.size(1) - 1) // T
+            logits, probs, xobj, pred_bboxes, contact = ops.head_forward(
+                x, self.projection.weight, self.projection.bias, self.boxes_mlp[0].weight, self.boxes_mlp[0].bias,
+                self.boxes_bce_mlp.weight, self.boxes_bce_mlp.bias, self.contact_mlp.weight, self.contact_mlp.bias, T, O,
+                act_sigmoid=self.act_func == "sigmoid", eval_mode=not self.training, want_probs=not self.training)
+            extra.update(obj_desc=xobj, logits=logits, pred_bboxes=pred_bboxes, pred_contact_state=contact)
+            return (logits if self.training else probs), extra
         x = x.float()
         cls, xobj = x[:, 0].contiguous(), x[:, 1:]
         xobj = xobj.reshape(B, T, -1, xobj.size(-1)).contiguous()

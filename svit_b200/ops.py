@@ -828,3 +828,64 @@ def zero_empty_boxes_device(boxes, eps=0.05):
     assert boxes.dtype == torch.float32 and boxes.is_contiguous()
     _call("svit_zero_empty_boxes", boxes.data_ptr(), boxes.numel() // 4, float(eps), _stream())
     return boxes
+
+
+# --------------------------------------------------------------------------------------------
+# head (inference) and HAOG losses
+# --------------------------------------------------------------------------------------------
+def head_forward(x, wp, bp, wb, bb, ws, bs, wc, bc, Tx, O, act_sigmoid=False, eval_mode=True, want_probs=True):
+    """SViTHead.forward without autograd in one launch (video_model_builder.py:507-546).
+    x [B, 1 + Tx*O, C].  Returns (logits, probs | None, obj_desc, pred_bboxes, pred_contact), all fp32."""
+    _chk(x, "head_forward")
+    x = x.contiguous()
+    B, R, Cn = x.shape
+    assert R == 1 + Tx * O
+    NC = wp.shape[0]
+    dev = x.device
+    logits = torch.empty(B, NC, dtype=torch.float32, device=dev)
+    probs = torch.empty(B, NC, dtype=torch.float32, device=dev) if want_probs else None
+    obj = torch.empty(B, Tx, O, Cn, dtype=torch.float32, device=dev)
+    boxes = torch.empty(B, Tx, O, 5, dtype=torch.float32, device=dev)
+    contact = torch.empty(B, Tx, 2, 5, dtype=torch.float32, device=dev)
+    ws_ = [_f32(t) for t in (wp, bp, wb, bb, ws, bs, wc, bc)]
+    _call("svit_head_fwd", x.data_ptr(), *[t.data_ptr() for t in ws_], logits.data_ptr(), _p(probs), obj.data_ptr(),
+          boxes.data_ptr(), contact.data_ptr(), B, Tx, O, Cn, NC, int(act_sigmoid), int(eval_mode), _dt(x), _stream())
+    return logits, probs, obj, boxes, contact
+
+
+class _HaogLoss(torch.autograd.Function):
+    """(l1, bce, giou, contact ce) of VideoImageLoss._haog_loss (models/losses.py:50-92, 138-155) in one launch; the
+    same launch produces the gradient of every term, so backward is four tiny scaled adds."""
+
+    @staticmethod
+    def forward(ctx, pred_bboxes, tar_boxes, pred_contact, tar_contact):
+        _chk(pred_bboxes, "haog_loss")
+        pb = pred_bboxes.detach().float().contiguous().reshape(-1, 5)
+        tb = tar_boxes.detach().to(device=pb.device, dtype=torch.float32).contiguous()
+        tcols = tb.shape[-1]
+        tb = tb.reshape(-1, tcols)
+        pc = pred_contact.detach().float().contiguous().reshape(-1, 5)
+        tcn = tar_contact.detach().to(device=pb.device, dtype=torch.int64).contiguous().reshape(-1)
+        N, M = pb.shape[0], pc.shape[0]
+        out = torch.empty(4, dtype=torch.float32, device=pb.device)
+        d_l1 = torch.empty(N, 4, dtype=torch.float32, device=pb.device)
+        d_giou = torch.empty(N, 4, dtype=torch.float32, device=pb.device)
+        d_bce = torch.empty(N, dtype=torch.float32, device=pb.device)
+        d_ce = torch.empty(M, 5, dtype=torch.float32, device=pb.device)
+        _call("svit_haog_loss", pb.data_ptr(), tb.data_ptr(), tcols, N, pc.data_ptr(), tcn.data_ptr(), M, out.data_ptr(),
+              d_l1.data_ptr(), d_bce.data_ptr(), d_giou.data_ptr(), d_ce.data_ptr(), _stream())
+        ctx.save_for_backward(d_l1, d_bce, d_giou, d_ce)
+        ctx.shapes = (pred_bboxes.shape, pred_contact.shape, pred_bboxes.dtype, pred_contact.dtype)
+        return out[0], out[1], out[2], out[3]
+
+    @staticmethod
+    def backward(ctx, g_l1, g_bce, g_giou, g_ce):
+        d_l1, d_bce, d_giou, d_ce = ctx.saved_tensors
+        bshape, cshape, bdt, cdt = ctx.shapes
+        dboxes = torch.cat([(g_bce * d_bce).unsqueeze(-1), g_l1 * d_l1 + g_giou * d_giou], dim=-1)
+        return dboxes.reshape(bshape).to(bdt), None, (g_ce * d_ce).reshape(cshape).to(cdt), None
+
+
+def haog_loss(pred_bboxes, tar_boxes, pred_contact, tar_contact):
+    """Returns (boxes_l1_loss, boxes_bce_loss, boxes_giou_loss, loss_contact_state) as device scalars."""
+    return _HaogLoss.apply(pred_bboxes, tar_boxes, pred_contact, tar_contact)
