@@ -213,6 +213,19 @@ int svit_zero_empty_boxes(float* boxes_cxcywh, int64_t n, float eps, void* strea
 int svit_normalize_u8(const void* frames, void* out, int B, int T, int H, int W, float mean0, float mean1, float mean2,
                       float std0, float std1, float std2, int out_dtype, void* stream);
 
+/* ---- input side on the GPU, beyond svit_normalize_u8: per-sample spatial crop (offsets x_off / y_off [B],
+ * int32, device) + optional horizontal flip (flip [B] int32 or NULL) + colour normalisation + THWC -> CTHW, one pass
+ * (datasets/transform.py:154-190, 248-285; datasets/utils.py:287-303); out [B, 3, T, crop_h, crop_w] fp32 / bf16.
+ * svit_boxes_crop_flip moves the boxes with the frames and into the loss format: crop_clip_boxes, flip, / crop size,
+ * clip [0, 1], xyxy -> cxcywh, zero boxes with w or h <= eps (transform.py:107-132; ssv2_frames.py:347-353;
+ * utils/box_ops.py:32-36, 116-130); boxes [B, boxes_per_sample, 4] fp32 pixels -> [B, boxes_per_sample, 4]. */
+int svit_crop_flip_normalize_u8(const void* frames, void* out, const int32_t* x_off, const int32_t* y_off,
+                                const int32_t* flip, int B, int T, int H, int W, int crop_h, int crop_w, float mean0,
+                                float mean1, float mean2, float std0, float std1, float std2, int out_dtype, void* stream);
+int svit_boxes_crop_flip(const float* boxes_xyxy, float* out_cxcywh, const int32_t* x_off, const int32_t* y_off,
+                         const int32_t* flip, int B, int64_t boxes_per_sample, int crop_h, int crop_w, float eps,
+                         void* stream);
+
 /* ---- head + losses.
  * svit_head_fwd: SViTHead.forward without autograd (video_model_builder.py:507-546) in one launch.  x [B, 1 + Tx*O, C]
  * = [cls ; object tokens] (fp32 or bf16); weights fp32: projection [num_classes, C], boxes_mlp.0 [4, C], boxes_bce_mlp

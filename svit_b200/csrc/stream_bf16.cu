@@ -378,3 +378,120 @@ extern "C" int svit_normalize_u8(const void* frames, void* out, int B, int T, in
   SVIT_CHECK_LAUNCH();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ N4: crop / flip
+// Input side on the GPU: decoded uint8 frames [B, T, H, W, 3] -> per-sample spatial crop
+// (datasets/transform.py:154-190 random_crop / uniform_crop with the offsets chosen by the host), optional horizontal
+// flip (transform.py:248-285), colour normalisation (datasets/utils.py:287-303) and the THWC -> CTHW layout, one pass.
+// thread = 4 consecutive output pixels of a row; fp32 operation order of the reference (bit-identical fp32 output).
+template <typename OT>
+__global__ void __launch_bounds__(256) crop_flip_normalize_u8_kernel(const uint8_t* __restrict__ in, OT* __restrict__ out,
+                                                                     const int32_t* __restrict__ x_off,
+                                                                     const int32_t* __restrict__ y_off,
+                                                                     const int32_t* __restrict__ flip, int64_t nquads, int T,
+                                                                     int H, int W, int cs_h, int cs_w, float m0, float m1,
+                                                                     float m2, float s0, float s1, float s2) {
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+  const int qw = cs_w >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % qw);
+    int64_t r = i / qw;
+    const int y = (int)(r % cs_h);
+    r /= cs_h;
+    const int t = (int)(r % T);
+    const int b = (int)(r / T);
+    const int xo = x_off[b], yo = y_off[b];
+    const bool fl = flip && flip[b] != 0;
+    const uint8_t* row = in + ((((int64_t)b * T + t) * H + (y + yo)) * W) * 3;
+    float v[3][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = q * 4 + k;
+      const int sx = xo + (fl ? cs_w - 1 - x : x);  // images.flip(-1) after the crop
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float f = (float)__ldg(row + (int64_t)sx * 3 + c);
+        v[c][k] = __fdiv_rn(__fsub_rn(__fdiv_rn(f, 255.0f), mean[c]), sd[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      OT* dst = out + ((((int64_t)b * 3 + c) * T + t) * cs_h + y) * cs_w + q * 4;
+      if (sizeof(OT) == 2) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[c][0], v[c][1]), h1 = __floats2bfloat162_rn(v[c][2], v[c][3]);
+        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+      }
+    }
+  }
+}
+
+// Boxes follow the frames (transform.py:107-132 crop_clip_boxes, :248-285 horizontal_flip on [N, 4] boxes) and are then
+// brought to the loss's format (datasets/ssv2_frames.py:347-353): normalise by the crop size, clip to [0, 1],
+// xyxy -> cxcywh (utils/box_ops.py:32-36), zero boxes with w or h <= eps (utils/box_ops.py:116-130).  Every step is the
+// reference's float32 operation, so the result is bit-identical.
+__global__ void boxes_crop_flip_kernel(const float* __restrict__ in, float* __restrict__ out, const int32_t* __restrict__ x_off,
+                                       const int32_t* __restrict__ y_off, const int32_t* __restrict__ flip, int64_t n,
+                                       int per_sample, int cs_h, int cs_w, float eps) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_sample);
+    const float xo = (float)x_off[b], yo = (float)y_off[b];
+    const float W = (float)cs_w, Hh = (float)cs_h;
+    float x0 = fminf(fmaxf(__fsub_rn(in[4 * i + 0], xo), 0.f), W), y0 = fminf(fmaxf(__fsub_rn(in[4 * i + 1], yo), 0.f), Hh);
+    float x1 = fminf(fmaxf(__fsub_rn(in[4 * i + 2], xo), 0.f), W), y1 = fminf(fmaxf(__fsub_rn(in[4 * i + 3], yo), 0.f), Hh);
+    if (flip && flip[b] != 0) {
+      const float nx0 = __fsub_rn(__fsub_rn(W, x1), 1.f), nx1 = __fsub_rn(__fsub_rn(W, x0), 1.f);
+      x0 = nx0;
+      x1 = nx1;
+    }
+    x0 = fminf(fmaxf(__fdiv_rn(x0, W), 0.f), 1.f);
+    x1 = fminf(fmaxf(__fdiv_rn(x1, W), 0.f), 1.f);
+    y0 = fminf(fmaxf(__fdiv_rn(y0, Hh), 0.f), 1.f);
+    y1 = fminf(fmaxf(__fdiv_rn(y1, Hh), 0.f), 1.f);
+    float cx = __fdiv_rn(__fadd_rn(x0, x1), 2.f), cy = __fdiv_rn(__fadd_rn(y0, y1), 2.f);
+    float w = __fsub_rn(x1, x0), h = __fsub_rn(y1, y0);
+    if (w <= eps || h <= eps) cx = cy = w = h = 0.f;
+    out[4 * i + 0] = cx;
+    out[4 * i + 1] = cy;
+    out[4 * i + 2] = w;
+    out[4 * i + 3] = h;
+  }
+}
+
+extern "C" int svit_crop_flip_normalize_u8(const void* frames, void* out, const int32_t* x_off, const int32_t* y_off,
+                                           const int32_t* flip, int B, int T, int H, int W, int crop_h, int crop_w,
+                                           float mean0, float mean1, float mean2, float std0, float std1, float std2,
+                                           int out_dtype, void* stream) {
+  if (!frames || !out || !x_off || !y_off || B < 0 || T < 1 || H < 1 || W < 1 || crop_h < 1 || crop_w < 1 || crop_h > H ||
+      crop_w > W)
+    return SVIT_EINVAL;
+  if (crop_w % 4 || (reinterpret_cast<uintptr_t>(out) & 15)) return SVIT_ENOTSUP;
+  if (B == 0) return 0;
+  const int64_t nq = (int64_t)B * T * crop_h * (crop_w / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t grid = (nq + 255) / 256;
+  const int64_t cap = (int64_t)svit_num_sms() * 16;
+  if (grid > cap) grid = cap;
+  if (out_dtype == SVIT_BF16)
+    crop_flip_normalize_u8_kernel<bf16><<<(unsigned)grid, 256, 0, st>>>((const uint8_t*)frames, (bf16*)out, x_off, y_off, flip, nq, T, H, W, crop_h, crop_w, mean0, mean1, mean2, std0, std1, std2);
+  else if (out_dtype == SVIT_F32)
+    crop_flip_normalize_u8_kernel<float><<<(unsigned)grid, 256, 0, st>>>((const uint8_t*)frames, (float*)out, x_off, y_off, flip, nq, T, H, W, crop_h, crop_w, mean0, mean1, mean2, std0, std1, std2);
+  else
+    return SVIT_EINVAL;
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int svit_boxes_crop_flip(const float* boxes_xyxy, float* out_cxcywh, const int32_t* x_off, const int32_t* y_off,
+                                    const int32_t* flip, int B, int64_t boxes_per_sample, int crop_h, int crop_w, float eps,
+                                    void* stream) {
+  if (!boxes_xyxy || !out_cxcywh || !x_off || !y_off || B < 0 || boxes_per_sample < 0 || crop_h < 1 || crop_w < 1)
+    return SVIT_EINVAL;
+  const int64_t n = (int64_t)B * boxes_per_sample;
+  if (n == 0) return 0;
+  if (boxes_per_sample > 0x7fffffff) return SVIT_EINVAL;
+  boxes_crop_flip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(boxes_xyxy, out_cxcywh, x_off, y_off, flip, n, (int)boxes_per_sample, crop_h, crop_w, eps);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}

@@ -889,3 +889,50 @@ class _HaogLoss(torch.autograd.Function):
 def haog_loss(pred_bboxes, tar_boxes, pred_contact, tar_contact):
     """Returns (boxes_l1_loss, boxes_bce_loss, boxes_giou_loss, loss_contact_state) as device scalars."""
     return _HaogLoss.apply(pred_bboxes, tar_boxes, pred_contact, tar_contact)
+
+
+# --------------------------------------------------------------------------------------------
+# input side on the GPU (SURVEY 8f N4): crop + flip + normalise, boxes follow the frames
+# --------------------------------------------------------------------------------------------
+def _i32(v, n, device):
+    t = torch.as_tensor(v, dtype=torch.int32)
+    if t.dim() == 0:
+        t = t.expand(n)
+    return t.to(device).contiguous()
+
+
+def crop_flip_normalize_u8(frames, x_off, y_off, flip, crop, mean, std, dtype=torch.bfloat16):
+    """uint8 frames [B, T, H, W, 3] -> normalised clip [B, 3, T, crop, crop]: per-sample crop at (x_off[b], y_off[b])
+    (transform.py:154-190), horizontal flip where flip[b] (transform.py:248-285), (x / 255 - mean) / std
+    (datasets/utils.py:287-303), CTHW layout -- one streaming kernel; fp32 output bit-identical to the reference ops."""
+    if frames.dtype != torch.uint8 or frames.dim() != 5 or frames.shape[-1] != 3:
+        raise ValueError("crop_flip_normalize_u8 expects uint8 [B, T, H, W, 3]")
+    _chk(frames, "crop_flip_normalize_u8")
+    frames = frames.contiguous()
+    B, T, H, W, _ = frames.shape
+    ch, cw = (crop, crop) if isinstance(crop, int) else crop
+    xo, yo = _i32(x_off, B, frames.device), _i32(y_off, B, frames.device)
+    fl = _i32(flip, B, frames.device) if flip is not None else None
+    if int(xo.max()) + cw > W or int(yo.max()) + ch > H or int(xo.min()) < 0 or int(yo.min()) < 0:
+        raise ValueError("crop window leaves the frame")
+    out = torch.empty(B, 3, T, ch, cw, dtype=dtype, device=frames.device)
+    _call("svit_crop_flip_normalize_u8", frames.data_ptr(), out.data_ptr(), xo.data_ptr(), yo.data_ptr(), _p(fl), B, T, H, W,
+          ch, cw, float(mean[0]), float(mean[1]), float(mean[2]), float(std[0]), float(std[1]), float(std[2]), _dt(out),
+          _stream())
+    return out
+
+
+def boxes_crop_flip(boxes_xyxy, x_off, y_off, flip, crop, eps=0.05):
+    """boxes [B, ..., 4] xyxy pixels of the un-cropped frames -> the loss's targets [B, ..., 4] cxcywh in [0, 1] for the
+    cropped / flipped clip, boxes thinner than eps zeroed (transform.py:107-132, 248-285; ssv2_frames.py:347-353)."""
+    _chk(boxes_xyxy, "boxes_crop_flip")
+    b = boxes_xyxy.to(torch.float32).contiguous()
+    B = b.shape[0]
+    per = b[0].numel() // 4 if B else 0
+    ch, cw = (crop, crop) if isinstance(crop, int) else crop
+    xo, yo = _i32(x_off, B, b.device), _i32(y_off, B, b.device)
+    fl = _i32(flip, B, b.device) if flip is not None else None
+    out = torch.empty_like(b)
+    _call("svit_boxes_crop_flip", b.data_ptr(), out.data_ptr(), xo.data_ptr(), yo.data_ptr(), _p(fl), B, per, ch, cw,
+          float(eps), _stream())
+    return out

@@ -8,6 +8,7 @@ outputs.  The fixtures pin oracle/svit_oracle.py (tests/test_oracle_golden.py) a
 ground truth of the GPU parity tests.  Weights come from tests/golden/recipe.py and are
 regenerated, not stored, when they are large.
 """
+import importlib.util
 import os
 import sys
 
@@ -326,6 +327,53 @@ def loss_cases():
     save("losses.pt", dict(boxes=cases, haog=haog))
 
 
+# ---------------------------------------------------------------- N4 input side: crop / flip / normalise + boxes
+def aug_cases():
+    """The reference's own functions -- datasets/utils.py tensor_normalize, transform.py random_crop (crop_clip_boxes) and
+    horizontal_flip with fixed draws, then the box post-processing of ssv2_frames.py:347-353 -- on uint8 frames and
+    [N, 4] pixel boxes.  (NO_RAND_PARAMS is a module flag of transform.py: switched off at run time so that the crop
+    offsets / flip draw can be passed in; the file itself is untouched.)"""
+    import importlib
+    ref_loader._shell("slowfast.datasets", os.path.join(ref_loader.REF_ROOT, "slowfast", "datasets"))
+    TR = importlib.import_module("slowfast.datasets.transform")
+    TR.NO_RAND_PARAMS = False
+    spec = importlib.util.spec_from_file_location("ref_dutils_part", os.path.join(ref_loader.REF_ROOT, "slowfast", "datasets", "utils.py"))
+    src = open(spec.origin).read()
+    g = {"torch": torch}
+    start = src.index("def tensor_normalize(")
+    exec(src[start:src.index("\ndef ", start + 10)], g)   # tensor_normalize only (utils.py:287-303), verbatim
+    tensor_normalize = g["tensor_normalize"]
+    rng = np.random.RandomState(4242)
+    mean, std = [0.45, 0.40, 0.35], [0.225, 0.25, 0.2]
+    cases = []
+    for i, (T, H, W, cs) in enumerate(((4, 40, 52, 32), (2, 36, 36, 36), (3, 48, 44, 24), (1, 33, 41, 28))):
+        frames = torch.from_numpy(rng.randint(0, 256, (T, H, W, 3)).astype(np.uint8))
+        xo = int(rng.randint(0, W - cs + 1)); yo = int(rng.randint(0, H - cs + 1))
+        flip = bool(i % 2 == 0)
+        boxes = rng.rand(12, 4).astype(np.float32) * np.array([W, H, W, H], np.float32) * 0.7
+        boxes[:, 2:] = boxes[:, :2] + rng.rand(12, 2).astype(np.float32) * np.array([W, H], np.float32) * 0.6
+        boxes[3] = 0                                           # an empty slot
+        boxes[5, 2:] = boxes[5, :2] + 0.5                      # thinner than eps after normalisation
+        x = tensor_normalize(frames, mean, std).permute(3, 0, 1, 2)          # C T H W
+        rp = {"random_crop_x_offset": xo, "random_crop_y_offset": yo, "horizontal_flip": 0.25 if flip else 0.75}
+        if H == cs and W == cs:
+            xc, bc = x, TR.crop_clip_boxes(boxes, 0, 0, cs)    # random_crop returns the images alone in this case
+        else:
+            xc, bc = TR.random_crop(x, cs, boxes=boxes, rand_params=rp)
+        xf, bf = TR.horizontal_flip(0.5, xc, boxes=bc, rand_params=rp)
+        h, w = xf.shape[-2:]
+        bb = bf.copy()
+        bb[..., [0, 2]] = bb[..., [0, 2]] / w
+        bb[..., [1, 3]] = bb[..., [1, 3]] / h
+        bb = torch.from_numpy(np.clip(bb, 0, 1))
+        bb = ns.box_ops.box_xyxy_to_cxcywh(bb)
+        bb = ns.box_ops.zero_empty_boxes(bb, mode="cxcywh")
+        cases.append(dict(frames=frames, boxes=torch.from_numpy(boxes), x_off=xo if not (H == cs and W == cs) else 0,
+                          y_off=yo if not (H == cs and W == cs) else 0, flip=flip, crop=cs, mean=mean, std=std,
+                          clip=xf.contiguous(), boxes_out=bb))
+    save("aug.pt", cases)
+
+
 if __name__ == "__main__":
     relpos_tables()
     pool_cases()
@@ -333,5 +381,6 @@ if __name__ == "__main__":
     block_cases()
     model_cases()
     droppath_case()
+    aug_cases()
     box_cases()
     loss_cases()
