@@ -177,6 +177,20 @@ int svit_assemble_tokens_bwd(const void* dx, float* dcls, float* dqueries, float
 int svit_im2col3d(const void* x, void* cols, int B, int Cin, int T, int H, int W, int kt, int kh, int kw, int st, int sh,
                   int sw, int pt, int ph, int pw, int Kpad, int in_dtype, int out_dtype, void* stream);
 
+/* ---- PatchEmbed as an implicit GEMM (stem_helper.py:309-320; csrc/patch_embed_tc.cu): no im2col matrix.
+ * svit_s2d_clip: the clip in space-to-depth cells, bf16 [B, ceil(T/st), ceil(H/sh), ceil(W/sw), C*st*sh*sw] with
+ * cell index ((c*st + tt)*sh + hh)*sw + ww, zero beyond T/H/W.  in_kind: SVIT_F32 / SVIT_BF16 = clip [B, C, T, H, W];
+ * 2 = uint8 frames [B, T, H, W, C] (C <= 3), normalised on the fly with mean / std (datasets/utils.py:287-303).
+ * svit_patch_embed_s2d: out rows row_off + (t'*Ho + h')*Wo + w' of every sample (out_batch_stride elements apart, bf16,
+ * E columns) = conv3d(clip) + bias; w2 [E, ntaps*cell] bf16 = the conv weight scattered into the cell taps
+ * (tap-major, zero where a tap has no kernel element).  svit_patch_embed_s2d_supported tells whether a geometry fits. */
+int svit_s2d_clip(const void* x, void* cells, int B, int C, int T, int H, int W, int st, int sh, int sw, int in_kind,
+                  float mean0, float mean1, float mean2, float std0, float std1, float std2, void* stream);
+int svit_patch_embed_s2d_supported(int C, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw, int E);
+int svit_patch_embed_s2d(const void* cells, const void* w2, const float* bias, void* out, int64_t out_batch_stride,
+                         int row_off, int B, int C, int T, int H, int W, int kt, int kh, int kw, int st, int sh, int sw,
+                         int pt, int ph, int pw, int E, void* stream);
+
 /* ---- token split: video_model_builder.py:377-384. out [B, 1+O, C] = rows {0} U {N-O .. N-1} of x [B, N, C]. */
 int svit_gather_cls_obj_fwd(const void* x, void* out, int B, int64_t N, int O, int C, int dtype, void* stream);
 int svit_gather_cls_obj_bwd(const void* dout, void* dx, int B, int64_t N, int O, int C, int dtype, void* stream);

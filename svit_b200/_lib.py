@@ -77,6 +77,9 @@ PROTOTYPES = {
     "svit_match_haog": [vp, vp, i64, vp],
     "svit_zero_empty_boxes": [vp, i64, f32, vp],
     "svit_normalize_u8": [vp, vp] + [C.c_int] * 4 + [f32] * 6 + [C.c_int, vp],
+    "svit_s2d_clip": [vp, vp] + [C.c_int] * 9 + [f32] * 6 + [vp],
+    "svit_patch_embed_s2d_supported": [C.c_int] * 11,
+    "svit_patch_embed_s2d": [vp, vp, vp, vp, i64, C.c_int] + [C.c_int] * 15 + [vp],
     "svit_crop_flip_normalize_u8": [vp, vp, vp, vp, vp] + [C.c_int] * 6 + [f32] * 6 + [C.c_int, vp],
     "svit_boxes_crop_flip": [vp, vp, vp, vp, vp, C.c_int, i64, C.c_int, C.c_int, f32, vp],
     "svit_head_fwd": [vp] * 14 + [C.c_int] * 8 + [vp],

@@ -161,18 +161,18 @@ class SViT(nn.Module):
     def forward_tokens(self, clip):
         """clip [B,3,T,H,W] (or [B,3,H,W] frame mode) -> (normed tokens [B, N, C], thw, Tx)."""
         x = clip
-        if x.dtype == torch.uint8:  # decoded frames [B, T, H, W, 3]: normalise + CTHW layout on the device (8f N4)
-            x = clip = ops.normalize_u8(x, self.cfg.DATA.MEAN, self.cfg.DATA.STD,
-                                        torch.float32 if self.compute_dtype == torch.float32 else torch.bfloat16)
-        if x.ndim == 4:
+        u8 = x.dtype == torch.uint8  # decoded frames [B, T, H, W, 3]: normalised on the device (8f N4)
+        if not u8 and x.ndim == 4:
             x = x.unsqueeze(2)
-        Tx = x.shape[2]
+        Tx = x.shape[1] if u8 else x.shape[2]
+        Hin, Win = (x.shape[2], x.shape[3]) if u8 else (x.shape[-2], x.shape[-1])
         pe = self.patch_embed.proj
         x = ops.patch_embed_tokens(x, pe.weight, pe.bias, self.cls_token, self.object_queries, self.pos_embed_temporal,
-                                   pe.kernel_size, pe.stride, pe.padding, self.compute_dtype)
+                                   pe.kernel_size, pe.stride, pe.padding, self.compute_dtype,
+                                   mean=self.cfg.DATA.MEAN, std=self.cfg.DATA.STD)
         T = self.cfg.DATA.NUM_FRAMES // self.patch_stride[0] if Tx > 1 else Tx
-        H = (clip.shape[-2] + 2 * pe.padding[1] - pe.kernel_size[1]) // pe.stride[1] + 1
-        W = (clip.shape[-1] + 2 * pe.padding[2] - pe.kernel_size[2]) // pe.stride[2] + 1
+        H = (Hin + 2 * pe.padding[1] - pe.kernel_size[1]) // pe.stride[1] + 1
+        W = (Win + 2 * pe.padding[2] - pe.kernel_size[2]) // pe.stride[2] + 1
         thw = [T, H, W]
         for blk in self.blocks:
             x, thw = blk(x, thw)

@@ -93,7 +93,8 @@ def cast_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 _FAMILY = {"svit_gemm": "gemm", "svit_attn_fwd": "attention", "svit_attn_bwd": "attention_bwd",
            "svit_pool_ln_fwd": "pool_ln", "svit_pool_ln_bwd": "pool_ln_bwd", "svit_layernorm_fwd": "layernorm",
-           "svit_layernorm_bwd": "layernorm_bwd", "svit_skip_maxpool_fwd": "skip_pool", "svit_im2col3d": "im2col"}
+           "svit_layernorm_bwd": "layernorm_bwd", "svit_skip_maxpool_fwd": "skip_pool", "svit_im2col3d": "im2col", "svit_s2d_clip": "im2col",
+           "svit_patch_embed_s2d": "gemm"}
 _prof = None
 
 
@@ -681,8 +682,91 @@ def _padded_weight(w, K, Kpad, dtype):
     return w2
 
 
-def patch_embed_tokens(clip, w, b, cls, queries, pos_t, kernel, stride, padding, dtype):
-    return _PatchEmbedTokens.apply(clip, w, b, cls, queries, pos_t, tuple(kernel), tuple(stride), tuple(padding), dtype)
+def _floor_div(a, b):
+    return a // b  # Python floors towards -inf, which is what the tap arithmetic needs
+
+
+def s2d_conv_weight(w, stride, padding):
+    """Conv3d weight [E, C, kt, kh, kw] scattered into the space-to-depth taps of csrc/patch_embed_tc.cu:
+    W2[E, ((it*nh + ih)*nw + iw) * cell + ((c*st + tt)*sh + hh)*sw + ww] = w[E, c, k_t, k_h, k_w] with
+    k_t - pt = (lo_t + it)*st + tt (same for h, w); positions no kernel element maps to stay zero."""
+    E, Cin, kt, kh, kw = w.shape
+    (st, sh, sw), (pt, ph, pw) = stride, padding
+    lo = [_floor_div(-p_, s_) for p_, s_ in zip((pt, ph, pw), (st, sh, sw))]
+    n = [_floor_div(k_ - 1 - p_, s_) - l_ + 1 for k_, p_, s_, l_ in zip((kt, kh, kw), (pt, ph, pw), (st, sh, sw), lo)]
+    W2 = torch.zeros(E, n[0], n[1], n[2], Cin, st, sh, sw, dtype=torch.float32, device=w.device)
+    wf = w.detach().float()
+    for a in range(kt):
+        it, tt = _floor_div(a - pt, st) - lo[0], (a - pt) % st
+        for bb in range(kh):
+            ih, hh = _floor_div(bb - ph, sh) - lo[1], (bb - ph) % sh
+            for c in range(kw):
+                iw, ww = _floor_div(c - pw, sw) - lo[2], (c - pw) % sw
+                W2[:, it, ih, iw, :, tt, hh, ww] = wf[:, :, a, bb, c]
+    return W2.reshape(E, -1).to(torch.bfloat16).contiguous()
+
+
+def s2d_clip(clip, stride, mean=None, std=None):
+    """Space-to-depth cells of a clip for the implicit-GEMM patch embed: clip [B, C, T, H, W] (fp32 / bf16) or uint8 frames
+    [B, T, H, W, C] (normalised on the fly) -> bf16 [B, ceil(T/st), ceil(H/sh), ceil(W/sw), C*st*sh*sw]."""
+    _chk(clip, "s2d_clip")
+    clip = clip.contiguous()
+    st, sh, sw = stride
+    if clip.dtype == torch.uint8:
+        B, T, H, W, Cin = clip.shape
+        kind = 2
+        m, sd = list(mean) + [0.0] * 3, list(std) + [1.0] * 3
+    else:
+        B, Cin, T, H, W = clip.shape
+        kind = _dt(clip)
+        m, sd = [0.0] * 3, [1.0] * 3
+    cells = torch.empty(B, -(-T // st), -(-H // sh), -(-W // sw), Cin * st * sh * sw, dtype=torch.bfloat16, device=clip.device)
+    _call("svit_s2d_clip", clip.data_ptr(), cells.data_ptr(), B, Cin, T, H, W, st, sh, sw, kind, float(m[0]), float(m[1]),
+          float(m[2]), float(sd[0]), float(sd[1]), float(sd[2]), _stream())
+    return cells
+
+
+def _patch_embed_implicit(clip, w, b, cls, queries, pos_t, kernel, stride, padding, mean, std):
+    """Inference path: conv3d as an implicit GEMM over space-to-depth cells (no im2col matrix), then cls / object rows."""
+    if clip.dtype == torch.uint8:
+        B, T, H, W, Cin = clip.shape
+    else:
+        B, Cin, T, H, W = clip.shape
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    pt, ph, pw = padding
+    To, Ho, Wo = (T + 2 * pt - kt) // st + 1, (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    L = To * Ho * Wo
+    E = w.shape[0]
+    Tx, O = T, queries.shape[1]
+    Ntot = 1 + L + Tx * O
+    cells = s2d_clip(clip, stride, mean, std)
+    tag = ("s2d", tuple(stride), tuple(padding))
+    w2 = _cache_get(w, tag)
+    if w2 is None:
+        w2 = _cache_put(w, tag, s2d_conv_weight(w, stride, padding))
+    x = torch.empty(B, Ntot, E, dtype=torch.bfloat16, device=clip.device)
+    _call("svit_patch_embed_s2d", cells.data_ptr(), w2.data_ptr(), _f32(b).data_ptr(), x.data_ptr(), Ntot * E, 1, B, Cin, T, H, W,
+          kt, kh, kw, st, sh, sw, pt, ph, pw, E, _stream(), tag=f"[B{B} {T}x{H}x{W}]" if _prof is not None else None)
+    _call("svit_assemble_tokens_fwd", x.data_ptr(), _f32(cls).data_ptr(), _f32(queries).data_ptr(),
+          _f32(pos_t).data_ptr(), B, L, Tx, O, E, BF16, _stream())
+    return x
+
+
+def patch_embed_tokens(clip, w, b, cls, queries, pos_t, kernel, stride, padding, dtype, mean=None, std=None):
+    """[cls | conv3d(clip) patch tokens | object queries + temporal embedding].  clip: [B, C, T, H, W] (fp32 / bf16) or
+    decoded uint8 frames [B, T, H, W, C].  Without autograd and in bf16 the stem is an implicit GEMM
+    (csrc/patch_embed_tc.cu); with autograd (the weight gradient needs the im2col matrix) or in the fp32 parity mode it is
+    svit_im2col3d + svit_gemm."""
+    kernel, stride, padding = tuple(kernel), tuple(stride), tuple(padding)
+    Cin = clip.shape[-1] if clip.dtype == torch.uint8 else clip.shape[1]
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (w, b, cls, queries, pos_t))
+    if (not needs_grad and dtype == torch.bfloat16 and _state.get("implicit_patch_embed", True)
+            and _lib.lib().svit_patch_embed_s2d_supported(Cin, *kernel, *stride, *padding, w.shape[0])):
+        return _patch_embed_implicit(clip, w, b, cls, queries, pos_t, kernel, stride, padding, mean, std)
+    if clip.dtype == torch.uint8:
+        clip = normalize_u8(clip, mean, std, torch.float32 if dtype == torch.float32 else torch.bfloat16)
+    return _PatchEmbedTokens.apply(clip, w, b, cls, queries, pos_t, kernel, stride, padding, dtype)
 
 
 class _GatherClsObj(torch.autograd.Function):
