@@ -52,6 +52,16 @@ int svit_pool_ln_bwd(const void* in, int64_t in_batch_stride, int64_t in_tok_str
                      const float* conv_w, const float* tap_frac, const float* gamma, const void* dout, void* dpre,
                      void* dz, float* dw, float* dgamma, float* dbeta, int B, int h, int T, int H, int W, int O,
                      int stride_hw, float eps, int dtype, void* stream);
+/* Training variants (bf16 only, else SVIT_ENOTSUP): the forward also writes the pre-LayerNorm rows to `pre` (shape of out)
+ * and the backward reads them instead of recomputing the convolution per output token. */
+int svit_pool_ln_fwd_save(const void* in, int64_t in_batch_stride, int64_t in_tok_stride, int64_t in_head_stride,
+                          const float* conv_w, const float* tap_frac, const float* gamma, const float* beta, void* out,
+                          void* pre, int B, int h, int T, int H, int W, int O, int stride_hw, float eps, int dtype,
+                          void* stream);
+int svit_pool_ln_bwd_saved(const void* in, int64_t in_batch_stride, int64_t in_tok_stride, int64_t in_head_stride,
+                           const float* conv_w, const float* tap_frac, const float* gamma, const void* dout,
+                           const void* pre, void* dpre, void* dz, float* dw, float* dgamma, float* dbeta, int B, int h,
+                           int T, int H, int W, int O, int stride_hw, float eps, int dtype, void* stream);
 
 /* ---- skip-path attention_pool with MaxPool3d k(1,3,3) s(1,s,s) p(0,1,1): attention.py:503-505,549-555,562-564.
  * x [B, 1+T*H*W+O, C] -> y [B, 1+T*Ho*Wo+O, C]; cls and object rows are copied. stride_hw must be >= 2. */

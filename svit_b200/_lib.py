@@ -58,6 +58,8 @@ PROTOTYPES = {
     "svit_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i64, C.c_int, f32, C.c_int, vp],
     "svit_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp],
     "svit_pool_ln_fwd": [vp, i64, i64, i64, vp, vp, vp, vp, vp] + [C.c_int] * 7 + [f32, C.c_int, vp],
+    "svit_pool_ln_fwd_save": [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp] + [C.c_int] * 7 + [f32, C.c_int, vp],
+    "svit_pool_ln_bwd_saved": [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp] + [C.c_int] * 7 + [f32, C.c_int, vp],
     "svit_pool_ln_bwd": [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp] + [C.c_int] * 7 + [f32, C.c_int, vp],
     "svit_skip_maxpool_fwd": [vp, vp] + [C.c_int] * 8 + [vp],
     "svit_skip_maxpool_bwd": [vp, vp, vp] + [C.c_int] * 8 + [vp],

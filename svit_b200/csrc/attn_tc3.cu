@@ -416,14 +416,33 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       {
         const float2 negm = make_float2(-m_ref, -m_ref);
         const float2* yy = reinterpret_cast<const float2*>(y);
+        // columns of this half that hold real keys: only the last tile is ragged (Nk = 457 leaves 9 of 64).  Padding
+        // keys carry the -1e30 mask entry, so their probability is exactly 0: write the zero without spending the
+        // special-function unit on it (the loop is MUFU-bound; 55 of 512 exponentials per row at Nk = 457).
+        const int nv = p.Nk - j * BN - half * HB;
+        if (nv >= HB) {
 #pragma unroll
-        for (int c = 0; c < HB / 2; ++c) {
-          const float2 d = tc::fma2(yy[c], c1c1, negm);
-          float2 e;
-          e.x = tc::ex2_approx(d.x);
-          e.y = tc::ex2_approx(d.y);
-          sum2 = tc::add2(sum2, e);
-          pk[c] = pack2(e.x, e.y);
+          for (int c = 0; c < HB / 2; ++c) {
+            const float2 d = tc::fma2(yy[c], c1c1, negm);
+            float2 e;
+            e.x = tc::ex2_approx(d.x);
+            e.y = tc::ex2_approx(d.y);
+            sum2 = tc::add2(sum2, e);
+            pk[c] = pack2(e.x, e.y);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < HB / 2; ++c) {
+            pk[c] = 0u;
+            if (2 * c < nv) {  // warp-uniform
+              const float2 d = tc::fma2(yy[c], c1c1, negm);
+              float2 e;
+              e.x = tc::ex2_approx(d.x);
+              e.y = 2 * c + 1 < nv ? tc::ex2_approx(d.y) : 0.f;
+              sum2 = tc::add2(sum2, e);
+              pk[c] = pack2(e.x, e.y);
+            }
+          }
         }
       }
       l += sum2.x + sum2.y;

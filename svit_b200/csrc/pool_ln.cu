@@ -277,14 +277,14 @@ __global__ void __launch_bounds__(256) pool_ln_bwd_in_kernel(const T* __restrict
 
 int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const float* conv_w,
                           const float* tap_frac, const float* gamma, const float* beta, void* out, int B, int h, int T,
-                          int H, int W, int O, int s, float eps, cudaStream_t st);  // pool_ln_tiled.cu
+                          int H, int W, int O, int s, float eps, cudaStream_t st, void* pre);  // pool_ln_tiled.cu
 
 int svit_pool_ln_bwd_bf16_supported(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const void* dout,
                                     const void* dpre, const void* dz);  // pool_ln_bwd_bf16.cu
 int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const float* conv_w,
                           const float* tap_frac, const float* gamma, const void* dout, void* dpre, void* dz, float* dw,
                           float* dgamma, float* dbeta, int B, int h, int T, int H, int W, int O, int s, float eps,
-                          cudaStream_t st);
+                          cudaStream_t st, const void* pre);
 
 static int make_geom(PoolGeom& g, int B, int h, int T, int H, int W, int O, int s, int64_t in_bs, int64_t in_ts,
                      int64_t in_hs) {
@@ -316,7 +316,7 @@ int svit_pool_ln_fwd(const void* in, int64_t in_batch_stride, int64_t in_tok_str
   if (dtype == SVIT_BF16 && in_batch_stride % 2 == 0 && in_tok_stride % 2 == 0 && in_head_stride % 2 == 0 &&
       (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0)
     return svit_pool_ln_fwd_bf16(in, in_batch_stride, in_tok_stride, in_head_stride, conv_w, tap_frac, gamma, beta, out,
-                                 B, h, T, H, W, O, stride_hw, eps, st);
+                                 B, h, T, H, W, O, stride_hw, eps, st, nullptr);
   if (dtype == SVIT_F32)
     pool_ln_fwd_kernel<float><<<pool_grid(tokens), 256, 0, st>>>((const float*)in, g, conv_w, tap_frac, gamma, beta, (float*)out, eps);
   else if (dtype == SVIT_BF16)
@@ -342,7 +342,7 @@ int svit_pool_ln_bwd(const void* in, int64_t in_batch_stride, int64_t in_tok_str
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SVIT_BF16 && svit_pool_ln_bwd_bf16_supported(in, in_batch_stride, in_tok_stride, in_head_stride, dout, dpre, dz))
     return svit_pool_ln_bwd_bf16(in, in_batch_stride, in_tok_stride, in_head_stride, conv_w, tap_frac, gamma, dout, dpre,
-                                 dz, dw, dgamma, dbeta, B, h, T, H, W, O, stride_hw, eps, st);
+                                 dz, dw, dgamma, dbeta, B, h, T, H, W, O, stride_hw, eps, st, nullptr);
   int g1 = pool_grid(tok_out);
   if (g1 > svit_num_sms() * 2) g1 = svit_num_sms() * 2;
   if (dtype == SVIT_F32) {
@@ -356,6 +356,41 @@ int svit_pool_ln_bwd(const void* in, int64_t in_batch_stride, int64_t in_tok_str
   }
   SVIT_CHECK_LAUNCH();
   return 0;
+}
+
+// Training variants (bf16): the forward also writes the pre-LayerNorm rows (`pre`, same shape as out) and the backward
+// reads them instead of recomputing the 27-tap convolution per output token (a third of the pooling backward).
+int svit_pool_ln_fwd_save(const void* in, int64_t in_batch_stride, int64_t in_tok_stride, int64_t in_head_stride,
+                          const float* conv_w, const float* tap_frac, const float* gamma, const float* beta, void* out,
+                          void* pre, int B, int h, int T, int H, int W, int O, int stride_hw, float eps, int dtype,
+                          void* stream) {
+  PoolGeom g;
+  int rc = make_geom(g, B, h, T, H, W, O, stride_hw, in_batch_stride, in_tok_stride, in_head_stride);
+  if (rc) return rc;
+  if (!pre) return SVIT_EINVAL;
+  if (dtype != SVIT_BF16 || in_batch_stride % 2 || in_tok_stride % 2 || in_head_stride % 2 ||
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(pre)) & 15))
+    return SVIT_ENOTSUP;
+  if ((int64_t)B * h * (1 + (int64_t)T * g.Ho * g.Wo + O) == 0) return 0;
+  return svit_pool_ln_fwd_bf16(in, in_batch_stride, in_tok_stride, in_head_stride, conv_w, tap_frac, gamma, beta, out, B, h,
+                               T, H, W, O, stride_hw, eps, (cudaStream_t)stream, pre);
+}
+
+int svit_pool_ln_bwd_saved(const void* in, int64_t in_batch_stride, int64_t in_tok_stride, int64_t in_head_stride,
+                           const float* conv_w, const float* tap_frac, const float* gamma, const void* dout,
+                           const void* pre, void* dpre, void* dz, float* dw, float* dgamma, float* dbeta, int B, int h,
+                           int T, int H, int W, int O, int stride_hw, float eps, int dtype, void* stream) {
+  PoolGeom g;
+  int rc = make_geom(g, B, h, T, H, W, O, stride_hw, in_batch_stride, in_tok_stride, in_head_stride);
+  if (rc) return rc;
+  if (!pre) return SVIT_EINVAL;
+  if (dtype != SVIT_BF16 ||
+      !svit_pool_ln_bwd_bf16_supported(in, in_batch_stride, in_tok_stride, in_head_stride, dout, dpre, dz) ||
+      (reinterpret_cast<uintptr_t>(pre) & 7))
+    return SVIT_ENOTSUP;
+  if ((int64_t)B * h * (1 + (int64_t)T * g.Ho * g.Wo + O) == 0) return 0;
+  return svit_pool_ln_bwd_bf16(in, in_batch_stride, in_tok_stride, in_head_stride, conv_w, tap_frac, gamma, dout, dpre, dz,
+                               dw, dgamma, dbeta, B, h, T, H, W, O, stride_hw, eps, (cudaStream_t)stream, pre);
 }
 
 }  // extern "C"

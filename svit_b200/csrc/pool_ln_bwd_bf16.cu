@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
                                                            const float* __restrict__ w, const float* __restrict__ frac,
                                                            const float* __restrict__ gamma, const bf16* __restrict__ dout,
                                                            bf16* __restrict__ dpre, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, float eps) {
+                                                           float* __restrict__ dbeta, float eps,
+                                                           const bf16* __restrict__ pre) {
   __shared__ __align__(16) float sw[TAPS * PD];
   __shared__ __align__(16) float sweff[PD];
   __shared__ float sred[2 * PD];
@@ -83,7 +84,9 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     float dy[4];
     unpack4(act ? __ldg(reinterpret_cast<const uint2*>(dout + i * PD + c0)) : make_uint2(0, 0), dy);
-    if (act) {
+    if (act && pre) {  // the forward saved the pre-LayerNorm row: no convolution to recompute
+      unpack4(__ldg(reinterpret_cast<const uint2*>(pre + i * PD + c0)), v);
+    } else if (act) {
       if (tok == 0) {
         unpack4(__ldg(reinterpret_cast<const uint2*>(zin)), v);
       } else if (tok > Lo) {
@@ -358,7 +361,7 @@ int svit_pool_ln_bwd_bf16_supported(const void* in, int64_t in_bs, int64_t in_ts
 int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const float* conv_w,
                           const float* tap_frac, const float* gamma, const void* dout, void* dpre, void* dz, float* dw,
                           float* dgamma, float* dbeta, int B, int h, int T, int H, int W, int O, int s, float eps,
-                          cudaStream_t st) {
+                          cudaStream_t st, const void* pre) {
   Geom g;
   g.B = B; g.h = h; g.T = T; g.H = H; g.W = W; g.O = O; g.s = s;
   g.Ho = (H - 1) / s + 1;
@@ -374,7 +377,8 @@ int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
     return (unsigned)(need < want ? need : want);
   };
   pool_bwd_pre_kernel<<<dim3(gx(Nout), BH), 256, 0, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma,
-                                                                (const bf16*)dout, (bf16*)dpre, dgamma, dbeta, eps);
+                                                                (const bf16*)dout, (bf16*)dpre, dgamma, dbeta, eps,
+                                                                (const bf16*)pre);
   SVIT_CHECK_LAUNCH();
   int64_t chunk = ceil_div64(tok_out, (int64_t)svit_num_sms() * 8);  // ~8 CTAs (72 warps) per SM: latency-bound loop
   if (chunk < 32) chunk = 32;

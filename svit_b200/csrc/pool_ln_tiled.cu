@@ -111,7 +111,7 @@ constexpr int MK_PITCH = 50;  // staging token pitch in float2: conflict-free 16
 // LayerNorm + store of the first `ntok` staged tokens (pre-LN fp32, MK_PITCH float2 per token); four lanes per token,
 // 24 channels per lane, packed fp32x2 arithmetic.
 __device__ __forceinline__ void mk_ln_flush(const float2* stg, const long long* stg_tok, const float* aff, int ntok, float eps,
-                                            bf16* __restrict__ obase, int tid) {
+                                            bf16* __restrict__ obase, int tid, bf16* __restrict__ pre_base = nullptr) {
   const int tok = tid >> 2, q = tid & 3;
   if ((tid & ~31) >= ntok * 4) return;  // whole warp idle
   const bool live = tok < ntok;
@@ -131,6 +131,16 @@ __device__ __forceinline__ void mk_ln_flush(const float2* stg, const long long* 
   sum += __shfl_xor_sync(0xffffffffu, sum, 2);
   const float nmean = sum * (-1.f / PD);
   const float2 nm2 = make_float2(nmean, nmean);
+  const long long gtok = live ? stg_tok[tok] : -1;
+  if (pre_base && gtok >= 0) {  // training: the pre-LayerNorm row for the backward
+    uint32_t pw[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pw[i] = pack2(x[i].x, x[i].y);
+    uint4* pd = reinterpret_cast<uint4*>(pre_base + gtok * PD + q * 24);
+    pd[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+    pd[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+    pd[2] = make_uint4(pw[8], pw[9], pw[10], pw[11]);
+  }
   float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
@@ -141,7 +151,6 @@ __device__ __forceinline__ void mk_ln_flush(const float2* stg, const long long* 
   var += __shfl_xor_sync(0xffffffffu, var, 1);
   var += __shfl_xor_sync(0xffffffffu, var, 2);
   const float rstd = rsqrtf(var * (1.f / PD) + eps);
-  const long long gtok = live ? stg_tok[tok] : -1;
   if (gtok < 0) return;
   const float2 r2 = make_float2(rstd, rstd);
   const float4* gm = reinterpret_cast<const float4*>(aff + q * 24);
@@ -208,11 +217,13 @@ template <int S, int SPR> struct MkCfg {
   static constexpr int SMEM = OFF_RED + 2 * 24 * 16 * 4;
 };
 
-template <int S, int SPR, bool PERSIST>
+// SAVE (training): the pre-LayerNorm rows are written to `pre` as well (same layout as out), so that the backward does
+// not have to recompute the convolution.
+template <int S, int SPR, bool PERSIST, bool SAVE>
 __global__ void __launch_bounds__(MK_THREADS, 2)
 pool_ln_march_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ in, Geom g, const float* __restrict__ w,
                      const float* __restrict__ frac, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     bf16* __restrict__ out, float eps, int tiles, int ncols) {
+                     bf16* __restrict__ out, float eps, int tiles, int ncols, bf16* __restrict__ pre) {
   using C = MkCfg<S, SPR>;
   constexpr int IW = C::IW, XN = C::XN, SW = C::SW;
   constexpr int NV = SW > 4 ? 16 : 8;  // LayerNorm butterfly width: token sums in v[0, NV/2), sums of squares in v[NV/2, NV)
@@ -303,6 +314,7 @@ pool_ln_march_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __res
   // per column: this thread's output tokens are row ho0 + srow, columns wo0 + scol + o for o < nvalid; optr walks the planes
   int nvalid = 0;
   uint32_t* optr = nullptr;
+  uint32_t* pptr = nullptr;  // SAVE: walks `pre` like optr walks `out`
   int slot = 0, parity = 0;  // ring position of the plane being consumed
 
   float2 acc[3][SW];
@@ -349,6 +361,12 @@ pool_ln_march_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __res
     const float var = fmaxf(fmaf(sq, 1.f / PD, -mean * mean), 0.f);
     const float sc = rsqrtf(var + eps);
     const float sh = -mean * sc;
+    if (SAVE) {
+#pragma unroll
+      for (int o = 0; o < SW; ++o)
+        if (o < nvalid) pptr[o * (PD / 2)] = pack2(set[o].x, set[o].y);
+      pptr += plane_words;
+    }
     uint32_t pk[SW];
 #pragma unroll
     for (int o = 0; o < SW; ++o) {
@@ -441,7 +459,9 @@ pool_ln_march_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __res
       const int wo0 = (tile % tiles_w) * C::TW, ho0 = (tile / tiles_w) * C::ROWS;
       nvalid = min(SW, min(C::TW - scol, g.Wo - (wo0 + scol)));
       if (ho0 + srow >= g.Ho || nvalid < 0) nvalid = 0;
-      optr = reinterpret_cast<uint32_t*>(out + ((int64_t)bh * Nout + 1 + (int64_t)(ho0 + srow) * g.Wo + wo0 + scol) * PD) + wd;
+      const int64_t row0 = ((int64_t)bh * Nout + 1 + (int64_t)(ho0 + srow) * g.Wo + wo0 + scol) * PD;
+      optr = reinterpret_cast<uint32_t*>(out + row0) + wd;
+      if (SAVE) pptr = reinterpret_cast<uint32_t*>(pre + row0) + wd;
     }
     if (g.T == 1) {
       step(R0{}, EONLY{}, 0);
@@ -506,7 +526,7 @@ pool_ln_march_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __res
           if (ww == 0) stg_tok[k] = r == 0 ? 0 : Lo + r;
         }
         __syncthreads();
-        mk_ln_flush(stg, stg_tok, aff, n, eps, obase, threadIdx.x);
+        mk_ln_flush(stg, stg_tok, aff, n, eps, obase, threadIdx.x, SAVE ? pre + (int64_t)item * Nout * PD : nullptr);
       }
     }
   }
@@ -518,7 +538,7 @@ pool_ln_march_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __res
 __global__ void __launch_bounds__(256, 4)
 pool_ln_direct_kernel(const bf16* __restrict__ in, Geom g, const float* __restrict__ w, const float* __restrict__ frac,
                       const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ out, float eps,
-                      int mode) {
+                      int mode, bf16* __restrict__ pre) {
   __shared__ float sw[TAPS * PD];
   __shared__ float sweff[PD];
   for (int i = threadIdx.x; i < PD * TAPS; i += blockDim.x) sw[(i % TAPS) * PD + i / TAPS] = w[i];
@@ -589,6 +609,11 @@ pool_ln_direct_kernel(const bf16* __restrict__ in, Geom g, const float* __restri
       }
     }
     uint32_t* dst = reinterpret_cast<uint32_t*>(out + (((int64_t)b * g.h + head) * Nout + tok) * PD);
+    if (pre) {  // training: pre-LayerNorm row for the backward
+      uint32_t* pd = reinterpret_cast<uint32_t*>(pre + (((int64_t)b * g.h + head) * Nout + tok) * PD);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) pd[l16 + 16 * j] = pack2(v[2 * j], v[2 * j + 1]);
+    }
     ln_store(v, gm, bt, eps, dst, l16);
   }
 }
@@ -603,9 +628,9 @@ extern "C" int svit_debug_pool_timeline(void* device_buffer) {
 #endif
 
 namespace {
-template <int SV, int SPRV, bool PERSIST>
+template <int SV, int SPRV, bool PERSIST, bool SAVE>
 int launch_march(const void* in, int64_t in_bs, int64_t in_ts, const Geom& g, const float* conv_w, const float* tap_frac,
-                 const float* gamma, const float* beta, void* out, float eps, cudaStream_t st) {
+                 const float* gamma, const float* beta, void* out, float eps, cudaStream_t st, void* pre) {
   using C = MkCfg<SV, SPRV>;
   // 5-D view of the patch tokens: (head*96 + c, w, h, t, b); the box of a CTA is (96, IW, IH, 1, 1), zero fill outside
   svit_tmap_encode_fn enc = svit_get_tmap_encode();
@@ -620,7 +645,7 @@ int launch_march(const void* in, int64_t in_bs, int64_t in_ts, const Geom& g, co
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return SVIT_EINVAL;
-  auto kern = pool_ln_march_kernel<SV, SPRV, PERSIST>;
+  auto kern = pool_ln_march_kernel<SV, SPRV, PERSIST, SAVE>;
   static SvitDevOnce configured;
   if (configured.need()) {
     SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -632,7 +657,7 @@ int launch_march(const void* in, int64_t in_bs, int64_t in_ts, const Geom& g, co
   int64_t grid = PERSIST ? (int64_t)svit_num_sms() * 2 : ncols;
   if (grid > ncols) grid = ncols;
   kern<<<(unsigned)grid, MK_THREADS, C::SMEM, st>>>(tm, (const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps,
-                                                    tiles, (int)ncols);
+                                                    tiles, (int)ncols, (bf16*)pre);
   SVIT_CHECK_LAUNCH();
   return 0;
 }
@@ -641,7 +666,7 @@ int launch_march(const void* in, int64_t in_bs, int64_t in_ts, const Geom& g, co
 // bf16 fast path of svit_pool_ln_fwd (pool_ln.cu dispatches here).  Requires 4-byte aligned token slices.
 int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const float* conv_w,
                           const float* tap_frac, const float* gamma, const float* beta, void* out, int B, int h, int T,
-                          int H, int W, int O, int s, float eps, cudaStream_t st) {
+                          int H, int W, int O, int s, float eps, cudaStream_t st, void* pre) {
   Geom g;
   g.B = B; g.h = h; g.T = T; g.H = H; g.W = W; g.O = O; g.s = s;
   g.Ho = (H - 1) / s + 1; g.Wo = (W - 1) / s + 1;
@@ -657,9 +682,11 @@ int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
     const bool wide = s == 1 && g.Wo > 7;
     const int64_t cols_s2 = (int64_t)((g.Wo + 6) / 7) * ((g.Ho + 3) / 4) * h * B;
     const bool persist = mode < 0 ? (s == 2 && cols_s2 >= (int64_t)sms * 12) : mode != 0;
-#define MARCH(SV, SPRV) \
-  (persist ? launch_march<SV, SPRV, true>(in, in_bs, in_ts, g, conv_w, tap_frac, gamma, beta, out, eps, st) \
-           : launch_march<SV, SPRV, false>(in, in_bs, in_ts, g, conv_w, tap_frac, gamma, beta, out, eps, st))
+#define MARCH(SV, SPRV)                                                                                               \
+  (pre ? (persist ? launch_march<SV, SPRV, true, true>(in, in_bs, in_ts, g, conv_w, tap_frac, gamma, beta, out, eps, st, pre)    \
+                  : launch_march<SV, SPRV, false, true>(in, in_bs, in_ts, g, conv_w, tap_frac, gamma, beta, out, eps, st, pre)) \
+       : (persist ? launch_march<SV, SPRV, true, false>(in, in_bs, in_ts, g, conv_w, tap_frac, gamma, beta, out, eps, st, nullptr) \
+                  : launch_march<SV, SPRV, false, false>(in, in_bs, in_ts, g, conv_w, tap_frac, gamma, beta, out, eps, st, nullptr)))
     if (s == 2) return MARCH(2, 2);
     if (!wide) return MARCH(1, 1);
     return MARCH(1, 2);
@@ -669,7 +696,7 @@ int svit_pool_ln_fwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   int64_t blocks = (total + 15) / 16;
   if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
   if (blocks < 1) blocks = 1;
-  pool_ln_direct_kernel<<<(unsigned)blocks, 256, 0, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps, 0);
+  pool_ln_direct_kernel<<<(unsigned)blocks, 256, 0, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma, beta, (bf16*)out, eps, 0, (bf16*)pre);
   SVIT_CHECK_LAUNCH();
   return 0;
 }

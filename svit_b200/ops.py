@@ -92,7 +92,8 @@ def cast_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 
 _FAMILY = {"svit_gemm": "gemm", "svit_attn_fwd": "attention", "svit_attn_bwd": "attention_bwd",
-           "svit_pool_ln_fwd": "pool_ln", "svit_pool_ln_bwd": "pool_ln_bwd", "svit_layernorm_fwd": "layernorm",
+           "svit_pool_ln_fwd": "pool_ln", "svit_pool_ln_fwd_save": "pool_ln", "svit_pool_ln_bwd": "pool_ln_bwd",
+           "svit_pool_ln_bwd_saved": "pool_ln_bwd", "svit_layernorm_fwd": "layernorm",
            "svit_layernorm_bwd": "layernorm_bwd", "svit_skip_maxpool_fwd": "skip_pool", "svit_im2col3d": "im2col", "svit_s2d_clip": "im2col",
            "svit_patch_embed_s2d": "gemm"}
 _prof = None
@@ -412,7 +413,7 @@ class _QKVPool(torch.autograd.Function):
     (attention.py:368-388), reading the packed [B, N, 3, h, 96] GEMM output in place."""
 
     @staticmethod
-    def forward(ctx, qkv, thw, O, stride_q, stride_kv, wq, gq, bq, wk, gk, bk, wv, gv, bv):
+    def forward(ctx, qkv, thw, O, stride_q, stride_kv, wq, gq, bq, wk, gk, bk, wv, gv, bv, grad_mode):
         _chk(qkv, "qkv_pool")
         qkv = qkv.contiguous()
         B, N, D3 = qkv.shape
@@ -426,15 +427,27 @@ class _QKVPool(torch.autograd.Function):
             Ho, Wo = pooled_hw(H, s), pooled_hw(W, s)
             out = torch.empty(B, h, 1 + T * Ho * Wo + O, HEAD_DIM, dtype=qkv.dtype, device=qkv.device)
             prepared.append((out, _f32(w).reshape(HEAD_DIM, 27), _f32(g), _f32(b), tap_fractions(s, qkv.device), s))
+        # training (bf16): the forward also writes the pre-LayerNorm rows, the backward reads them instead of recomputing
+        # the convolution per output token (svit_pool_ln_fwd_save / svit_pool_ln_bwd_saved)
+        save_pre = grad_mode and qkv.dtype == torch.bfloat16 and _state.get("pool_save_pre", True)
+        pres = [torch.empty_like(p_[0]) if save_pre else None for p_ in prepared]
         with _Fork(3) as fork:
             for which, (out, w32, g32, b32, frac, s) in enumerate(prepared):
                 with fork.branch(which):
-                    _call("svit_pool_ln_fwd", qkv.data_ptr() + which * h * HEAD_DIM * qkv.element_size(), N * D3, D3,
-                          HEAD_DIM, w32.data_ptr(), frac.data_ptr(), g32.data_ptr(), b32.data_ptr(), out.data_ptr(),
-                          B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream(),
-                          tag=f"[{'qkv'[which]} B{B} h{h} {T}x{H}x{W} s{s}]" if _prof is not None else None)
+                    src = qkv.data_ptr() + which * h * HEAD_DIM * qkv.element_size()
+                    tag = f"[{'qkv'[which]} B{B} h{h} {T}x{H}x{W} s{s}]" if _prof is not None else None
+                    if save_pre:
+                        _call("svit_pool_ln_fwd_save", src, N * D3, D3, HEAD_DIM, w32.data_ptr(), frac.data_ptr(),
+                              g32.data_ptr(), b32.data_ptr(), out.data_ptr(), pres[which].data_ptr(), B, h, T, H, W, O, s,
+                              LN_EPS, _dt(qkv), _stream(), tag=tag)
+                    else:
+                        _call("svit_pool_ln_fwd", src, N * D3, D3, HEAD_DIM, w32.data_ptr(), frac.data_ptr(), g32.data_ptr(),
+                              b32.data_ptr(), out.data_ptr(), B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream(), tag=tag)
                 outs.append(out)
                 saved += [w32, g32]
+        if save_pre:
+            saved += pres
+        ctx.save_pre = save_pre
         ctx.save_for_backward(qkv, *saved)
         ctx.geom = (B, N, h, T, H, W, O, stride_q, stride_kv)
         ctx.wshape = wq.shape
@@ -457,17 +470,24 @@ class _QKVPool(torch.autograd.Function):
                 dw, dg, db = acc[which, :HEAD_DIM * 27], acc[which, HEAD_DIM * 27:HEAD_DIM * 28], acc[which, HEAD_DIM * 28:]
                 off = which * h * HEAD_DIM * qkv.element_size()
                 with fork.branch(which):
-                    _call("svit_pool_ln_bwd", qkv.data_ptr() + off, N * D3, D3, HEAD_DIM, w32.data_ptr(),
-                          fracs[which].data_ptr(), g32.data_ptr(), douts[which].data_ptr(), dpres[which].data_ptr(),
-                          dqkv.data_ptr() + off, dw.data_ptr(), dg.data_ptr(), db.data_ptr(), B, h, T, H, W, O, s, LN_EPS,
-                          _dt(qkv), _stream())
+                    if ctx.save_pre:
+                        _call("svit_pool_ln_bwd_saved", qkv.data_ptr() + off, N * D3, D3, HEAD_DIM, w32.data_ptr(),
+                              fracs[which].data_ptr(), g32.data_ptr(), douts[which].data_ptr(), saved[6 + which].data_ptr(),
+                              dpres[which].data_ptr(), dqkv.data_ptr() + off, dw.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                              B, h, T, H, W, O, s, LN_EPS, _dt(qkv), _stream())
+                    else:
+                        _call("svit_pool_ln_bwd", qkv.data_ptr() + off, N * D3, D3, HEAD_DIM, w32.data_ptr(),
+                              fracs[which].data_ptr(), g32.data_ptr(), douts[which].data_ptr(), dpres[which].data_ptr(),
+                              dqkv.data_ptr() + off, dw.data_ptr(), dg.data_ptr(), db.data_ptr(), B, h, T, H, W, O, s,
+                              LN_EPS, _dt(qkv), _stream())
                 grads += [dw.reshape(ctx.wshape), dg, db]
-        return (dqkv, None, None, None, None, *grads)
+        return (dqkv, None, None, None, None, *grads, None)
 
 
 def qkv_pool(qkv, thw, O, stride_q, stride_kv, pq, nq, pk, nk, pv, nv):
     """pq/pk/pv: conv weights [96,1,3,3,3]; nq/nk/nv: (gamma, beta)."""
-    return _QKVPool.apply(qkv, tuple(thw), O, stride_q, stride_kv, pq, nq[0], nq[1], pk, nk[0], nk[1], pv, nv[0], nv[1])
+    return _QKVPool.apply(qkv, tuple(thw), O, stride_q, stride_kv, pq, nq[0], nq[1], pk, nk[0], nk[1], pv, nv[0], nv[1],
+                          torch.is_grad_enabled())
 
 
 class _SkipPool(torch.autograd.Function):
