@@ -104,8 +104,19 @@ typedef struct svit_gemm_args {
   /* same two-level split for A: A + (i / a_inner)*strideA + (i % a_inner)*strideA_inner when a_inner > 1 */
   int64_t a_inner, strideA_inner;
   float alpha;               /* accumulator scale applied before the bias; 0 is read as 1 (tcgen05 path only) */
+  /* LayerNorm folded into the GEMM (inference; tcgen05 TMA-store kernel only, else SVIT_ENOTSUP; K-major B, no
+   * residual / gelu_pre / sample_scale): A holds the UN-normalised rows x, B the weight scaled by gamma
+   * (W' = W diag(gamma)), ln_stats [M, 2] = (mean, rstd) of every row (svit_row_stats), ln_colsum [N / 2][4] the
+   * interleaved table (c[2i], c[2i+1], b'[2i], b'[2i+1]) with c[n] = sum_k W'[n, k] and b' = bias + W beta (`bias` itself
+   * is ignored).  The epilogue computes rstd * (acc - mean * c[n]) + b'[n] = LayerNorm(x) W^T + bias
+   * (attention.py:558-561, 566-567). */
+  const float* ln_stats;
+  const float* ln_colsum;
 } svit_gemm_args;
 int svit_gemm(const svit_gemm_args* args, void* stream);
+/* stats[m] = (mean, 1 / sqrt(var + eps)) of row m of x [M, C] (fp32 pair per row): the LayerNorm statistics a folded
+ * GEMM needs (half the traffic of a LayerNorm pass: the rows are read, nothing is written back) */
+int svit_row_stats(const void* x, float* stats, int64_t M, int C, float eps, int dtype, void* stream);
 /* out[n] += sum_m x[m,n]  (bias gradients) */
 int svit_colsum(const void* x, float* out, int64_t M, int N, int64_t ld, int dtype, void* stream);
 

@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("dtype", i32), ("out_dtype", i32), ("impl", i32),
         ("batch", i64), ("strideA", i64), ("strideB", i64), ("strideC", i64), ("b_inner", i64), ("strideB_inner", i64),
         ("a_inner", i64), ("strideA_inner", i64), ("alpha", f32),
+        ("ln_stats", vp), ("ln_colsum", vp),
     ]
 
 
@@ -55,6 +56,7 @@ class AttnArgs(C.Structure):
 PROTOTYPES = {
     "svit_abi_version": [],
     "svit_destroy": [],
+    "svit_row_stats": [vp, vp, i64, C.c_int, f32, C.c_int, vp],
     "svit_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i64, C.c_int, f32, C.c_int, vp],
     "svit_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp],
     "svit_pool_ln_fwd": [vp, i64, i64, i64, vp, vp, vp, vp, vp] + [C.c_int] * 7 + [f32, C.c_int, vp],

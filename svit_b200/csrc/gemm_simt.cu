@@ -217,7 +217,7 @@ int svit_gemm(const svit_gemm_args* a, void* stream) {
     return svit_gemm_tc(a, st);
   }
   if (a->impl == 0 && svit_gemm_tc_supported(a)) return svit_gemm_tc(a, st);
-  if (a->batch > 1 || (a->alpha != 0.f && a->alpha != 1.f)) return SVIT_ENOTSUP;  // tcgen05-only features
+  if (a->batch > 1 || (a->alpha != 0.f && a->alpha != 1.f) || a->ln_stats) return SVIT_ENOTSUP;  // tcgen05-only features
   return gemm_simt(a, st);
 }
 

@@ -455,6 +455,7 @@ int svit_gemm_tc_tma(const svit_gemm_args* a, cudaStream_t st);
 int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st) {
   const bool plain_scale = a->alpha == 0.f || a->alpha == 1.f;
   if (a->batch <= 1 && plain_scale && a->N % 8 == 0 && a->K % 8 == 0 && svit_gemm_tc_tma_supported(a)) return svit_gemm_tc_tma(a, st);
+  if (a->ln_stats) return SVIT_ENOTSUP;  // the folded-LayerNorm epilogue exists in the TMA-store kernel only
   const bool a_mn = a->transA != 0;  // A stored [K, M]
   const bool b_mn = a->transB == 0;  // B stored [K, N]
   if (!a_mn && !b_mn) return dispatch_bn<false, false>(a, st);

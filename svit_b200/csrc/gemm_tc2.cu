@@ -57,6 +57,8 @@ struct Epi {
   int act;
   int aux;  // AUX_*
   int64_t rows_in, rows_out, row_off;
+  const float* ln_stats;   // folded LayerNorm: (mean, rstd) per row of A, or NULL
+  const float* ln_colsum;  // ... and sum_k B[n, k]
   unsigned long long* dbg;  // optional timeline buffer (CTA 0 only): [role][event] = (tag, clock64)
 };
 
@@ -165,7 +167,7 @@ __device__ __forceinline__ int remap_row(const Epi& e, int m) {  // all row coun
 
 // PAIR: clusters of two CTAs compute 256 x BN tiles with tcgen05.mma.cta_group::2 -- each CTA loads its 128 rows of A
 // and HALF of the B tile, the leader CTA issues the MMAs for both, completion is multicast to both CTAs' barriers.
-template <int BN, bool B_MN, int G, bool PAIR>
+template <int BN, bool B_MN, int G, bool PAIR, bool LN>
 __global__ void __launch_bounds__(threads_of(G), 1)
 gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_x, int M,
@@ -325,6 +327,15 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       for (int i = 0; i < PF_DIST; ++i) request_aux();
     }
 
+    // folded LayerNorm: (mean, rstd) of this thread's row, fetched ONE TILE AHEAD (the load misses L1/L2: ~1 us that
+    // must not sit between the accumulator becoming ready and the first box)
+    auto load_stats = [&](int t) {
+      const int m = (t / n_tiles) * TM + (int)crank * BM + r;
+      return __ldg(reinterpret_cast<const float2*>(e.ln_stats) + (m < M ? m : M - 1));
+    };
+    float2 st_next = make_float2(0.f, 1.f);
+    if (LN && unit0 < num_tiles) st_next = load_stats(unit0);
+
     uint32_t cnt = 0;
     int it = 0;
     int tl_n = leader ? 0 : 4096;
@@ -340,6 +351,13 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (e.sample_scale) {
         const int m = m0 + r < M ? m0 + r : M - 1;
         sc = e.sample_scale[m / (int)e.rps];
+      }
+      float2 ln_a = make_float2(1.f, 1.f), ln_b = make_float2(0.f, 0.f);  // rstd, -rstd * mean of this thread's row
+      if (LN) {
+        const float2 st = st_next;
+        if (t + unit_stride < num_tiles) st_next = load_stats(t + unit_stride);
+        ln_a = make_float2(st.y, st.y);
+        ln_b = make_float2(-st.y * st.x, -st.y * st.x);
       }
       int last_c = -1;
       for (int c = g; c < nbox; c += G) last_c = c;
@@ -362,7 +380,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int ncol = n0 + c * BOX_N;
         // bias (L1-resident broadcast loads) while the TMEM load is in flight
         float bv[BOX_N];
-        if (e.bias) {
+        if (!LN && e.bias) {
 #pragma unroll
           for (int j = 0; j < BOX_N; j += 4) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -378,7 +396,17 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (lane == 0) release_tmem(as);
         }
         float2* v2 = reinterpret_cast<float2*>(v);
-        if (e.bias) {
+        if (LN) {
+          // LayerNorm(x) W^T + b = rstd * (x W'^T) + (-rstd * mean) * colsum(W') + b'; e.ln_colsum is the interleaved
+          // table [N / 2][4] = (colsum[2i], colsum[2i + 1], b'[2i], b'[2i + 1]): one 16-byte load per column pair
+#pragma unroll
+          for (int j = 0; j < BOX_N / 2; ++j) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ncol + 2 * j < N) t4 = __ldg(reinterpret_cast<const float4*>(e.ln_colsum) + ((ncol >> 1) + j));
+            v2[j] = fma2(v2[j], ln_a, fma2(ln_b, make_float2(t4.x, t4.y), make_float2(t4.z, t4.w)));
+          }
+        }
+        if (!LN && e.bias) {
           const float2* b2 = reinterpret_cast<const float2*>(bv);
 #pragma unroll
           for (int j = 0; j < BOX_N / 2; ++j) v2[j] = add2(v2[j], b2[j]);
@@ -477,7 +505,7 @@ bool svit_gemm_pair_enabled() {
 unsigned long long* g_timeline = nullptr;
 unsigned long long* svit_gemm_timeline_buffer() { return g_timeline; }
 
-template <int BN, bool B_MN, int G, bool PAIR = false>
+template <int BN, bool B_MN, int G, bool PAIR = false, bool LN = false>
 int launch_g(const svit_gemm_args* a, cudaStream_t st) {
   using L = Cfg<BN, G, PAIR>;
   static_assert(L::STAGES >= 2, "pipeline too shallow");
@@ -496,12 +524,13 @@ int launch_g(const svit_gemm_args* a, cudaStream_t st) {
   e.act = a->act;
   e.aux = a->residual ? AUX_RESIDUAL : (a->gelu_pre ? AUX_GELU_PRE : AUX_NONE);
   e.rows_in = a->rows_in; e.rows_out = a->rows_out; e.row_off = a->row_off;
+  e.ln_stats = a->ln_stats; e.ln_colsum = a->ln_colsum;
   e.dbg = svit_gemm_timeline_buffer();
   tx = tcm;
   if (e.aux == AUX_RESIDUAL) rc = make_box_map(&tx, a->residual, out_rows, (uint64_t)a->N, (uint64_t)a->ldr);
   else if (e.aux == AUX_GELU_PRE) rc = make_box_map(&tx, a->gelu_pre, (uint64_t)a->M, (uint64_t)a->N, (uint64_t)a->ldg);
   if (rc) return rc;
-  auto kern = gemm_tc_tma_kernel<BN, B_MN, G, PAIR>;
+  auto kern = gemm_tc_tma_kernel<BN, B_MN, G, PAIR, LN>;
   static SvitDevOnce configured;
   if (configured.need()) {
     SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -541,6 +570,18 @@ int launch(const svit_gemm_args* a, cudaStream_t st) {
   // (measured on B200: +3..12 % for K >= 768; for K = 384 the extra epilogue coupling of the pair costs more than the
   // halved B traffic saves)
   constexpr bool CAN_PAIR = !B_MN && (BN == 256 || BN == 192 || BN == 128);
+  if constexpr (!B_MN) {
+    if (a->ln_stats) {  // folded LayerNorm (K = the block width: 96 .. 768)
+      if constexpr (CAN_PAIR) {
+        if (svit_gemm_pair_enabled() && a->K >= 768 && a->M >= 2048) {
+          if (a->act == 1) return launch_g<BN, B_MN, 3, true, true>(a, st);
+          return launch_g<BN, B_MN, 2, true, true>(a, st);
+        }
+      }
+      if (a->act == 1 || a->K <= 256) return launch_g<BN, B_MN, 3, false, true>(a, st);
+      return launch_g<BN, B_MN, 2, false, true>(a, st);
+    }
+  }
   if constexpr (CAN_PAIR) {
     if (svit_gemm_pair_enabled() && a->K >= 768 && a->M >= 2048) {
       if (a->act == 1 || a->gelu_pre) return launch_g<BN, B_MN, 3, true>(a, st);
@@ -594,6 +635,9 @@ int svit_gemm_tc_tma_supported(const svit_gemm_args* a) {
   if (a->residual && (a->ldr % 8 || !aligned16(a->residual))) return 0;
   if (a->gelu_pre && (a->ldg % 8 || !aligned16(a->gelu_pre))) return 0;
   if (a->bias && !aligned16(a->bias)) return 0;
+  if (a->ln_stats && (!a->ln_colsum || !aligned16(a->ln_colsum) || (reinterpret_cast<uintptr_t>(a->ln_stats) & 7) || a->N % 2 ||
+                      a->transB == 0 || a->gelu_pre || a->residual || a->sample_scale))
+    return 0;
   if (a->M < BM) return 0;  // tiny problems (heads): the generic kernel is fine
   return 1;
 }

@@ -495,3 +495,124 @@ extern "C" int svit_boxes_crop_flip(const float* boxes_xyxy, float* out_cxcywh, 
   SVIT_CHECK_LAUNCH();
   return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------ row statistics
+// (mean, rstd) per row for a LayerNorm folded into the consuming GEMM (gemm_tc2.cu).  Same work split as
+// layernorm_bf16_kernel (G lanes per row, NQ bf16x4 quads per lane, the row stays in registers between the mean pass and
+// the centred second-moment pass) without the write-back: half the traffic of a LayerNorm pass.
+template <int G, int NQ>
+__global__ void __launch_bounds__(256) row_stats_bf16_kernel(const bf16* __restrict__ x, float2* __restrict__ stats,
+                                                             int64_t rows, float eps) {
+  constexpr int C = 4 * G * NQ;
+  const int lg = threadIdx.x % G;
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
+  const int64_t iters = (rows + ngroups - 1) / ngroups;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t row = group + it * ngroups;
+    const bool ok = row < rows;
+    float v[NQ][4];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      uint2 raw = make_uint2(0u, 0u);
+      if (ok) raw = __ldg(reinterpret_cast<const uint2*>(x + row * C + 4 * (lg + G * q)));
+      unpack4(raw, v[q]);
+      s += v[q][0] + v[q][1] + v[q][2] + v[q][3];
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
+    float qq = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float d = v[q][i] - mean;
+        qq = fmaf(d, d, qq);
+      }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    if (ok && lg == 0) stats[row] = make_float2(mean, rsqrtf(qq * (1.f / C) + eps));
+  }
+}
+
+// generic widths / fp32 rows: warp per row, 16-byte loads (C <= 128 vectors)
+template <typename T>
+__global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x, float2* __restrict__ stats, int64_t M, int C,
+                                                        float eps) {
+  constexpr int V = 16 / sizeof(T);  // elements per 16-byte load
+  const int lane = threadIdx.x & 31;
+  const int nv = C / V;              // vectors per row
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * 8) {
+    const uint4* src = reinterpret_cast<const uint4*>(x + row * C);
+    float v[4][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = lane + 32 * k;
+      if (i < nv) {
+        const uint4 q = __ldg(src + i);
+        if (sizeof(T) == 2) {
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            v[k][2 * u] = __uint_as_float(w[u] << 16);
+            v[k][2 * u + 1] = __uint_as_float(w[u] & 0xffff0000u);
+          }
+        } else {
+          v[k][0] = __uint_as_float(q.x); v[k][1] = __uint_as_float(q.y);
+          v[k][2] = __uint_as_float(q.z); v[k][3] = __uint_as_float(q.w);
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) s += v[k][u];
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float qsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (lane + 32 * k < nv) {
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          const float d = v[k][u] - mean;
+          qsum = fmaf(d, d, qsum);
+        }
+      }
+    }
+    const float var = warp_sum(qsum) / (float)C;
+    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
+  }
+}
+
+extern "C" int svit_row_stats(const void* x, float* stats, int64_t M, int C, float eps, int dtype, void* stream) {
+  if (!x || !stats || M < 0 || C < 1) return SVIT_EINVAL;
+  if (M == 0) return 0;
+  const int V = dtype == SVIT_BF16 ? 8 : 4;
+  if ((dtype != SVIT_BF16 && dtype != SVIT_F32) || C % V || C / V > 128 || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (reinterpret_cast<uintptr_t>(stats) & 7))
+    return SVIT_ENOTSUP;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t cap = (int64_t)svit_num_sms() * 16;
+#define RS_LAUNCH(G, NQ)                                                                                        \
+  {                                                                                                             \
+    int64_t blocks = (M * G + 255) / 256;                                                                       \
+    if (blocks > cap) blocks = cap;                                                                             \
+    row_stats_bf16_kernel<G, NQ><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)x, (float2*)stats, M, eps);     \
+  }
+  if (dtype == SVIT_BF16 && (C == 96 || C == 192 || C == 384 || C == 768)) {
+    if (C == 96) RS_LAUNCH(8, 3)
+    else if (C == 192) RS_LAUNCH(16, 3)
+    else if (C == 384) RS_LAUNCH(32, 3)
+    else RS_LAUNCH(32, 6)
+  } else {
+    int64_t grid = (M + 7) / 8;
+    if (grid > cap) grid = cap;
+    if (dtype == SVIT_BF16) row_stats_kernel<bf16><<<(unsigned)grid, 256, 0, st>>>((const bf16*)x, (float2*)stats, M, C, eps);
+    else row_stats_kernel<float><<<(unsigned)grid, 256, 0, st>>>((const float*)x, (float2*)stats, M, C, eps);
+  }
+#undef RS_LAUNCH
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}

@@ -222,14 +222,18 @@ class MultiScaleAttention(nn.Module):
         self.residual_pooling = residual_pooling
 
     def forward(self, x, thw_shape, residual: Optional[torch.Tensor] = None,
-                sample_scale: Optional[torch.Tensor] = None):
-        """x [B, N, C] -> (y [B, Nq, dim_out], q_shape).  `residual` / `sample_scale` are optional fusion
-        hooks used by MultiScaleBlock: y = residual + sample_scale[b] * proj(attn)."""
+                sample_scale: Optional[torch.Tensor] = None, ln=None):
+        """x [B, N, C] -> (y [B, Nq, dim_out], q_shape).  `residual` / `sample_scale` / `ln` are optional fusion
+        hooks used by MultiScaleBlock: y = residual + sample_scale[b] * proj(attn); `ln = (row statistics,
+        nn.LayerNorm)` means x is the un-normalised input and the LayerNorm is applied inside the qkv GEMM."""
         B, N, _ = x.shape
         T, H, W = thw_shape
         O = N - 1 - T * H * W
         assert O > 0
-        qkv = ops.linear(x, self.qkv.weight, self.qkv.bias)
+        if ln is not None:  # x is the UN-normalised block input; norm1 is folded into the qkv GEMM
+            qkv = ops.linear_ln(x, ln[0], ln[1].weight, ln[1].bias, self.qkv.weight, self.qkv.bias)
+        else:
+            qkv = ops.linear(x, self.qkv.weight, self.qkv.bias)
         q, k, v = ops.qkv_pool(qkv, thw_shape, O, self._sq, self._skv,
                                self.pool_q.weight, (self.norm_q.weight, self.norm_q.bias),
                                self.pool_k.weight, (self.norm_k.weight, self.norm_k.bias),
@@ -333,6 +337,8 @@ class MultiScaleBlock(nn.Module):
     def forward(self, x, thw_shape):
         T, H, W = thw_shape
         O = x.shape[1] - 1 - T * H * W
+        if ops.ln_fold_applicable(x, self.attn.qkv.weight, self.mlp.fc1.weight):
+            return self._forward_folded(x, thw_shape, O)
         x_norm = ops.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         if self.dim != self.dim_out:
             x = ops.linear(x_norm, self.proj.weight, self.proj.bias)  # skip path uses the normalised input (:560-561)
@@ -340,4 +346,22 @@ class MultiScaleBlock(nn.Module):
         x, thw_new = self.attn(x_norm, thw_shape, residual=x_res, sample_scale=self._scale(x))
         x_norm2 = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         x = self.mlp(x_norm2, residual=x, sample_scale=self._scale(x))
+        return x, thw_new
+
+    def _forward_folded(self, x, thw_shape, O):
+        """Inference form of forward(): norm1 lives inside the qkv (and skip-projection) GEMM, norm2 inside fc1
+        -- one statistics pass per LayerNorm instead of a normalised copy of the activations."""
+        st1 = ops.row_stats(x, self.norm1.eps)
+        x_in = x
+        if self.dim != self.dim_out:
+            x = ops.linear_ln(x_in, st1, self.norm1.weight, self.norm1.bias, self.proj.weight, self.proj.bias)
+        x_res = ops.skip_pool(x, thw_shape, O, self._sq)
+        x, thw_new = self.attn(x_in, thw_shape, residual=x_res, sample_scale=self._scale(x), ln=(st1, self.norm1))
+        if not ops.ln_fold_applicable(x, self.mlp.fc1.weight):  # fewer than 128 pooled rows (tiny test geometries)
+            x_norm2 = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+            return self.mlp(x_norm2, residual=x, sample_scale=self._scale(x)), thw_new
+        st2 = ops.row_stats(x, self.norm2.eps)
+        m = self.mlp
+        x = ops.mlp_ln(x, st2, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias,
+                       residual=x, sample_scale=self._scale(x))
         return x, thw_new

@@ -7,6 +7,7 @@ parameters are produced in fp32 regardless of the activation dtype.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -93,7 +94,7 @@ def cast_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 _FAMILY = {"svit_gemm": "gemm", "svit_attn_fwd": "attention", "svit_attn_bwd": "attention_bwd",
            "svit_pool_ln_fwd": "pool_ln", "svit_pool_ln_fwd_save": "pool_ln", "svit_pool_ln_bwd": "pool_ln_bwd",
-           "svit_pool_ln_bwd_saved": "pool_ln_bwd", "svit_layernorm_fwd": "layernorm",
+           "svit_pool_ln_bwd_saved": "pool_ln_bwd", "svit_layernorm_fwd": "layernorm", "svit_row_stats": "layernorm",
            "svit_layernorm_bwd": "layernorm_bwd", "svit_skip_maxpool_fwd": "skip_pool", "svit_im2col3d": "im2col", "svit_s2d_clip": "im2col",
            "svit_patch_embed_s2d": "gemm"}
 _prof = None
@@ -140,8 +141,9 @@ def _call(name, *args, tag=None):
 def gemm(A, B, out, M, N, K, lda, ldb, ldc, transA=0, transB=1, bias=None, residual=None, ldr=0,
          sample_scale=None, rows_per_sample=0, gelu_pre=None, ldg=0, pre_out=None, ldp=0, act=0,
          remap=(0, 0, 0), impl=None, batch=0, strideA=0, strideB=0, strideC=0, b_inner=0, strideB_inner=0,
-         a_inner=0, strideA_inner=0, alpha=0.0):
+         a_inner=0, strideA_inner=0, alpha=0.0, ln_stats=None, ln_colsum=None):
     a = GemmArgs()
+    a.ln_stats, a.ln_colsum = _p(ln_stats), _p(ln_colsum)
     a.a_inner, a.strideA_inner, a.alpha = a_inner, strideA_inner, alpha
     a.batch, a.strideA, a.strideB, a.strideC, a.b_inner, a.strideB_inner = batch, strideA, strideB, strideC, b_inner, strideB_inner
     a.A, a.B, a.C = A.data_ptr(), B.data_ptr(), out.data_ptr()
@@ -311,6 +313,93 @@ class _LayerNorm(torch.autograd.Function):
 
 def layer_norm(x, gamma, beta, eps=LN_EPS):
     return _LayerNorm.apply(x, gamma, beta, eps, torch.is_grad_enabled())
+
+
+# LayerNorm folded into the consuming GEMM (inference; attention.py:558-561, 566-567):
+#   LayerNorm(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (b + W beta),   W' = W diag(gamma)
+# The normalised activation never exists in HBM: one statistics pass reads x (svit_row_stats), the GEMM reads x
+# itself and its epilogue applies the per-row correction.
+# Measured on B200 (B = 64 forward): the 33 LayerNorm launches cost 1.54 ms, the statistics passes 0.88 ms, but the
+# folded epilogues (two table values per column, one more FFMA2 per pair) add 0.64 ms to the qkv / fc1 GEMMs, which are
+# epilogue-bound -- break-even, so the folded form is opt-in (SVIT_LN_FOLD=1) and the LayerNorm kernel stays the default.
+_LN_FOLD = {"enabled": os.environ.get("SVIT_LN_FOLD", "0") == "1"}
+_fold_cache = {}
+
+
+def ln_fold_applicable(x: torch.Tensor, *weights) -> bool:
+    """The folded form runs on the tcgen05 TMA-store GEMM only: bf16, no autograd, >= 128 rows, 8-aligned widths."""
+    if not _LN_FOLD["enabled"] or torch.is_grad_enabled() or x.dtype != torch.bfloat16:
+        return False
+    if _state["gemm_impl"] == IMPL_SIMT or x.numel() // x.shape[-1] < 128 or x.shape[-1] % 8:
+        return False
+    return all(w.shape[0] % 8 == 0 for w in weights)
+
+
+def row_stats(x: torch.Tensor, eps: float = LN_EPS) -> torch.Tensor:
+    """[M, 2] fp32 (mean, rstd) of every row of x [.., C]."""
+    _chk(x, "row_stats")
+    x = x.contiguous()
+    Cn = x.shape[-1]
+    M = x.numel() // Cn
+    stats = torch.empty(M, 2, dtype=torch.float32, device=x.device)
+    _call("svit_row_stats", x.data_ptr(), stats.data_ptr(), M, Cn, float(eps), _dt(x), _stream())
+    return stats
+
+
+def folded_ln_weight(weight, bias, gamma, beta, dtype):
+    """(W' [N, K] in `dtype`, table [N / 2, 4] fp32 = (c[2i], c[2i+1], b'[2i], b'[2i+1]) with c = the row sums of the
+    ROUNDED W' and b' = bias + W beta), cached until any of the four parameters is modified."""
+    tensors = (weight, bias, gamma, beta)
+    key = (id(weight), id(gamma), dtype)
+    sig = tuple((id(t), t._version, t.data_ptr()) if t is not None else None for t in tensors)
+    ent = _fold_cache.get(key)
+    if ent is not None and ent[0] == sig and all(r is None or r() is t for r, t in zip(ent[1], tensors)):
+        return ent[2]
+    import weakref
+
+    w32, g32, b32 = weight.detach().float(), gamma.detach().float(), beta.detach().float()
+    wf = (w32 * g32[None, :]).to(dtype).contiguous()
+    colsum = wf.float().sum(dim=1).contiguous()
+    bias2 = w32 @ b32
+    if bias is not None:
+        bias2 = bias2 + bias.detach().float()
+    N = wf.shape[0]
+    table = torch.cat([colsum.reshape(N // 2, 2), bias2.reshape(N // 2, 2)], dim=1).contiguous()
+    refs = tuple(weakref.ref(t, lambda _r, k=key: _fold_cache.pop(k, None)) if t is not None else None for t in tensors)
+    _fold_cache[key] = (sig, refs, (wf, table))
+    return _fold_cache[key][2]
+
+
+def linear_ln(x, stats, gamma, beta, weight, bias=None):
+    """LayerNorm(x; gamma, beta) W^T + b with the statistics of `row_stats(x)`; inference only (no autograd)."""
+    assert not torch.is_grad_enabled()
+    x = x.contiguous()
+    K = x.shape[-1]
+    N = weight.shape[0]
+    M = x.numel() // K
+    wf, table = folded_ln_weight(weight, bias, gamma, beta, x.dtype)
+    out = torch.empty(*x.shape[:-1], N, dtype=x.dtype, device=x.device)
+    gemm(x, wf, out, M, N, K, K, K, N, 0, 1, ln_stats=stats, ln_colsum=table)
+    return out
+
+
+def mlp_ln(x, stats, gamma, beta, w1, b1, w2, b2, residual=None, sample_scale=None):
+    """residual + sample_scale * fc2(gelu(fc1(LayerNorm(x))))  (common.py:27-34, attention.py:566-570); inference only."""
+    assert not torch.is_grad_enabled()
+    x = x.contiguous()
+    K = x.shape[-1]
+    Hd = w1.shape[0]
+    N = w2.shape[0]
+    M = x.numel() // K
+    wf, table = folded_ln_weight(w1, b1, gamma, beta, x.dtype)
+    hid = torch.empty(*x.shape[:-1], Hd, dtype=x.dtype, device=x.device)
+    gemm(x, wf, hid, M, Hd, K, K, K, Hd, 0, 1, act=1, ln_stats=stats, ln_colsum=table)
+    out = torch.empty(*x.shape[:-1], N, dtype=x.dtype, device=x.device)
+    rps = (M // sample_scale.numel()) if sample_scale is not None else 0
+    res = residual.contiguous() if residual is not None else None
+    gemm(hid, cast_weight(w2, x.dtype), out, M, N, Hd, Hd, Hd, N, 0, 1, bias=_f32(b2), residual=res, ldr=N,
+         sample_scale=sample_scale, rows_per_sample=rps)
+    return out
 
 
 # --------------------------------------------------------------------------------------------

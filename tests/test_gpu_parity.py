@@ -244,6 +244,43 @@ def test_block_bf16_golden_forward(golden):
         assert err < 2e-2, i  # north_star bf16 tolerance
 
 
+def test_block_folded_layernorm_matches_unfolded():
+    """Inference blocks fold norm1 / norm2 into the consuming GEMMs (MultiScaleBlock._forward_folded); the result must
+    agree with the LayerNorm-kernel path to bf16 rounding at the real stage widths, including a dim-changing block."""
+    from svit_b200.msa import MultiScaleBlock
+    torch.manual_seed(5)
+    kw = dict(qkv_bias=True, kernel_q=(3, 3, 3), kernel_kv=(3, 3, 3), rel_pos_spatial=True, rel_pos_temporal=True,
+              residual_pooling=True, dim_mul_in_att=True)
+    for dim, dim_out, heads, size, sq, skv in ((96, 96, 1, (4, 16, 16), (1, 1, 1), (1, 4, 4)),
+                                               (96, 192, 2, (4, 16, 16), (1, 2, 2), (1, 2, 2)),
+                                               (384, 384, 4, (2, 14, 14), (1, 1, 1), (1, 2, 2))):
+        m = MultiScaleBlock(dim, dim_out, heads, list(size), stride_q=sq, stride_kv=skv, **kw).to(DEV)
+        for n, p in m.named_parameters():
+            if n.endswith("norm1.weight") or n.endswith("norm2.weight"):
+                p.data.add_(0.2 * torch.randn_like(p))
+            if n.endswith("norm1.bias") or n.endswith("norm2.bias"):
+                p.data.add_(0.2 * torch.randn_like(p))
+        x = (torch.randn(2, 1 + size[0] * size[1] * size[2] + 8, dim, device=DEV) + 0.3).to(torch.bfloat16)
+        was = ops._LN_FOLD["enabled"]
+        try:
+            with torch.no_grad():
+                ops._LN_FOLD["enabled"] = True
+                assert ops.ln_fold_applicable(x, m.attn.qkv.weight, m.mlp.fc1.weight)
+                n0 = ops.launches()
+                y1, thw1 = m(x, list(size))
+                folded_calls = ops.launches() - n0
+                ops._LN_FOLD["enabled"] = False
+                n0 = ops.launches()
+                y0, thw0 = m(x, list(size))
+                plain_calls = ops.launches() - n0
+        finally:
+            ops._LN_FOLD["enabled"] = was
+        assert thw0 == thw1 and folded_calls == plain_calls  # row_stats replaces layer_norm one for one
+        err = max_rel_err(cpu(y1), cpu(y0))
+        print(f"folded vs unfolded block dim {dim}->{dim_out}: {err:.2e}")
+        assert err < 1.5e-2
+
+
 # ------------------------------------------------------------------------------------------------ models
 def _model(cfg, g, dtype):
     m = svit_b200.SViT(cfg, compute_dtype=dtype)

@@ -291,3 +291,60 @@ def test_attention_backward_tc_matches_simt(shape, unfused):
         # table gradients sum dE = -(dS over the few cls / object keys) over thousands of rows: heavy cancellation on
         # top of the bf16 rounding of dS, hence the wider bound
         assert err < (5e-2 if name.startswith("dR") else 2e-2), (shape, name, err)
+
+
+# ------------------------------------------------------------------------------------------------ folded LayerNorm
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_row_stats(dtype):
+    gen = torch.Generator().manual_seed(41)
+    for (M, Cn) in ((1, 96), (777, 96), (1000, 192), (333, 384), (130, 768), (257, 128), (64, 512)):
+        if dtype == torch.float32 and Cn > 512:
+            continue  # at most 128 16-byte vectors per row
+        x = (torch.randn(M, Cn, generator=gen) * 2.0 + 0.7 * torch.randn(M, 1, generator=gen)).to(dtype)
+        st = cpu(ops.row_stats(x.to(DEV), 1e-6))
+        xd = x.double()
+        mean = xd.mean(1)
+        rstd = 1.0 / torch.sqrt(xd.var(1, unbiased=False) + 1e-6)
+        assert max_rel_err(st[:, 0], mean) < 1e-5, (M, Cn)
+        assert max_rel_err(st[:, 1], rstd) < 1e-5, (M, Cn)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(300, 288, 96, 0), (1000, 384, 96, 1), (640, 576, 192, 0), (520, 1536, 384, 1),
+                                        (4100, 1152, 384, 0), (2304, 3072, 768, 1), (2100, 2304, 768, 0)])
+def test_gemm_folded_layernorm(M, N, K, act):
+    """LayerNorm(x) W^T + b through the folded epilogue (rstd * (x W'^T - mean * colsum(W')) + b') against an fp64
+    LayerNorm followed by the product with the fp32 weight (attention.py:558-561, 566-567)."""
+    gen = torch.Generator().manual_seed(43 + N)
+    x = (torch.randn(M, K, generator=gen) * 1.5 + 0.5 * torch.randn(M, 1, generator=gen)).to(torch.bfloat16)
+    W = torch.randn(N, K, generator=gen) * 0.05
+    b = torch.randn(N, generator=gen) * 0.1
+    gamma = 1.0 + 0.2 * torch.randn(K, generator=gen)
+    beta = 0.1 * torch.randn(K, generator=gen)
+    Wp, bp, gp, btp = (torch.nn.Parameter(t.to(DEV)) for t in (W, b, gamma, beta))
+    with torch.no_grad():
+        xs = x.to(DEV)
+        st = ops.row_stats(xs, 1e-6)
+        if act:
+            w2 = torch.nn.Parameter(torch.eye(N, device=DEV)[:96].contiguous())
+            b2 = torch.nn.Parameter(torch.zeros(96, device=DEV))
+            y = ops.mlp_ln(xs, st, gp, btp, Wp, bp, w2, b2)
+        else:
+            y = ops.linear_ln(xs, st, gp, btp, Wp, bp)
+    xn = torch.nn.functional.layer_norm(x.double(), (K,), gamma.double(), beta.double(), 1e-6)
+    ref = xn @ W.double().t() + b.double()
+    if act:
+        ref = torch.nn.functional.gelu(ref).to(torch.bfloat16).double()[:, :96]
+    err = max_rel_err(cpu(y), ref)
+    assert err < 8e-3, (M, N, K, act, err)
+
+
+def test_folded_weight_cache_follows_parameter_updates():
+    W = torch.nn.Parameter(torch.randn(96, 96, device=DEV) * 0.05)
+    g = torch.nn.Parameter(torch.ones(96, device=DEV))
+    bt = torch.nn.Parameter(torch.zeros(96, device=DEV))
+    a = ops.folded_ln_weight(W, None, g, bt, torch.bfloat16)
+    assert ops.folded_ln_weight(W, None, g, bt, torch.bfloat16) is a
+    with torch.no_grad():
+        g.mul_(2.0)
+    b = ops.folded_ln_weight(W, None, g, bt, torch.bfloat16)
+    assert b is not a and max_rel_err(cpu(b[0]), 2.0 * cpu(a[0])) < 1e-6
