@@ -329,6 +329,8 @@ def main():
     ap.add_argument("--no-torch-gpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (configs[2])")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel breakdown here")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("SVIT_FWD_LANES", "1")),
+                    help="inference graph: independent sub-batches captured on separate streams")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-overlap", action="store_true", help="training leg: all-reduce after backward instead of overlapped")
     ap.add_argument("--host-input", default="uint8", choices=["uint8", "bf16"],
@@ -369,7 +371,7 @@ def main():
     # The forward is captured once in a CUDA graph (svit_b200.GraphedForward) and replayed: one graph launch per step
     eager = model
     if not args.no_graph:
-        model = svit_b200.GraphedForward(eager, dev_in[0])
+        model = svit_b200.GraphedForward(eager, dev_in[0], lanes=args.lanes)
     # ---- device-resident throughput
     with torch.no_grad():
         for i in range(W):

@@ -30,27 +30,62 @@ class GraphedForward:
     compute-dtype weight copies that were current at capture time; if a parameter is modified afterwards
     (load_state_dict, an optimizer step, .to()) the next call re-captures instead of replaying stale weights."""
 
-    def __init__(self, model, example_clip: torch.Tensor, warmup: int = 2):
+    def __init__(self, model, example_clip: torch.Tensor, warmup: int = 2, lanes: int = 1):
+        """`lanes` > 1 splits the batch into that many independent sub-batches whose forwards are captured on
+        separate streams (clips are independent: no forward communication): inside the graph the kernels of one lane
+        fill the SMs that the tail waves of another lane's kernels leave idle."""
         assert example_clip.is_cuda, "GraphedForward needs a CUDA clip"
         if model.training:
             raise RuntimeError("GraphedForward captures the inference forward: call model.eval() first")
         self.model = model
         self.static_in = example_clip.clone()
         self.warmup = max(1, warmup)
+        self.lanes = max(1, min(int(lanes), self.static_in.shape[0]))
+        self._lane_streams = [torch.cuda.Stream(device=self.static_in.device) for _ in range(self.lanes - 1)]
         self._capture()
+
+    def _forward(self):
+        if self.lanes == 1:
+            return self.model([self.static_in])
+        B = self.static_in.shape[0]
+        bounds = [B * i // self.lanes for i in range(self.lanes + 1)]
+        cur = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(cur)
+        outs, done = [], []
+        for i in range(self.lanes):
+            part = self.static_in[bounds[i]:bounds[i + 1]]
+            if i == 0:
+                outs.append(self.model([part]))
+                continue
+            st = self._lane_streams[i - 1]
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                outs.append(self.model([part]))
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done.append(ev)
+        for ev in done:
+            cur.wait_event(ev)
+        probs = torch.cat([o[0] for o in outs])
+        extra = {}
+        for k, v in outs[0][1].items():
+            same = torch.is_tensor(v) and v.ndim > 0 and v.shape[0] == bounds[1] - bounds[0]
+            extra[k] = torch.cat([o[1][k] for o in outs]) if same else v
+        return probs, extra
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.static_in.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(self.warmup):  # first-call work (kernel attributes, table caches) must not be captured
-                self.model([self.static_in])
+                self._forward()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = ops.launches()
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.out, self.extra = self.model([self.static_in])
+            self.out, self.extra = self._forward()
         self.launches_per_replay = ops.launches() - n0
         # the graph holds raw pointers into the cached weight copies: keep them alive and remember their versions
         self._weights = [ent[3] for ent in ops._wcache.values()]

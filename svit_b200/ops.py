@@ -439,7 +439,7 @@ def _branches(n: int):
     kernels are small and latency-bound; running the three chains side by side fills the SMs that each kernel's tail
     leaves idle.  Fork / join are event waits, so the pattern is graph-capturable."""
     cur = torch.cuda.current_stream()
-    key = (cur.device.index, n)
+    key = (cur.device.index, n, cur.cuda_stream)  # per launching stream: concurrent forwards (graph lanes) do not share
     if key not in _side_streams:
         _side_streams[key] = [torch.cuda.Stream(device=cur.device) for _ in range(n - 1)]
     return [cur] + _side_streams[key]

@@ -104,3 +104,22 @@ def test_graphed_train_step_draws_fresh_droppath_masks():
     step = svit_b200.GraphedTrainStep(m, opt, clip, labels, max_norm=None, warmup=1)
     vals = {round(float(step(clip, labels)), 6) for _ in range(8)}
     assert len(vals) > 1
+
+
+def test_graphed_forward_lanes_match_single_lane():
+    """GraphedForward(lanes=n) captures n independent sub-batch forwards on separate streams; the clips do not interact,
+    so every output must equal the single-lane graph bit for bit (same kernels per clip, different co-scheduling)."""
+    cfg, m = _tiny()
+    m.eval()
+    clip = synth_input("lanes.clip", (6, 3, 4, 32, 32), 9).to(DEV).bfloat16()
+    g1 = svit_b200.GraphedForward(m, clip)
+    p1, e1 = g1(clip)
+    p1, e1 = p1.clone(), {k: v.clone() for k, v in e1.items() if torch.is_tensor(v)}
+    for lanes in (2, 3):
+        g = svit_b200.GraphedForward(m, clip, lanes=lanes)
+        for _ in range(2):
+            p, e = g(clip)
+        torch.cuda.synchronize()
+        assert p.shape == p1.shape and torch.equal(p, p1), lanes
+        for k, v in e1.items():
+            assert e[k].shape == v.shape and torch.equal(e[k], v), (lanes, k)
