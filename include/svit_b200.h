@@ -117,6 +117,16 @@ int svit_gemm(const svit_gemm_args* args, void* stream);
 /* stats[m] = (mean, 1 / sqrt(var + eps)) of row m of x [M, C] (fp32 pair per row): the LayerNorm statistics a folded
  * GEMM needs (half the traffic of a LayerNorm pass: the rows are read, nothing is written back) */
 int svit_row_stats(const void* x, float* stats, int64_t M, int C, float eps, int dtype, void* stream);
+/* Fused MLP (inference): out = residual + fc2(gelu(fc1(LN(x)))) with the hidden activation kept on chip (TMEM -> shared
+ * memory), replacing the two svit_gemm calls of Mlp.forward (common.py:27-34), the residual add and -- optionally -- the
+ * norm2 launch of MultiScaleBlock.forward (attention.py:566-570).  x [M, C], w1 [H, C], w2 [N, H], residual / out [M, N]:
+ * bf16; b1 [H], b2 [N]: fp32; residual may be NULL; out must not alias x or residual.  ln_gamma / ln_beta [C] fp32 (both or neither): x is normalised on the
+ * fly (LayerNorm over C, eps) and residual must then be x itself or NULL.  Supported:
+ * (C, H, N) = (96, 384, 96), both weight matrices resident in shared memory; else SVIT_ENOTSUP. */
+int svit_mlp_fused_supported(int64_t M, int C, int H, int N);
+int svit_mlp_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const void* residual,
+                   void* out, int64_t M, int C, int H, int N, const float* ln_gamma, const float* ln_beta, float eps,
+                   void* stream);
 /* out[n] += sum_m x[m,n]  (bias gradients) */
 int svit_colsum(const void* x, float* out, int64_t M, int N, int64_t ld, int dtype, void* stream);
 

@@ -57,6 +57,8 @@ PROTOTYPES = {
     "svit_abi_version": [],
     "svit_destroy": [],
     "svit_row_stats": [vp, vp, i64, C.c_int, f32, C.c_int, vp],
+    "svit_mlp_fused_supported": [i64, C.c_int, C.c_int, C.c_int],
+    "svit_mlp_fused": [vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp, f32, vp],
     "svit_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i64, C.c_int, f32, C.c_int, vp],
     "svit_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp],
     "svit_pool_ln_fwd": [vp, i64, i64, i64, vp, vp, vp, vp, vp] + [C.c_int] * 7 + [f32, C.c_int, vp],

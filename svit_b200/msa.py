@@ -344,8 +344,15 @@ class MultiScaleBlock(nn.Module):
             x = ops.linear(x_norm, self.proj.weight, self.proj.bias)  # skip path uses the normalised input (:560-561)
         x_res = ops.skip_pool(x, thw_shape, O, self._sq)
         x, thw_new = self.attn(x_norm, thw_shape, residual=x_res, sample_scale=self._scale(x))
+        m = self.mlp
+        sc = self._scale(x)  # ONE draw per branch, in the reference's order (common.py:46-70)
+        if ops.mlp_fused_applicable(x, m.fc1.weight, m.fc2.weight, sc):
+            # inference, first stage: norm2 + fc1 + GELU + fc2 + residual as one kernel (hidden activation stays on chip)
+            x = ops.mlp_fused(x, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, residual=x,
+                              ln=(self.norm2.weight, self.norm2.bias, self.norm2.eps))
+            return x, thw_new
         x_norm2 = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        x = self.mlp(x_norm2, residual=x, sample_scale=self._scale(x))
+        x = self.mlp(x_norm2, residual=x, sample_scale=sc)
         return x, thw_new
 
     def _forward_folded(self, x, thw_shape, O):
@@ -357,6 +364,10 @@ class MultiScaleBlock(nn.Module):
             x = ops.linear_ln(x_in, st1, self.norm1.weight, self.norm1.bias, self.proj.weight, self.proj.bias)
         x_res = ops.skip_pool(x, thw_shape, O, self._sq)
         x, thw_new = self.attn(x_in, thw_shape, residual=x_res, sample_scale=self._scale(x), ln=(st1, self.norm1))
+        m = self.mlp
+        if ops.mlp_fused_applicable(x, m.fc1.weight, m.fc2.weight):  # (the folded path is inference only: no DropPath scale)
+            return ops.mlp_fused(x, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, residual=x,
+                                 ln=(self.norm2.weight, self.norm2.bias, self.norm2.eps)), thw_new
         if not ops.ln_fold_applicable(x, self.mlp.fc1.weight):  # fewer than 128 pooled rows (tiny test geometries)
             x_norm2 = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
             return self.mlp(x_norm2, residual=x, sample_scale=self._scale(x)), thw_new

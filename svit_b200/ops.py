@@ -96,7 +96,7 @@ _FAMILY = {"svit_gemm": "gemm", "svit_attn_fwd": "attention", "svit_attn_bwd": "
            "svit_pool_ln_fwd": "pool_ln", "svit_pool_ln_fwd_save": "pool_ln", "svit_pool_ln_bwd": "pool_ln_bwd",
            "svit_pool_ln_bwd_saved": "pool_ln_bwd", "svit_layernorm_fwd": "layernorm", "svit_row_stats": "layernorm",
            "svit_layernorm_bwd": "layernorm_bwd", "svit_skip_maxpool_fwd": "skip_pool", "svit_im2col3d": "im2col", "svit_s2d_clip": "im2col",
-           "svit_patch_embed_s2d": "gemm"}
+           "svit_patch_embed_s2d": "gemm", "svit_mlp_fused": "gemm"}
 _prof = None
 
 
@@ -272,7 +272,44 @@ class _Mlp(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2, dres, None, None
 
 
+_MLP_FUSED = {"enabled": os.environ.get("SVIT_MLP_FUSED", "1") != "0"}
+
+
+def mlp_fused_applicable(x, w1, w2, sample_scale=None) -> bool:
+    """svit_mlp_fused: inference (no autograd, no DropPath scale), bf16, the tcgen05 path, a supported (C, H, N)."""
+    if not _MLP_FUSED["enabled"] or torch.is_grad_enabled() or sample_scale is not None or x.dtype != torch.bfloat16:
+        return False
+    if _state["gemm_impl"] == IMPL_SIMT or not x.is_cuda:
+        return False
+    M = x.numel() // x.shape[-1]
+    return bool(_lib.lib().svit_mlp_fused_supported(M, x.shape[-1], w1.shape[0], w2.shape[0]))
+
+
+def mlp_fused(x, w1, b1, w2, b2, residual=None, ln=None):
+    """out = residual + fc2(gelu(fc1(LN(x)))) in one kernel, the hidden activation never written to HBM (inference).
+    ln = (gamma, beta, eps): x is the UN-normalised input, normalised on the fly; residual must then be x or None."""
+    x = x.contiguous()
+    K, Hd, N = x.shape[-1], w1.shape[0], w2.shape[0]
+    M = x.numel() // K
+    out = torch.empty(*x.shape[:-1], N, dtype=x.dtype, device=x.device)
+    res = None
+    if residual is not None:
+        res = x if residual is x else residual.contiguous()
+    g = bt = None
+    eps = 0.0
+    if ln is not None:
+        g, bt, eps = _f32(ln[0]), _f32(ln[1]), float(ln[2])
+        if res is not None and res.data_ptr() != x.data_ptr():
+            raise ValueError("mlp_fused: with a LayerNorm prologue the residual must be the input itself")
+    _call("svit_mlp_fused", x.data_ptr(), cast_weight(w1, x.dtype).data_ptr(), _f32(b1).data_ptr(),
+          cast_weight(w2, x.dtype).data_ptr(), _f32(b2).data_ptr(), _p(res), out.data_ptr(), M, K, Hd, N, _p(g), _p(bt), eps,
+          _stream(), tag=f"[{M}x{K}x{Hd}x{N}]" if _prof is not None else None)
+    return out
+
+
 def mlp(x, w1, b1, w2, b2, residual=None, sample_scale=None):
+    if mlp_fused_applicable(x, w1, w2, sample_scale):
+        return mlp_fused(x, w1, b1, w2, b2, residual)
     return _Mlp.apply(x, w1, b1, w2, b2, residual, sample_scale, torch.is_grad_enabled())
 
 

@@ -348,3 +348,48 @@ def test_folded_weight_cache_follows_parameter_updates():
         g.mul_(2.0)
     b = ops.folded_ln_weight(W, None, g, bt, torch.bfloat16)
     assert b is not a and max_rel_err(cpu(b[0]), 2.0 * cpu(a[0])) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ fused MLP
+@pytest.mark.parametrize("M,mode", [(128, "res"), (1000, "res"), (40000, "none"), (257, "ln"), (30000, "ln"), (5000, "self"),
+                                    (129, "ln_nores")])
+def test_mlp_fused_matches_reference(M, mode):
+    """svit_mlp_fused (hidden activation kept on chip, optional LayerNorm prologue) against fp64 LayerNorm -> fc1 ->
+    exact-erf GELU -> fc2 (+ residual) of the same bf16 operands (common.py:27-34, attention.py:566-570), and against the
+    LayerNorm + two-GEMM path it replaces."""
+    Cn = 96
+    gen = torch.Generator().manual_seed(51 + M)
+    Hd = 4 * Cn
+    x = (torch.randn(M, Cn, generator=gen) * 1.3 + 0.4 * torch.randn(M, 1, generator=gen)).to(torch.bfloat16)
+    w1 = (torch.randn(Hd, Cn, generator=gen) * Cn ** -0.5).to(torch.bfloat16)
+    w2 = (torch.randn(Cn, Hd, generator=gen) * Hd ** -0.5).to(torch.bfloat16)
+    b1 = torch.randn(Hd, generator=gen) * 0.2
+    b2 = torch.randn(Cn, generator=gen) * 0.2
+    gamma = 1.0 + 0.2 * torch.randn(Cn, generator=gen)
+    beta = 0.1 * torch.randn(Cn, generator=gen)
+    res = torch.randn(M, Cn, generator=gen).to(torch.bfloat16) if mode == "res" else None
+    dev = lambda t: None if t is None else t.to(DEV)
+    xd, w1d, w2d, b1d, b2d = dev(x), dev(w1), dev(w2), dev(b1), dev(b2)
+    use_ln = mode in ("ln", "ln_nores")
+    with torch.no_grad():
+        assert ops.mlp_fused_applicable(xd, w1d, w2d)
+        rd = dev(res) if mode == "res" else (xd if mode in ("ln", "self") else None)
+        got = ops.mlp_fused(xd, w1d, b1d, w2d, b2d, rd, ln=(dev(gamma), dev(beta), 1e-6) if use_ln else None)
+        ops._MLP_FUSED["enabled"] = False
+        try:
+            xin = ops.layer_norm(xd, dev(gamma), dev(beta), 1e-6) if use_ln else xd
+            two = ops.mlp(xin, w1d, b1d, w2d, b2d, rd)
+        finally:
+            ops._MLP_FUSED["enabled"] = True
+    torch.cuda.synchronize()
+    xin = x.double()
+    if use_ln:
+        xin = torch.nn.functional.layer_norm(xin, (Cn,), gamma.double(), beta.double(), 1e-6).to(torch.bfloat16).double()
+    hid = torch.nn.functional.gelu(xin @ w1.double().t() + b1.double()).to(torch.bfloat16).double()
+    ref = hid @ w2.double().t() + b2.double()
+    if mode == "res":
+        ref = ref + res.double()
+    elif mode in ("ln", "self"):
+        ref = ref + x.double()
+    err, err2 = max_rel_err(cpu(got), ref), max_rel_err(cpu(got), cpu(two))
+    assert err < 8e-3 and err2 < 8e-3, (M, mode, err, err2)
