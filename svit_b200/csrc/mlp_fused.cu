@@ -1,19 +1,19 @@
-// Fused MLP of a MultiScaleBlock (inference): out = residual + fc2(gelu(fc1(x)))     slowfast/models/common.py:27-34,
+// Fused MLP of a MultiScaleBlock (inference): out = residual + fc2(gelu(fc1(LN(x))))     slowfast/models/common.py:27-34,
 // slowfast/models/attention.py:566-570.  The hidden activation [M, 4C] never reaches HBM: per 128-row tile the hidden
 // units are produced 64 at a time into TMEM, activated by the epilogue warps, written to shared memory as the bf16 A
 // operand of the second product and consumed from there.  For the wide, short stages (C = 96 with 1.6 M rows, C = 192 with
 // 0.4 M rows at batch 64) fc1 / fc2 as two GEMMs are HBM-bound on exactly that tensor (write 4C, read 4C per row against
 // C in, C out).
 //
-// Persistent, one CTA per SM, 320 threads:
-//   warp 0     TMA producer: x tile [128, C] (resident for the tile), ring of {W1 chunk [64, C], W2 chunk [NOUT, 64]}
-//   warp 1     tcgen05.mma issuer (one lane):  acc1[c & 1] = x W1_c^T  (128 x 64 x C),  acc2 += h_c W2_c^T  (128 x NOUT x 64);
-//              the first product runs LOOK chunks ahead of the second, so the tensor pipe works on chunk c + LOOK while
-//              the epilogue warps activate chunk c
-//   warps 2-9  epilogue, two warps per TMEM lane quarter (32 of a chunk's 64 hidden units each): tcgen05.ld -> + b1 ->
-//              GELU -> bf16 -> 128-byte-swizzled K-major tile in shared memory -> mbarrier;  once per tile the second
-//              accumulator: + b2 + residual (TMA-loaded one tile ahead into the staging slot, combined in place) -> TMA store
-// TMEM: acc1 double-buffered (2 x 64 columns) | acc2 (NOUT columns).
+// Persistent, one CTA per SM.  Roles:
+//   producer warp(s)  TMA: x tile [128, C] (resident for the tile); C = 96: both weight matrices once per CTA (144 KB
+//                     resident), C = 192: weight chunks through two rings
+//   MMA issuer        one lane:  acc1[g % 4] = x W1_c^T  (128 x 64 x C),  acc2 += h_c W2_c^T  (128 x NOUT x 64); the first
+//                     product runs up to three chunks ahead of the second
+//   2 x 8 epilogue warps ("teams", two warps per TMEM lane quarter, 32 of a chunk's 64 hidden units each):
+//                     tcgen05.ld -> + b1 -> GELU -> bf16 -> 128-byte-swizzled K-major tile in shared memory -> mbarrier;
+//                     per tile the LayerNorm prologue (C = 96) and the output (acc2 + b2 + residual -> TMA store)
+// TMEM: four first-product accumulators (4 x 64 columns) | acc2 (NOUT columns).
 #include "tc_common.cuh"
 #include "../../include/svit_b200.h"
 
@@ -23,44 +23,7 @@ constexpr int BM = 128;
 constexpr int HC = 64;                       // hidden units per chunk
 constexpr int BOX_N = 32;                    // output columns per staging slot
 constexpr int SLOT_BYTES = BM * BOX_N * 2;   // 8 KB
-constexpr int NTHREADS = 320;
-constexpr int EPI_WARPS = 8;
 constexpr int SMEM_LIMIT = 232448;
-
-template <int C, int NOUT>
-struct Cfg {
-  static constexpr int KA = C / 64;                                   // 64-column boxes (128-byte swizzle) along K = C
-  static constexpr int KB = (C % 64) / 32;                            // trailing 32-column box (64-byte swizzle)
-  static constexpr int XS_BYTES = KA * BM * 128 + KB * BM * 64;
-  static constexpr int W1_BYTES = KA * HC * 128 + KB * HC * 64;
-  static constexpr int W2_BYTES = NOUT * 128;
-  static constexpr int WSLOT = W1_BYTES + W2_BYTES;
-  static constexpr int NXB = C <= 96 ? 2 : 1;                         // x tile buffers
-  static constexpr int WST = C <= 96 ? 3 : 2;                         // weight ring stages
-  static constexpr int LOOK = WST - 1;                                // chunks the first product runs ahead
-  static constexpr int HS_BYTES = BM * 128;
-  static constexpr int NBOX = NOUT / BOX_N;
-  static constexpr int SPG = (NBOX + 1) / 2;                          // staging slots per epilogue group (one per box)
-  static constexpr int OFF_XS = 0;
-  static constexpr int OFF_W = OFF_XS + NXB * XS_BYTES;
-  static constexpr int OFF_HS = OFF_W + WST * WSLOT;
-  static constexpr int OFF_SLOT = OFF_HS + 2 * HS_BYTES;
-  static constexpr int OFF_BAR = OFF_SLOT + 2 * SPG * SLOT_BYTES;
-  static constexpr int NBARS = 2 * NXB + 2 * WST + 4 + 4 + 2 + 2 * SPG;
-  static constexpr int TOTAL = OFF_BAR + 512 + 1024;
-  static constexpr uint32_t TMEM_COLS = 128 + NOUT <= 256 ? 256 : 512;
-  static_assert(C % 32 == 0 && NOUT % BOX_N == 0 && NOUT <= 256, "shape");
-  static_assert(XS_BYTES % 1024 == 0 && W1_BYTES % 1024 == 0 && W2_BYTES % 1024 == 0, "swizzle atoms need 1 KB alignment");
-  static_assert(NBARS * 8 + 8 <= 512, "barrier area");
-  static_assert(TOTAL <= SMEM_LIMIT, "shared memory budget");
-};
-
-struct Params {
-  const float* b1;
-  const float* b2;
-  int M, H;
-  int has_res;
-};
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -108,272 +71,6 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-template <int C, int NOUT>
-__global__ void __launch_bounds__(NTHREADS, 1)
-mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_x64, const __grid_constant__ CUtensorMap tmap_x32,
-                 const __grid_constant__ CUtensorMap tmap_w1_64, const __grid_constant__ CUtensorMap tmap_w1_32,
-                 const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_res,
-                 const __grid_constant__ CUtensorMap tmap_out, Params p) {
-  using L = Cfg<C, NOUT>;
-  constexpr int KA = L::KA, KB = L::KB, NXB = L::NXB, WST = L::WST, LOOK = L::LOOK, SPG = L::SPG, NBOX = L::NBOX;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* xs_full = bars;                 // [NXB]
-  uint64_t* xs_empty = xs_full + NXB;       // [NXB]
-  uint64_t* w_full = xs_empty + NXB;        // [WST]
-  uint64_t* w_empty = w_full + WST;         // [WST]
-  uint64_t* acc1_full = w_empty + WST;      // [2]
-  uint64_t* acc1_empty = acc1_full + 2;     // [2]
-  uint64_t* hs_full = acc1_empty + 2;       // [2]
-  uint64_t* hs_empty = hs_full + 2;         // [2]
-  uint64_t* acc2_full = hs_empty + 2;       // [1]
-  uint64_t* acc2_empty = acc2_full + 1;     // [1]
-  uint64_t* res_full = acc2_empty + 1;      // [2 * SPG]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2 * SPG);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = (p.M + BM - 1) / BM;
-  const int NC = p.H / HC;  // chunks per tile (even)
-
-  if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmap_x64); tc::prefetch_tmap(&tmap_w1_64); tc::prefetch_tmap(&tmap_w2); tc::prefetch_tmap(&tmap_out);
-    if (KB) { tc::prefetch_tmap(&tmap_x32); tc::prefetch_tmap(&tmap_w1_32); }
-    if (p.has_res) tc::prefetch_tmap(&tmap_res);
-    for (int i = 0; i < NXB; ++i) { tc::mbar_init(&xs_full[i], 1); tc::mbar_init(&xs_empty[i], 1); }
-    for (int i = 0; i < WST; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&acc1_empty[i], EPI_WARPS);
-      tc::mbar_init(&hs_full[i], EPI_WARPS); tc::mbar_init(&hs_empty[i], 1);
-    }
-    tc::mbar_init(acc2_full, 1); tc::mbar_init(acc2_empty, EPI_WARPS);
-    for (int i = 0; i < 2 * SPG; ++i) tc::mbar_init(&res_full[i], 1);
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) tc::tmem_alloc(tmem_ptr, L::TMEM_COLS);
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr;
-  constexpr uint32_t COL_ACC2 = 128;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t wcnt = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int m0 = t * BM;
-        const int xb = it % NXB;
-        tc::mbar_wait(&xs_empty[xb], ((it / NXB) & 1) ^ 1);
-        unsigned char* xs = smem + L::OFF_XS + xb * L::XS_BYTES;
-        tc::mbar_arrive_expect_tx(&xs_full[xb], L::XS_BYTES);
-#pragma unroll
-        for (int kb = 0; kb < KA; ++kb) tc::tma_load_2d(xs + kb * (BM * 128), &tmap_x64, &xs_full[xb], kb * 64, m0);
-        if (KB) tc::tma_load_2d(xs + KA * (BM * 128), &tmap_x32, &xs_full[xb], KA * 64, m0);
-        if (t + (int)gridDim.x < num_tiles) {  // the next tile's rows: L2 now, shared memory when the buffer frees up
-          const int m1 = m0 + (int)gridDim.x * BM;
-#pragma unroll
-          for (int kb = 0; kb < KA; ++kb) tma_prefetch_l2_2d(&tmap_x64, kb * 64, m1);
-          if (KB) tma_prefetch_l2_2d(&tmap_x32, KA * 64, m1);
-        }
-        for (int c = 0; c < NC; ++c, ++wcnt) {
-          const int slot = wcnt % WST;
-          tc::mbar_wait(&w_empty[slot], ((wcnt / WST) & 1) ^ 1);
-          unsigned char* w1 = smem + L::OFF_W + slot * L::WSLOT;
-          unsigned char* w2 = w1 + L::W1_BYTES;
-          tc::mbar_arrive_expect_tx(&w_full[slot], L::WSLOT);
-#pragma unroll
-          for (int kb = 0; kb < KA; ++kb) tc::tma_load_2d(w1 + kb * (HC * 128), &tmap_w1_64, &w_full[slot], kb * 64, c * HC);
-          if (KB) tc::tma_load_2d(w1 + KA * (HC * 128), &tmap_w1_32, &w_full[slot], KA * 64, c * HC);
-          tc::tma_load_2d(w2, &tmap_w2, &w_full[slot], c * HC, 0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = tc::idesc_bf16(BM, HC, 0, 0);
-      constexpr uint32_t idesc2 = tc::idesc_bf16(BM, NOUT, 0, 0);
-      uint32_t g1 = 0, g2 = 0;  // global chunk counters of the first / second product
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int xb = it % NXB;
-        const uint32_t xs = tc::smem_u32(smem + L::OFF_XS + xb * L::XS_BYTES);
-        for (int step = 0; step < NC + LOOK; ++step) {
-          if (step < NC) {
-            const int c = step;
-            const int b = c & 1;
-            const int slot = g1 % WST;
-            if (c == 0) tc::mbar_wait(&xs_full[xb], (it / NXB) & 1);
-            tc::mbar_wait(&w_full[slot], (g1 / WST) & 1);
-            tc::mbar_wait(&acc1_empty[b], ((g1 >> 1) & 1) ^ 1);
-            tc::fence_after_sync();
-            const uint32_t w1 = tc::smem_u32(smem + L::OFF_W + slot * L::WSLOT);
-            const uint32_t d = tmem_base + (uint32_t)(b * HC);
-#pragma unroll
-            for (int kb = 0; kb < KA; ++kb)
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc::umma_bf16_ss(d, tc::smem_desc_sw128(xs + kb * (BM * 128) + k * 32, 16, 1024),
-                                 tc::smem_desc_sw128(w1 + kb * (HC * 128) + k * 32, 16, 1024), idesc1, (kb | k) != 0 ? 1u : 0u);
-            if (KB) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k)
-                tc::umma_bf16_ss(d, smem_desc_sw64(xs + KA * (BM * 128) + k * 32), smem_desc_sw64(w1 + KA * (HC * 128) + k * 32),
-                                 idesc1, 1u);
-            }
-            tc::umma_commit(&acc1_full[b]);
-            if (c == NC - 1) tc::umma_commit(&xs_empty[xb]);  // every first product of this tile has read the x tile
-            ++g1;
-          }
-          if (step >= LOOK) {
-            const int cc = step - LOOK;
-            const int b = cc & 1;
-            const int slot = g2 % WST;
-            tc::mbar_wait(&hs_full[b], (g2 >> 1) & 1);
-            if (cc == 0) tc::mbar_wait(acc2_empty, (it & 1) ^ 1);
-            tc::fence_after_sync();
-            const uint32_t hs = tc::smem_u32(smem + L::OFF_HS + b * L::HS_BYTES);
-            const uint32_t w2 = tc::smem_u32(smem + L::OFF_W + slot * L::WSLOT + L::W1_BYTES);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc::umma_bf16_ss(tmem_base + COL_ACC2, tc::smem_desc_sw128(hs + k * 32, 16, 1024),
-                               tc::smem_desc_sw128(w2 + k * 32, 16, 1024), idesc2, (cc | k) != 0 ? 1u : 0u);
-            tc::umma_commit(&w_empty[slot]);
-            tc::umma_commit(&hs_empty[b]);
-            if (cc == NC - 1) tc::umma_commit(acc2_full);
-            ++g2;
-          }
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3;            // TMEM lane quarter
-    const int half = (warp - 2) >> 2;  // column half of a chunk / epilogue group of the output boxes
-    const int r = q * 32 + lane;       // row inside the tile
-    const bool leader = (warp - 2) == half * 4 && lane == 0;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    unsigned char* my_slots = smem + L::OFF_SLOT + half * SPG * SLOT_BYTES;
-    uint64_t* my_res = res_full + half * SPG;
-    const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
-    const int nmy = (NBOX - half + 1) / 2;  // output boxes of this group: half, half + 2, ...
-
-    auto request_residual = [&](int t) {  // leader: this group's residual boxes of tile t, one staging slot each
-      for (int i = 0; i < nmy; ++i) {
-        tc::mbar_arrive_expect_tx(&my_res[i], SLOT_BYTES);
-        tc::tma_load_2d(my_slots + i * SLOT_BYTES, &tmap_res, &my_res[i], (half + 2 * i) * BOX_N, t * BM);
-      }
-    };
-    if (leader && p.has_res && (int)blockIdx.x < num_tiles) request_residual(blockIdx.x);
-
-    uint32_t g = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      // ---- hidden chunks: acc1 -> + b1 -> GELU -> bf16 A operand of the second product
-      for (int c = 0; c < NC; ++c, ++g) {
-        const int b = c & 1;
-        float bv[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b1 + c * HC + half * 32 + j));
-          bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
-        }
-        tc::mbar_wait_hot(&acc1_full[b], (g >> 1) & 1);
-        tc::fence_after_sync();
-        float v[32];
-        tc::tmem_ld32(lane_addr + (uint32_t)(b * HC + half * 32), v);
-        tc::tmem_ld_wait();
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&acc1_empty[b]);
-        float2* v2 = reinterpret_cast<float2*>(v);
-        const float2* b2 = reinterpret_cast<const float2*>(bv);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v2[j] = gelu2(add2(v2[j], b2[j]));
-        tc::mbar_wait_hot(&hs_empty[b], ((g >> 1) & 1) ^ 1);  // the second product two chunks back has read this buffer
-        unsigned char* hrow = smem + L::OFF_HS + b * L::HS_BYTES + r * 128;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint4 o = {pack_bf16(v[k * 8], v[k * 8 + 1]), pack_bf16(v[k * 8 + 2], v[k * 8 + 3]),
-                           pack_bf16(v[k * 8 + 4], v[k * 8 + 5]), pack_bf16(v[k * 8 + 6], v[k * 8 + 7])};
-          *reinterpret_cast<uint4*>(hrow + ((((uint32_t)(half * 4 + k)) ^ (uint32_t)(r & 7)) << 4)) = o;
-        }
-        tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&hs_full[b]);
-      }
-      // ---- output: acc2 + b2 (+ residual) -> bf16 -> TMA store, 32-column boxes half, half + 2, ...
-      tc::mbar_wait_hot(acc2_full, it & 1);
-      tc::fence_after_sync();
-      for (int i = 0; i < nmy; ++i) {
-        const int box = half + 2 * i;
-        unsigned char* sbase = my_slots + i * SLOT_BYTES;
-        float v[32];
-        tc::tmem_ld32(lane_addr + COL_ACC2 + (uint32_t)(box * BOX_N), v);
-        float bv[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + box * BOX_N + j));
-          bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
-        }
-        tc::tmem_ld_wait();
-        if (i == nmy - 1) {  // this warp's rows of the accumulator are in registers: the next tile may overwrite it
-          tc::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(acc2_empty);
-        }
-        float2* v2 = reinterpret_cast<float2*>(v);
-        const float2* b2 = reinterpret_cast<const float2*>(bv);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v2[j] = add2(v2[j], b2[j]);
-        if (p.has_res) {
-          tc::mbar_wait_hot(&my_res[i], it & 1);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint4 ax = *reinterpret_cast<const uint4*>(sbase + r * 64 + ((k ^ sw64) << 4));
-            const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&ax);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v2[k * 4 + u] = add2(v2[k * 4 + u], __bfloat1622float2(gp[u]));
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint4 o = {pack_bf16(v[k * 8], v[k * 8 + 1]), pack_bf16(v[k * 8 + 2], v[k * 8 + 3]),
-                           pack_bf16(v[k * 8 + 4], v[k * 8 + 5]), pack_bf16(v[k * 8 + 6], v[k * 8 + 7])};
-          *reinterpret_cast<uint4*>(sbase + r * 64 + ((k ^ sw64) << 4)) = o;
-        }
-        tc::fence_proxy_async();
-        named_bar_sync(1 + half, 128);
-        if (leader) {
-          tma_store_2d(&tmap_out, sbase, box * BOX_N, t * BM);
-          bulk_commit();
-        }
-      }
-      if (nmy == 0) {  // (never with NBOX >= 2; keeps the arrival count uniform)
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(acc2_empty);
-      }
-      if (leader) {
-        bulk_wait_read_all();  // the stores have read their slots: refill them with the next tile's residual boxes
-        if (p.has_res && t + (int)gridDim.x < num_tiles) request_residual(t + gridDim.x);
-      }
-      // the slots are rewritten by the group's threads only after the next tile's residual boxes have landed (or, with
-      // no residual, after the leader's wait above, published by the named barrier of the next tile's first box)
-      if (!p.has_res) named_bar_sync(1 + half, 128);
-    }
-    if (leader) bulk_wait_all();
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, L::TMEM_COLS);
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -749,6 +446,279 @@ mlp_resident96_kernel(const __grid_constant__ CUtensorMap tmap_x64, const __grid
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// C = 192, H = 768, NOUT = 192 (second stage: 6 337 tokens per clip).  590 KB of weights do not fit: they stream from L2
+// through two rings of two stages (W1 chunk [64, 192] = 24 KB, W2 chunk [192, 64] = 24 KB), requested by TWO producer
+// warps (one per ring: the first product runs up to three chunks ahead of the second, so the rings drain at different
+// times), and the MMA issuer POLLS both of its streams (next first product / next second product) and issues whichever
+// has its operands -- a blocking wait on one stream would stall the other behind a TMA round trip.  Same two epilogue
+// teams as above; the twelve chunks alternate between them, the six output boxes are split four / two.
+namespace s192 {
+constexpr int C = 192, H = 768, NOUT = 192, NC = H / HC, KA = C / 64;     // 12 chunks, 3 K boxes
+constexpr int XS_BYTES = KA * BM * 128;                                    // 48 KB
+constexpr int W1C_BYTES = KA * HC * 128;                                   // 24 KB
+constexpr int W2C_BYTES = NOUT * 128;                                      // 24 KB
+constexpr int NW = 2;                                                      // stages of each weight ring
+constexpr int OFF_XS = 0;
+constexpr int OFF_W1 = OFF_XS + XS_BYTES;
+constexpr int OFF_W2 = OFF_W1 + NW * W1C_BYTES;
+constexpr int OFF_HS = OFF_W2 + NW * W2C_BYTES;
+constexpr int OFF_SLOT = OFF_HS + 2 * BM * 128;                            // 4 x 8 KB: one per (team, column group)
+constexpr int OFF_BAR = OFF_SLOT + 4 * SLOT_BYTES;
+constexpr int TOTAL = OFF_BAR + 256 + 1024;
+constexpr int NA1 = 4;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_ACC2 = NA1 * HC;
+constexpr int TEAM_WARPS = 8;
+constexpr int NTHR = 64 + 2 * TEAM_WARPS * 32 + 32;                        // 608: + the second producer warp
+constexpr int NBOX = NOUT / BOX_N;                                         // 6
+static_assert(TOTAL <= SMEM_LIMIT, "shared memory budget");
+enum { B_XS_FULL = 0, B_XS_EMPTY, B_W1_FULL0, B_W1_EMPTY0 = B_W1_FULL0 + NW, B_W2_FULL0 = B_W1_EMPTY0 + NW,
+       B_W2_EMPTY0 = B_W2_FULL0 + NW, B_ACC1_FULL0 = B_W2_EMPTY0 + NW, B_ACC1_EMPTY0 = B_ACC1_FULL0 + NA1,
+       B_HS_FULL0 = B_ACC1_EMPTY0 + NA1, B_HS_FULL1, B_HS_EMPTY0, B_HS_EMPTY1, B_ACC2_FULL, B_ACC2_EMPTY, NUM_BARS };
+static_assert(NUM_BARS * 8 + 8 <= 256, "barrier area");
+}  // namespace s192
+
+__global__ void __launch_bounds__(s192::NTHR, 1)
+mlp_stream192_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
+                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out, ParamsR p) {
+  using namespace s192;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (p.M + BM - 1) / BM;
+  const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t total = (uint32_t)my_tiles * NC;  // chunks this CTA processes
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_x); tc::prefetch_tmap(&tmap_w1); tc::prefetch_tmap(&tmap_w2); tc::prefetch_tmap(&tmap_out);
+    for (int i = 0; i < NUM_BARS; ++i) {
+      int count = 1;
+      if ((i >= B_ACC1_EMPTY0 && i < B_ACC1_EMPTY0 + NA1) || i == B_HS_FULL0 || i == B_HS_FULL1) count = TEAM_WARPS;
+      if (i == B_ACC2_EMPTY) count = 2 * TEAM_WARPS;
+      tc::mbar_init(&bars[i], count);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== producer A: x tiles and the first-product weight ring =====================
+    if (lane == 0) {
+      uint32_t g = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int m0 = t * BM;
+        tc::mbar_wait(&bars[B_XS_EMPTY], (it & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&bars[B_XS_FULL], XS_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KA; ++kb) tc::tma_load_2d(smem + OFF_XS + kb * (BM * 128), &tmap_x, &bars[B_XS_FULL], kb * 64, m0);
+        if (t + (int)gridDim.x < num_tiles) {
+#pragma unroll
+          for (int kb = 0; kb < KA; ++kb) tma_prefetch_l2_2d(&tmap_x, kb * 64, m0 + (int)gridDim.x * BM);
+        }
+        for (int c = 0; c < NC; ++c, ++g) {
+          const int slot = g % NW;
+          tc::mbar_wait(&bars[B_W1_EMPTY0 + slot], ((g / NW) & 1) ^ 1);
+          unsigned char* w1 = smem + OFF_W1 + slot * W1C_BYTES;
+          tc::mbar_arrive_expect_tx(&bars[B_W1_FULL0 + slot], W1C_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < KA; ++kb) tc::tma_load_2d(w1 + kb * (HC * 128), &tmap_w1, &bars[B_W1_FULL0 + slot], kb * 64, c * HC);
+        }
+      }
+    }
+  } else if (warp == 2 + 2 * TEAM_WARPS) {
+    // ===================== producer B: the second-product weight ring =====================
+    if (lane == 0) {
+      for (uint32_t g = 0; g < total; ++g) {
+        const int slot = g % NW;
+        tc::mbar_wait(&bars[B_W2_EMPTY0 + slot], ((g / NW) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&bars[B_W2_FULL0 + slot], W2C_BYTES);
+        tc::tma_load_2d(smem + OFF_W2 + slot * W2C_BYTES, &tmap_w2, &bars[B_W2_FULL0 + slot], (int)(g % NC) * HC, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: two streams, whichever is ready =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = tc::idesc_bf16(BM, HC, 0, 0);
+      constexpr uint32_t idesc2 = tc::idesc_bf16(BM, NOUT, 0, 0);
+      const uint32_t xs = tc::smem_u32(smem + OFF_XS);
+      uint32_t i1 = 0, i2 = 0, idle = 0;
+      while (i2 < total) {
+        bool progressed = false;
+        if (i1 < total) {
+          const uint32_t c1 = i1 % NC, t1 = i1 / NC;
+          const int ws = i1 % NW, ab = i1 % NA1;
+          if ((c1 != 0 || tc::mbar_try_wait(&bars[B_XS_FULL], t1 & 1)) &&
+              tc::mbar_try_wait(&bars[B_W1_FULL0 + ws], (i1 / NW) & 1) &&
+              tc::mbar_try_wait(&bars[B_ACC1_EMPTY0 + ab], ((i1 / NA1) & 1) ^ 1)) {
+            tc::fence_after_sync();
+            const uint32_t w1 = tc::smem_u32(smem + OFF_W1 + ws * W1C_BYTES);
+            const uint32_t d = tmem_base + (uint32_t)(ab * HC);
+#pragma unroll
+            for (int kb = 0; kb < KA; ++kb)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc::umma_bf16_ss(d, tc::smem_desc_sw128(xs + kb * (BM * 128) + k * 32, 16, 1024),
+                                 tc::smem_desc_sw128(w1 + kb * (HC * 128) + k * 32, 16, 1024), idesc1, (kb | k) != 0 ? 1u : 0u);
+            tc::umma_commit(&bars[B_ACC1_FULL0 + ab]);
+            tc::umma_commit(&bars[B_W1_EMPTY0 + ws]);
+            if (c1 == NC - 1) tc::umma_commit(&bars[B_XS_EMPTY]);  // every first product of this tile has read the x tile
+            ++i1;
+            progressed = true;
+          }
+        }
+        if (i2 < i1) {
+          const uint32_t c2 = i2 % NC, t2 = i2 / NC;
+          const int ws = i2 % NW, b = i2 & 1;
+          if (tc::mbar_try_wait(&bars[B_HS_FULL0 + b], (i2 >> 1) & 1) && tc::mbar_try_wait(&bars[B_W2_FULL0 + ws], (i2 / NW) & 1) &&
+              (c2 != 0 || tc::mbar_try_wait(&bars[B_ACC2_EMPTY], (t2 & 1) ^ 1))) {
+            tc::fence_after_sync();
+            const uint32_t hs = tc::smem_u32(smem + OFF_HS + b * (BM * 128));
+            const uint32_t w2 = tc::smem_u32(smem + OFF_W2 + ws * W2C_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::umma_bf16_ss(tmem_base + COL_ACC2, tc::smem_desc_sw128(hs + k * 32, 16, 1024),
+                               tc::smem_desc_sw128(w2 + k * 32, 16, 1024), idesc2, (c2 | (uint32_t)k) != 0 ? 1u : 0u);
+            tc::umma_commit(&bars[B_W2_EMPTY0 + ws]);
+            tc::umma_commit(&bars[B_HS_EMPTY0 + b]);
+            if (c2 == NC - 1) tc::umma_commit(&bars[B_ACC2_FULL]);
+            ++i2;
+            progressed = true;
+          }
+        }
+        if (progressed) {
+          idle = 0;
+        } else {
+          __nanosleep(20);
+          if (++idle > (1u << 24)) __trap();  // bounded like every other wait
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue teams =====================
+    const int team = (warp - 2) >> 3;
+    const int q = warp & 3;
+    const int half = ((warp - 2) & 7) >> 2;
+    const int r = q * 32 + lane;
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
+    const int grp = team * 2 + half;  // output group: slot, named barrier
+    // output boxes of this group: column parity = half, pair index (box >> 1) in {0, 2} for team 0, {1} for team 1
+    const int nmy = team == 0 ? 2 : 1;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m0 = t * BM;
+      for (int c = team; c < NC; c += 2) {
+        const uint32_t u = (uint32_t)(it * (NC / 2) + (c >> 1));
+        const uint32_t gc = (uint32_t)(it * NC + c);
+        const int ab = gc % NA1;
+        float bv[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b1 + c * HC + half * 32 + j));
+          bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+        }
+        tc::mbar_wait_hot(&bars[B_ACC1_FULL0 + ab], (gc / NA1) & 1);
+        tc::fence_after_sync();
+        float v[32];
+        tc::tmem_ld32(lane_addr + (uint32_t)(ab * HC + half * 32), v);
+        tc::tmem_ld_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[B_ACC1_EMPTY0 + ab]);
+        float2* v2 = reinterpret_cast<float2*>(v);
+        const float2* b2 = reinterpret_cast<const float2*>(bv);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v2[j] = gelu2(add2(v2[j], b2[j]));
+        tc::mbar_wait_hot(&bars[B_HS_EMPTY0 + team], (u & 1) ^ 1);
+        unsigned char* hrow = smem + OFF_HS + team * (BM * 128) + r * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint4 o = {pack_bf16(v[k * 8], v[k * 8 + 1]), pack_bf16(v[k * 8 + 2], v[k * 8 + 3]),
+                           pack_bf16(v[k * 8 + 4], v[k * 8 + 5]), pack_bf16(v[k * 8 + 6], v[k * 8 + 7])};
+          *reinterpret_cast<uint4*>(hrow + ((((uint32_t)(half * 4 + k)) ^ (uint32_t)(r & 7)) << 4)) = o;
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[B_HS_FULL0 + team]);
+      }
+      // ---- output boxes of this group
+      unsigned char* sbase = smem + OFF_SLOT + grp * SLOT_BYTES;
+      const bool row_ok = m0 + r < p.M;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (i < nmy) {
+          const int box = half + 2 * (team == 0 ? 2 * i : 1);
+          uint4 rs[4];
+          if (p.residual) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              rs[k] = row_ok ? __ldg(reinterpret_cast<const uint4*>(p.residual + (int64_t)(m0 + r) * NOUT + box * BOX_N) + k)
+                             : make_uint4(0u, 0u, 0u, 0u);
+          }
+          if (i == 0) {
+            tc::mbar_wait_hot(&bars[B_ACC2_FULL], it & 1);
+            tc::fence_after_sync();
+          }
+          float v[32];
+          tc::tmem_ld32(lane_addr + COL_ACC2 + (uint32_t)(box * BOX_N), v);
+          tc::tmem_ld_wait();
+          if (i == nmy - 1) {
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bars[B_ACC2_EMPTY]);
+          }
+          float2* v2 = reinterpret_cast<float2*>(v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + box * BOX_N + j));
+            v2[j / 2] = add2(v2[j / 2], make_float2(b4.x, b4.y));
+            v2[j / 2 + 1] = add2(v2[j / 2 + 1], make_float2(b4.z, b4.w));
+          }
+          if (p.residual) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&rs[k]);
+#pragma unroll
+              for (int uu = 0; uu < 4; ++uu) v2[k * 4 + uu] = add2(v2[k * 4 + uu], __bfloat1622float2(gp[uu]));
+            }
+          }
+          if (leader) bulk_wait_read_all();  // the slot's previous store has been read
+          named_bar_sync(1 + grp, 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint4 o = {pack_bf16(v[k * 8], v[k * 8 + 1]), pack_bf16(v[k * 8 + 2], v[k * 8 + 3]),
+                             pack_bf16(v[k * 8 + 4], v[k * 8 + 5]), pack_bf16(v[k * 8 + 6], v[k * 8 + 7])};
+            *reinterpret_cast<uint4*>(sbase + r * 64 + ((k ^ sw64) << 4)) = o;
+          }
+          tc::fence_proxy_async();
+          named_bar_sync(1 + grp, 128);
+          if (leader) {
+            tma_store_2d(&tmap_out, sbase, box * BOX_N, m0);
+            bulk_commit();
+          }
+        }
+      }
+    }
+    if (leader) bulk_wait_all();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, s192::TMEM_COLS);
+  }
+}
+
 // 2-D bf16 tensor [rows, cols], box = [box_rows, 32 cols], 64-byte swizzle
 int make_map32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   svit_tmap_encode_fn enc = svit_get_tmap_encode();
@@ -761,37 +731,6 @@ int make_map32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, ui
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : SVIT_EINVAL;
-}
-
-template <int C, int NOUT>
-int launch(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const void* residual, void* out,
-           int64_t M, int H, cudaStream_t st) {
-  using L = Cfg<C, NOUT>;
-  CUtensorMap tx64, tx32, tw164, tw132, tw2, tres, tout;
-  int rc;
-  if ((rc = svit_make_tmap_2d(&tx64, x, (uint64_t)M, C, C, BM))) return rc;
-  tx32 = tx64;
-  if (L::KB && (rc = make_map32(&tx32, x, (uint64_t)M, C, C, BM))) return rc;
-  if ((rc = svit_make_tmap_2d(&tw164, w1, (uint64_t)H, C, C, HC))) return rc;
-  tw132 = tw164;
-  if (L::KB && (rc = make_map32(&tw132, w1, (uint64_t)H, C, C, HC))) return rc;
-  if ((rc = svit_make_tmap_2d(&tw2, w2, NOUT, (uint64_t)H, (uint64_t)H, NOUT))) return rc;
-  if ((rc = make_map32(&tout, out, (uint64_t)M, NOUT, NOUT, BM))) return rc;
-  tres = tout;
-  if (residual && (rc = make_map32(&tres, residual, (uint64_t)M, NOUT, NOUT, BM))) return rc;
-  Params p;
-  p.b1 = b1; p.b2 = b2; p.M = (int)M; p.H = H; p.has_res = residual ? 1 : 0;
-  auto kern = mlp_fused_kernel<C, NOUT>;
-  static SvitDevOnce configured;
-  if (configured.need()) {
-    SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured.done();
-  }
-  const int64_t tiles = (M + BM - 1) / BM;
-  const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
-  kern<<<grid, NTHREADS, L::TOTAL, st>>>(tx64, tx32, tw164, tw132, tw2, tres, tout, p);
-  SVIT_CHECK_LAUNCH();
-  return 0;
 }
 
 int launch_resident96(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const void* residual,
@@ -821,6 +760,31 @@ int launch_resident96(const void* x, const void* w1, const float* b1, const void
   return 0;
 }
 
+int launch_stream192(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const void* residual,
+                     void* out, int64_t M, cudaStream_t st) {
+  using namespace s192;
+  CUtensorMap tx, tw1, tw2, tout;
+  int rc;
+  if ((rc = svit_make_tmap_2d(&tx, x, (uint64_t)M, C, C, BM))) return rc;
+  if ((rc = svit_make_tmap_2d(&tw1, w1, (uint64_t)H, C, C, HC))) return rc;
+  if ((rc = svit_make_tmap_2d(&tw2, w2, NOUT, (uint64_t)H, (uint64_t)H, NOUT))) return rc;
+  if ((rc = make_map32(&tout, out, (uint64_t)M, NOUT, NOUT, BM))) return rc;
+  ParamsR p;
+  p.dbg = nullptr;
+  p.b1 = b1; p.b2 = b2; p.gamma = nullptr; p.beta = nullptr; p.eps = 0.f; p.M = (int)M;
+  p.residual = (const bf16*)residual;
+  static SvitDevOnce configured;
+  if (configured.need()) {
+    SVIT_CUDA(cudaFuncSetAttribute(mlp_stream192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    configured.done();
+  }
+  const int64_t tiles = (M + BM - 1) / BM;
+  const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
+  mlp_stream192_kernel<<<grid, NTHR, TOTAL, st>>>(tx, tw1, tw2, tout, p);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -834,9 +798,7 @@ extern "C" int svit_debug_mlp_timeline(void* device_buffer) {
 
 extern "C" int svit_mlp_fused_supported(int64_t M, int C, int H, int N) {
   if (M < 1 || M >= (1ll << 31) - BM) return 0;
-  // (192, 768, 192) runs through the weight-streaming kernel below, which is not yet faster than the two GEMMs it would
-  // replace (428 vs 398 us at M = 405 568): only the resident-weight shape is offered
-  if (!(C == 96 && N == 96)) return 0;
+  if (!((C == 96 && N == 96) || (C == 192 && N == 192))) return 0;
   return H == 4 * C;
 }
 
@@ -856,5 +818,5 @@ extern "C" int svit_mlp_fused(const void* x, const void* w1, const float* b1, co
   if (out == x || out == residual) return SVIT_ENOTSUP;  // rows are re-read (L2 prefetch, residual) while others are stored
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 96) return launch_resident96(x, w1, b1, w2, b2, residual, out, M, ln_gamma, ln_beta, eps, st);
-  return launch<192, 192>(x, w1, b1, w2, b2, residual, out, M, H, st);
+  return launch_stream192(x, w1, b1, w2, b2, residual, out, M, st);
 }

@@ -347,9 +347,14 @@ class MultiScaleBlock(nn.Module):
         m = self.mlp
         sc = self._scale(x)  # ONE draw per branch, in the reference's order (common.py:46-70)
         if ops.mlp_fused_applicable(x, m.fc1.weight, m.fc2.weight, sc):
-            # inference, first stage: norm2 + fc1 + GELU + fc2 + residual as one kernel (hidden activation stays on chip)
-            x = ops.mlp_fused(x, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, residual=x,
-                              ln=(self.norm2.weight, self.norm2.bias, self.norm2.eps))
+            # inference, first / second stage: fc1 + GELU + fc2 + residual as one kernel (hidden activation stays on chip);
+            # at width 96 norm2 is the kernel's prologue as well
+            if ops.mlp_fused_has_ln(x.shape[-1]):
+                x = ops.mlp_fused(x, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, residual=x,
+                                  ln=(self.norm2.weight, self.norm2.bias, self.norm2.eps))
+            else:
+                x_norm2 = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+                x = ops.mlp_fused(x_norm2, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, residual=x)
             return x, thw_new
         x_norm2 = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         x = self.mlp(x_norm2, residual=x, sample_scale=sc)
@@ -365,7 +370,7 @@ class MultiScaleBlock(nn.Module):
         x_res = ops.skip_pool(x, thw_shape, O, self._sq)
         x, thw_new = self.attn(x_in, thw_shape, residual=x_res, sample_scale=self._scale(x), ln=(st1, self.norm1))
         m = self.mlp
-        if ops.mlp_fused_applicable(x, m.fc1.weight, m.fc2.weight):  # (the folded path is inference only: no DropPath scale)
+        if ops.mlp_fused_applicable(x, m.fc1.weight, m.fc2.weight) and ops.mlp_fused_has_ln(x.shape[-1]):
             return ops.mlp_fused(x, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, residual=x,
                                  ln=(self.norm2.weight, self.norm2.bias, self.norm2.eps)), thw_new
         if not ops.ln_fold_applicable(x, self.mlp.fc1.weight):  # fewer than 128 pooled rows (tiny test geometries)

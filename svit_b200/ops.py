@@ -272,17 +272,22 @@ class _Mlp(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2, dres, None, None
 
 
-_MLP_FUSED = {"enabled": os.environ.get("SVIT_MLP_FUSED", "1") != "0"}
+_MLP_FUSED = {"enabled": os.environ.get("SVIT_MLP_FUSED", "1") != "0", "max_width": int(os.environ.get("SVIT_MLP_FUSED_MAXW", "192"))}
 
 
 def mlp_fused_applicable(x, w1, w2, sample_scale=None) -> bool:
     """svit_mlp_fused: inference (no autograd, no DropPath scale), bf16, the tcgen05 path, a supported (C, H, N)."""
     if not _MLP_FUSED["enabled"] or torch.is_grad_enabled() or sample_scale is not None or x.dtype != torch.bfloat16:
         return False
-    if _state["gemm_impl"] == IMPL_SIMT or not x.is_cuda:
+    if _state["gemm_impl"] == IMPL_SIMT or not x.is_cuda or x.shape[-1] > _MLP_FUSED["max_width"]:
         return False
     M = x.numel() // x.shape[-1]
     return bool(_lib.lib().svit_mlp_fused_supported(M, x.shape[-1], w1.shape[0], w2.shape[0]))
+
+
+def mlp_fused_has_ln(width: int) -> bool:
+    """The LayerNorm prologue exists in the resident-weight kernel (width 96) only."""
+    return width == 96
 
 
 def mlp_fused(x, w1, b1, w2, b2, residual=None, ln=None):

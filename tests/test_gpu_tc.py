@@ -351,14 +351,14 @@ def test_folded_weight_cache_follows_parameter_updates():
 
 
 # ------------------------------------------------------------------------------------------------ fused MLP
-@pytest.mark.parametrize("M,mode", [(128, "res"), (1000, "res"), (40000, "none"), (257, "ln"), (30000, "ln"), (5000, "self"),
-                                    (129, "ln_nores")])
-def test_mlp_fused_matches_reference(M, mode):
+@pytest.mark.parametrize("Cn,M,mode", [(96, 128, "res"), (96, 1000, "res"), (96, 40000, "none"), (96, 257, "ln"),
+                                       (96, 30000, "ln"), (96, 5000, "self"), (96, 129, "ln_nores"), (192, 128, "res"),
+                                       (192, 777, "none"), (192, 50000, "self"), (192, 19000, "res")])
+def test_mlp_fused_matches_reference(Cn, M, mode):
     """svit_mlp_fused (hidden activation kept on chip, optional LayerNorm prologue) against fp64 LayerNorm -> fc1 ->
     exact-erf GELU -> fc2 (+ residual) of the same bf16 operands (common.py:27-34, attention.py:566-570), and against the
     LayerNorm + two-GEMM path it replaces."""
-    Cn = 96
-    gen = torch.Generator().manual_seed(51 + M)
+    gen = torch.Generator().manual_seed(51 + M + Cn)
     Hd = 4 * Cn
     x = (torch.randn(M, Cn, generator=gen) * 1.3 + 0.4 * torch.randn(M, 1, generator=gen)).to(torch.bfloat16)
     w1 = (torch.randn(Hd, Cn, generator=gen) * Cn ** -0.5).to(torch.bfloat16)
