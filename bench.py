@@ -502,9 +502,13 @@ def main():
         m = re.match(r"svit_gemm\[(\d+)x(\d+)x(\d+)\]", tag)
         a = re.match(r"svit_attn_fwd\[B(\d+) h(\d+) Nq(\d+) Nk(\d+)\]", tag)
         pl = re.match(r"svit_pool_ln_fwd\[\w B(\d+) h(\d+) (\d+)x(\d+)x(\d+) s(\d+)\]", tag)
+        mf = re.match(r"svit_mlp_fused\[(\d+)x(\d+)x(\d+)x(\d+)\]", tag)
         if m:
             M_, N_, K_ = (int(x) for x in m.groups())
             work, bound = 2.0 * M_ * N_ * K_, "tensor"
+        elif mf:  # fc1 + fc2 in one kernel: [M x C x H x N]
+            M_, C_, H_, N_ = (int(x) for x in mf.groups())
+            work, bound = 2.0 * M_ * H_ * (C_ + N_), "tensor"
         elif a:
             B_, h_, Nq_, Nk_ = (int(x) for x in a.groups())
             work, bound = 4.0 * B_ * h_ * Nq_ * Nk_ * 96, "tensor"
