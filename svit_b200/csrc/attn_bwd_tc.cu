@@ -37,35 +37,58 @@ __device__ __forceinline__ const bf16* rel_row(const svit_attn_args& a, int c, i
 }
 
 // ---- prep: delta and the bias terms E ----------------------------------------------------------------------
+// 16-byte accesses throughout: a group of 16 lanes (12 active, 8 channels each) owns a row for delta; the bias terms are
+// one (row, column) item per thread against the row's fp32 copy of q in shared memory (broadcast 16-byte reads).
+constexpr int QP = D + 4;  // fp32 pitch of the q tile: 16-byte aligned rows
+
+__device__ __forceinline__ void unpack8(const uint4 w, float f[8]) {
+  f[0] = __uint_as_float(w.x << 16); f[1] = __uint_as_float(w.x & 0xffff0000u);
+  f[2] = __uint_as_float(w.y << 16); f[3] = __uint_as_float(w.y & 0xffff0000u);
+  f[4] = __uint_as_float(w.z << 16); f[5] = __uint_as_float(w.z & 0xffff0000u);
+  f[6] = __uint_as_float(w.w << 16); f[7] = __uint_as_float(w.w & 0xffff0000u);
+}
+
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, int nep) {
-  __shared__ float sq[PQ][D + 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ __align__(16) float sq[PQ][QP];
   const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
   const int64_t Nq = 1 + Lq + a.O;
   const int ne = a.kh + a.kw + a.kt;
   const int bh = blockIdx.y, b = bh / a.h, head = bh % a.h;
   const int64_t r0 = (int64_t)blockIdx.x * PQ;
   const bf16* q = (const bf16*)a.q + (int64_t)bh * Nq * D;
-  for (int idx = threadIdx.x; idx < PQ * D; idx += blockDim.x) {
-    const int r = idx / D, d = idx % D;
-    sq[r][d] = r0 + r < Nq ? __bfloat162float(q[(r0 + r) * D + d]) : 0.f;
+  for (int idx = threadIdx.x; idx < PQ * (D / 8); idx += blockDim.x) {
+    const int r = idx / (D / 8), u = idx % (D / 8);
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r0 + r < Nq) unpack8(__ldg(reinterpret_cast<const uint4*>(q + (r0 + r) * D) + u), f);
+    *reinterpret_cast<float4*>(&sq[r][u * 8]) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(&sq[r][u * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
   }
   __syncthreads();
+  {  // delta[row] = dO . (out - q[rows >= 1]): 16 lanes per row, two rows per group
+    const int grp = threadIdx.x >> 4, l = threadIdx.x & 15;
 #pragma unroll
-  for (int rr = 0; rr < PQ / 8; ++rr) {
-    const int r = warp * (PQ / 8) + rr;
-    const int64_t row = r0 + r;
-    if (row >= Nq) continue;
-    const int64_t off = (((int64_t)b * Nq + row) * a.h + head) * D;
-    float part = 0.f;
+    for (int rr = 0; rr < PQ / 16; ++rr) {
+      const int r = grp * (PQ / 16) + rr;
+      const int64_t row = r0 + r;
+      float part = 0.f;
+      if (row < Nq && l < D / 8) {
+        const int64_t off = (((int64_t)b * Nq + row) * a.h + head) * D + 8 * l;
+        float o[8], g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>((const bf16*)a.out + off)), o);
+        unpack8(__ldg(reinterpret_cast<const uint4*>((const bf16*)a.dout + off)), g);
+        if (row >= 1) {
+          const float4 qa = *reinterpret_cast<const float4*>(&sq[r][8 * l]);
+          const float4 qb = *reinterpret_cast<const float4*>(&sq[r][8 * l + 4]);
+          o[0] -= qa.x; o[1] -= qa.y; o[2] -= qa.z; o[3] -= qa.w;
+          o[4] -= qb.x; o[5] -= qb.y; o[6] -= qb.z; o[7] -= qb.w;
+        }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float o = __bfloat162float(((const bf16*)a.out)[off + lane + 32 * j]);
-      if (row >= 1) o -= sq[r][lane + 32 * j];
-      part += o * __bfloat162float(((const bf16*)a.dout)[off + lane + 32 * j]);
+        for (int e = 0; e < 8; ++e) part = fmaf(o[e], g[e], part);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o, 16);
+      if (l == 0 && row < Nq) a.ws_delta[(int64_t)bh * Nq + row] = part;
     }
-    part = warp_sum(part);
-    if (lane == 0) a.ws_delta[(int64_t)bh * Nq + row] = part;
   }
   for (int idx = threadIdx.x; idx < PQ * nep; idx += blockDim.x) {
     const int r = idx / nep, c = idx % nep;
@@ -76,17 +99,19 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, in
       const int64_t p = row - 1;
       const int j = (int)(p % a.qw), i = (int)((p / a.qw) % a.qh), t = (int)(p / ((int64_t)a.qw * a.qh));
       const uint4* R = reinterpret_cast<const uint4*>(rel_row(a, c, i, j, t));
+      float acc2 = 0.f;
 #pragma unroll
       for (int u = 0; u < D / 8; ++u) {
-        const uint4 w = __ldg(R + u);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(h2[e]);
-          acc = fmaf(sq[r][u * 8 + 2 * e], f.x, acc);
-          acc = fmaf(sq[r][u * 8 + 2 * e + 1], f.y, acc);
-        }
+        float f[8];
+        unpack8(__ldg(R + u), f);
+        const float4 qa = *reinterpret_cast<const float4*>(&sq[r][u * 8]);
+        const float4 qb = *reinterpret_cast<const float4*>(&sq[r][u * 8 + 4]);
+        acc = fmaf(qa.x, f[0], acc); acc2 = fmaf(qa.y, f[1], acc2);
+        acc = fmaf(qa.z, f[2], acc); acc2 = fmaf(qa.w, f[3], acc2);
+        acc = fmaf(qb.x, f[4], acc); acc2 = fmaf(qb.y, f[5], acc2);
+        acc = fmaf(qb.z, f[6], acc); acc2 = fmaf(qb.w, f[7], acc2);
       }
+      acc += acc2;
     }
     a.ws_e[((int64_t)bh * Nq + row) * nep + c] = acc;
   }
@@ -161,36 +186,59 @@ __global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(svit_attn_args a,
 // ---- dq = dq_part (already scaled) + sum_c dE[c] R_c + dO[rows >= 1] -------------------------------------------
 __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(svit_attn_args a, const float* __restrict__ dq_part,
                                                               int nep, int64_t total_rows) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // 16 lanes per (b, head, query row), 12 of them active with 8 channels each (16-byte accesses); the row's bias
+  // gradients dE[c] sit in registers of the group (lane l holds c = l, l + 16, ...) and are broadcast by shuffles
+  const int l = threadIdx.x & 15;
   const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
   const int64_t Nq = 1 + Lq + a.O;
   const int ne = a.kh + a.kw + a.kt;
-  const int64_t R = (int64_t)blockIdx.x * 8 + warp;
-  if (R >= total_rows) return;
-  const int64_t bh = R / Nq, row = R % Nq;
+  const int64_t R = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4);
+  const bool rok = R < total_rows;  // (all lanes stay for the shuffles)
+  const int64_t Rc = rok ? R : total_rows - 1;
+  const int64_t bh = Rc / Nq, row = Rc % Nq;
   const int b = (int)(bh / a.h), head = (int)(bh % a.h);
-  float g[3];
+  const bool act = l < D / 8;
+  float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (act) {
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(dq_part + Rc * D + 8 * l));
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(dq_part + Rc * D + 8 * l + 4));
+    g[0] = ga.x; g[1] = ga.y; g[2] = ga.z; g[3] = ga.w; g[4] = gb.x; g[5] = gb.y; g[6] = gb.z; g[7] = gb.w;
+  }
+  const bool patch = row >= 1 && row <= Lq;  // uniform within the 16-lane group
+  float dreg[MAXE / 16];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) g[j] = dq_part[R * D + lane + 32 * j];
-  if (row >= 1 && row <= Lq) {
-    const int64_t p = row - 1;
+  for (int k = 0; k < MAXE / 16; ++k) dreg[k] = (patch && l + 16 * k < ne) ? __ldg(a.ws_de + Rc * nep + l + 16 * k) : 0.f;
+  {
+    const int64_t p = patch ? row - 1 : 0;
     const int jq = (int)(p % a.qw), iq = (int)((p / a.qw) % a.qh), tq = (int)(p / ((int64_t)a.qw * a.qh));
-    const float* de = a.ws_de + R * nep;
-    for (int c = 0; c < ne; ++c) {
-      const float w = de[c];
-      const bf16* Rr = rel_row(a, c, iq, jq, tq);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) g[j] = fmaf(w, __bfloat162float(Rr[lane + 32 * j]), g[j]);
+    for (int k = 0; k < MAXE / 16; ++k) {
+      for (int cc = 0; cc < 16; ++cc) {
+        const int c = 16 * k + cc;
+        if (c >= ne) break;  // uniform
+        const float w = __shfl_sync(0xffffffffu, dreg[k], cc, 16);
+        if (patch && act) {
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(rel_row(a, c, iq, jq, tq)) + l), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] = fmaf(w, f[e], g[e]);
+        }
+      }
     }
   }
+  if (!rok || !act) return;
   if (row >= 1) {
-    const bf16* dO = (const bf16*)a.dout + (((int64_t)b * Nq + row) * a.h + head) * D;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>((const bf16*)a.dout + (((int64_t)b * Nq + row) * a.h + head) * D) + l), f);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) g[j] += __bfloat162float(dO[lane + 32 * j]);
+    for (int e = 0; e < 8; ++e) g[e] += f[e];
   }
-  bf16* dq = (bf16*)a.dq + R * D;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) dq[lane + 32 * j] = __float2bfloat16_rn(g[j]);
+  __nv_bfloat162 o0 = __floats2bfloat162_rn(g[0], g[1]), o1 = __floats2bfloat162_rn(g[2], g[3]);
+  __nv_bfloat162 o2 = __floats2bfloat162_rn(g[4], g[5]), o3 = __floats2bfloat162_rn(g[6], g[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&o0); o.y = *reinterpret_cast<uint32_t*>(&o1);
+  o.z = *reinterpret_cast<uint32_t*>(&o2); o.w = *reinterpret_cast<uint32_t*>(&o3);
+  *(reinterpret_cast<uint4*>((bf16*)a.dq + Rc * D) + l) = o;
 }
 
 void gemm_defaults(svit_gemm_args& g) {
@@ -294,7 +342,7 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
   g.M = rows; g.N = nep; g.K = Nk; g.batch = 1;
   if ((rc = run_gemm(g, st))) return rc;
 
-  attn_bwd_finish_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(*a, a->ws_dq, nep, rows);
+  attn_bwd_finish_kernel<<<(unsigned)ceil_div64(rows, 16), 256, 0, st>>>(*a, a->ws_dq, nep, rows);
   SVIT_CHECK_LAUNCH();
   return svit_attn_bwd_drel(a, nep, st);
 }

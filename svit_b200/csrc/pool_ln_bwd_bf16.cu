@@ -166,45 +166,48 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
   }
 }
 
-// block = 288 threads: pair = tid % 48 (channels 2 pair, 2 pair + 1), tg = (tid / 48) % 3 (temporal tap plane),
-// half = tid / 144 (token parity inside the chunk).  grid = (chunks, B * h).
-__global__ void __launch_bounds__(288) pool_bwd_dw_kernel(const bf16* __restrict__ in, Geom g,
+// block = 288 threads: quad = tid % 24 (channels 4 quad .. 4 quad + 3, 8-byte accesses), tg = (tid / 24) % 3 (temporal tap
+// plane), part = tid / 72 (token index mod 4 inside the chunk).  grid = (chunks, B * h).
+__global__ void __launch_bounds__(288, 3) pool_bwd_dw_kernel(const bf16* __restrict__ in, Geom g,
                                                           const float* __restrict__ frac, const bf16* __restrict__ dpre,
                                                           float* __restrict__ dw, int chunk) {
-  __shared__ float sacc[144 * 18];
-  const int pair = threadIdx.x % 48, tg = (threadIdx.x / 48) % 3, half = threadIdx.x / 144;
+  __shared__ float sacc[3 * 72 * 36];  // partials of parts 1..3, later the combined [96][27] gradient
+  __shared__ float swe[4 * 24 * 4];
+  const int quad = threadIdx.x % 24, tg = (threadIdx.x / 24) % 3, part = threadIdx.x / 72;
   const int Lo = g.T * g.Ho * g.Wo, L = g.T * g.H * g.W;
   const int Nout = 1 + Lo + g.O;
   const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
-  const bf16* zin = in + b * g.in_bs + head * g.in_hs + 2 * pair;
-  const bf16* dp_base = dpre + (int64_t)bh * Nout * PD + 2 * pair;
+  const bf16* zin = in + b * g.in_bs + head * g.in_hs + 4 * quad;
+  const bf16* dp_base = dpre + (int64_t)bh * Nout * PD + 4 * quad;
   const int t0 = blockIdx.x * chunk;
   const int t1 = t0 + chunk < Nout ? t0 + chunk : Nout;
-  float acc[9][2], aweff[2] = {0.f, 0.f};
+  float acc[9][4], aweff[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = 0.f;
-  // (to, ho, wo) of the thread's current patch token, advanced by 2 per iteration (no division in the loop)
+  for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+  // (to, ho, wo) of the thread's current patch token, advanced by 4 per iteration (no division in the loop)
   int wo, ho, to;
   {
-    const int first = t0 + half < 1 ? t0 + half + 2 : t0 + half;  // first token this thread decodes as a patch token
+    const int first = t0 + part < 1 ? t0 + part + 4 : t0 + part;  // first token this thread decodes as a patch token
     const unsigned p = first - 1;
     const unsigned pr = p / (unsigned)g.Wo;
     wo = (int)(p - pr * g.Wo); to = (int)(pr / (unsigned)g.Ho); ho = (int)(pr - to * g.Ho);
   }
 #pragma unroll 2
-  for (int tok = t0 + half; tok < t1; tok += 2) {
+  for (int tok = t0 + part; tok < t1; tok += 4) {
     if (tok == 0) continue;  // cls passes through: no weight gradient
-    const float2 dp = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp_base + tok * PD));
+    float dp[4];
+    unpack4(*reinterpret_cast<const uint2*>(dp_base + tok * PD), dp);
     if (tok > Lo) {
       if (tg == 0) {
-        const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zin + (tok - Lo + L) * g.its));
-        aweff[0] = fmaf(dp.x, z.x, aweff[0]);
-        aweff[1] = fmaf(dp.y, z.y, aweff[1]);
+        float z[4];
+        unpack4(*reinterpret_cast<const uint2*>(zin + (tok - Lo + L) * g.its), z);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) aweff[e] = fmaf(dp[e], z[e], aweff[e]);
       }
       continue;
     }
     const int cwo = wo, cho = ho, cto = to;
-    wo += 2;
+    wo += 4;
     while (wo >= g.Wo) {
       wo -= g.Wo;
       if (++ho == g.Ho) { ho = 0; ++to; }
@@ -220,57 +223,51 @@ __global__ void __launch_bounds__(288) pool_bwd_dw_kernel(const bf16* __restrict
       for (int kw = 0; kw < 3; ++kw) {
         const int ww = cwo * g.s - 1 + kw;
         if (ww < 0 || ww >= g.W) continue;
-        const float2 z = __bfloat1622float2(
-            *reinterpret_cast<const __nv_bfloat162*>(zin + (rowbase + ww) * g.its));
-        acc[kh * 3 + kw][0] = fmaf(dp.x, z.x, acc[kh * 3 + kw][0]);
-        acc[kh * 3 + kw][1] = fmaf(dp.y, z.y, acc[kh * 3 + kw][1]);
+        float z[4];
+        unpack4(*reinterpret_cast<const uint2*>(zin + (rowbase + ww) * g.its), z);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[kh * 3 + kw][e] = fmaf(dp[e], z[e], acc[kh * 3 + kw][e]);
       }
     }
   }
   // object-token path: every tap of the plane gets tap_frac * d w_eff (tg 0 holds d w_eff; share it through smem)
-  float* swe = sacc;  // [2][48][2] reused before the main reduction
   if (tg == 0) {
-    swe[(half * 48 + pair) * 2] = aweff[0];
-    swe[(half * 48 + pair) * 2 + 1] = aweff[1];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) swe[(part * 24 + quad) * 4 + e] = aweff[e];
+  }
+  if (part > 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[((part - 1) * 72 + tg * 24 + quad) * 36 + k * 4 + e] = acc[k][e];
   }
   __syncthreads();
-  if (half == 0) {
-    const float e0 = swe[pair * 2] + swe[(48 + pair) * 2], e1 = swe[pair * 2 + 1] + swe[(48 + pair) * 2 + 1];
+  if (part == 0) {
+    float e4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      e4[e] = swe[quad * 4 + e] + swe[(24 + quad) * 4 + e] + swe[(48 + quad) * 4 + e] + swe[(72 + quad) * 4 + e];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const float f = frac[tg * 9 + k];
-      acc[k][0] = fmaf(f, e0, acc[k][0]);
-      acc[k][1] = fmaf(f, e1, acc[k][1]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = fmaf(f, e4[e], acc[k][e]);
+#pragma unroll
+        for (int pp = 0; pp < 3; ++pp) v += sacc[(pp * 72 + tg * 24 + quad) * 36 + k * 4 + e];
+        acc[k][e] = v;
+      }
     }
   }
   __syncthreads();
-  if (half == 1) {
+  // laid out like dw ([channel][tap]) so that the global atomics of a warp fall on consecutive addresses (one L2
+  // transaction per 128-byte line instead of one per element)
+  float* sdw = sacc;  // [96 * 27]
+  if (part == 0) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      sacc[(threadIdx.x - 144) * 18 + 2 * k] = acc[k][0];
-      sacc[(threadIdx.x - 144) * 18 + 2 * k + 1] = acc[k][1];
-    }
-  }
-  __syncthreads();
-  // combine the two halves in place, laid out like dw ([channel][tap]) so that the global atomics of a warp fall on
-  // consecutive addresses (one L2 transaction per 128-byte line instead of one per element)
-  __syncthreads();
-  float* sdw = sacc;  // [96 * 27], written by half 0 after reading its partner's partials
-  float mine[9][2];
-  if (half == 0) {
+    for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      mine[k][0] = acc[k][0] + sacc[threadIdx.x * 18 + 2 * k];
-      mine[k][1] = acc[k][1] + sacc[threadIdx.x * 18 + 2 * k + 1];
-    }
-  }
-  __syncthreads();
-  if (half == 0) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      sdw[(2 * pair) * TAPS + tg * 9 + k] = mine[k][0];
-      sdw[(2 * pair + 1) * TAPS + tg * 9 + k] = mine[k][1];
-    }
+      for (int e = 0; e < 4; ++e) sdw[(4 * quad + e) * TAPS + tg * 9 + k] = acc[k][e];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < PD * TAPS; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
