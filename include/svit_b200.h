@@ -69,6 +69,13 @@ int svit_skip_maxpool_fwd(const void* x, void* y, int B, int C, int T, int H, in
                           void* stream);
 int svit_skip_maxpool_bwd(const void* x, const void* dy, void* dx, int B, int C, int T, int H, int W, int O,
                           int stride_hw, int dtype, void* stream);
+/* Training variant (bf16, C % 8 == 0, else SVIT_ENOTSUP): the forward also records, per output element, which of the nine
+ * window positions won (idx [B, 1+T*Ho*Wo+O, C] bytes, first maximum in ATen's scan order); the backward reads idx
+ * instead of x and re-scanning the windows. */
+int svit_skip_maxpool_fwd_idx(const void* x, void* y, void* idx, int B, int C, int T, int H, int W, int O, int stride_hw,
+                              int dtype, void* stream);
+int svit_skip_maxpool_bwd_idx(const void* idx, const void* dy, void* dx, int B, int C, int T, int H, int W, int O,
+                              int stride_hw, int dtype, void* stream);
 
 /* ---- GEMM with fused epilogue: nn.Linear sites attention.py:345 (qkv), :462 (proj), :561 (skip proj),
  * common.py:27-34 (fc1+GELU, fc2), stem_helper.py:317 (patch embed as im2col GEMM), and their gradients.

@@ -67,6 +67,8 @@ PROTOTYPES = {
     "svit_pool_ln_bwd": [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp] + [C.c_int] * 7 + [f32, C.c_int, vp],
     "svit_skip_maxpool_fwd": [vp, vp] + [C.c_int] * 8 + [vp],
     "svit_skip_maxpool_bwd": [vp, vp, vp] + [C.c_int] * 8 + [vp],
+    "svit_skip_maxpool_fwd_idx": [vp, vp, vp] + [C.c_int] * 8 + [vp],
+    "svit_skip_maxpool_bwd_idx": [vp, vp, vp] + [C.c_int] * 8 + [vp],
     "svit_gemm": [C.POINTER(GemmArgs), vp],
     "svit_colsum": [vp, vp, i64, C.c_int, i64, C.c_int, vp],
     "svit_scale_rows": [vp, vp, vp, i64, C.c_int, i64, C.c_int, vp],

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
   __shared__ __align__(16) float sw[TAPS * PD];
   __shared__ __align__(16) float sweff[PD];
   __shared__ float sred[2 * PD];
-  load_weights(w, frac, sw, sweff);
+  if (!pre) load_weights(w, frac, sw, sweff);  // the saved pre-LayerNorm rows make the convolution (and its weights) unnecessary
   for (int i = threadIdx.x; i < 2 * PD; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;

@@ -173,7 +173,11 @@ __global__ void __launch_bounds__(256) im2col_rows_vec_kernel(const bf16* __rest
 }
 
 // skip-path MaxPool3d k(1,3,3) s(1,s,s) p(0,1,1) on [B, N, C] (attention.py:562-564): one thread per 8 channels
-__global__ void __launch_bounds__(256) skip_maxpool_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int C,
+// IDX: also record, per output element, which of the 9 window positions (dh * 3 + dw, ATen's scan order, first maximum)
+// won -- the backward then compares one byte instead of re-scanning up to four windows of nine values per input element.
+template <bool IDX>
+__global__ void __launch_bounds__(256) skip_maxpool_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                                uint8_t* __restrict__ idx, int B, int C,
                                                                 int T_, int H, int W, int Ho, int Wo, int O, int s) {
   const int C8 = C >> 3;
   const int64_t Lin = (int64_t)T_ * H * W, Lout = (int64_t)T_ * Ho * Wo;
@@ -205,8 +209,9 @@ __global__ void __launch_bounds__(256) skip_maxpool_bf16_kernel(const bf16* __re
               ? *reinterpret_cast<const uint4*>(xb + (1 + ((int64_t)t * H + hh) * W + ww) * C) : make_uint4(0, 0, 0, 0);
         }
       float m[8];
+      uint32_t win[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) m[u] = -INFINITY;
+      for (int u = 0; u < 8; ++u) { m[u] = -INFINITY; win[u] = 0u; }
 #pragma unroll
       for (int k = 0; k < 9; ++k)
         if (ok[k]) {
@@ -214,17 +219,113 @@ __global__ void __launch_bounds__(256) skip_maxpool_bf16_kernel(const bf16* __re
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float a = __uint_as_float(wv[u] << 16), c = __uint_as_float(wv[u] & 0xffff0000u);
-            if (a > m[2 * u] || a != a) m[2 * u] = a;
-            if (c > m[2 * u + 1] || c != c) m[2 * u + 1] = c;
+            if (a > m[2 * u] || a != a) { m[2 * u] = a; if (IDX) win[2 * u] = (uint32_t)k; }
+            if (c > m[2 * u + 1] || c != c) { m[2 * u + 1] = c; if (IDX) win[2 * u + 1] = (uint32_t)k; }
           }
         }
       o.x = pack2(m[0], m[1]); o.y = pack2(m[2], m[3]); o.z = pack2(m[4], m[5]); o.w = pack2(m[6], m[7]);
+      if (IDX) {
+        uint2 iv;
+        iv.x = win[0] | (win[1] << 8) | (win[2] << 16) | (win[3] << 24);
+        iv.y = win[4] | (win[5] << 8) | (win[6] << 16) | (win[7] << 24);
+        *reinterpret_cast<uint2*>(idx + ((int64_t)b * Nout + tok) * C + c8 * 8) = iv;
+      }
     }
     *reinterpret_cast<uint4*>(y + ((int64_t)b * Nout + tok) * C + c8 * 8) = o;
   }
 }
 
+// Backward with the recorded window positions: thread = 8 channels of one INPUT token; for each of the (at most four)
+// windows that contain the token it compares the eight recorded positions with its own and takes dy where they match.
+__global__ void __launch_bounds__(256) skip_maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__ dy,
+                                                                   bf16* __restrict__ dx, int B, int C, int T_, int H, int W,
+                                                                   int Ho, int Wo, int O, int s) {
+  const int C8 = C >> 3;
+  const int64_t Lin = (int64_t)T_ * H * W, Lout = (int64_t)T_ * Ho * Wo;
+  const int64_t Nin = 1 + Lin + O, Nout = 1 + Lout + O;
+  const int64_t total = (int64_t)B * Nin * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const int64_t r = i / C8;
+    const int64_t tok = r % Nin;
+    const int b = (int)(r / Nin);
+    const bf16* dyb = dy + (int64_t)b * Nout * C + c;
+    const uint8_t* ib = idx + (int64_t)b * Nout * C + c;
+    bf16* o = dx + r * C + c;
+    if (tok == 0) {
+      *reinterpret_cast<uint4*>(o) = __ldg(reinterpret_cast<const uint4*>(dyb));
+      continue;
+    }
+    if (tok > Lin) {
+      *reinterpret_cast<uint4*>(o) = __ldg(reinterpret_cast<const uint4*>(dyb + (tok - Lin + Lout) * C));
+      continue;
+    }
+    const int64_t p = tok - 1;
+    const int w = (int)(p % W), h = (int)((p / W) % H), t = (int)(p / ((int64_t)W * H));
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ho = (h - 1 + s - 1) / s; ho * s <= h + 1 && ho < Ho; ++ho) {
+      if (ho < 0) continue;
+      const int dh = h - (ho * s - 1);
+      for (int wo = (w - 1 + s - 1) / s; wo * s <= w + 1 && wo < Wo; ++wo) {
+        if (wo < 0) continue;
+        const uint32_t me = (uint32_t)(dh * 3 + (w - (wo * s - 1)));
+        const int64_t orow = 1 + ((int64_t)t * Ho + ho) * Wo + wo;
+        const uint2 iv = __ldg(reinterpret_cast<const uint2*>(ib + orow * C));
+        const uint32_t hit_lo = iv.x ^ (me * 0x01010101u), hit_hi = iv.y ^ (me * 0x01010101u);  // zero byte = match
+        if (((hit_lo - 0x01010101u) & ~hit_lo & 0x80808080u) | ((hit_hi - 0x01010101u) & ~hit_hi & 0x80808080u)) {
+          const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dyb + orow * C));
+          const uint32_t wv[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t b0 = ((u < 2 ? hit_lo : hit_hi) >> (16 * (u & 1))) & 0xffu;
+            const uint32_t b1 = ((u < 2 ? hit_lo : hit_hi) >> (16 * (u & 1) + 8)) & 0xffu;
+            if (b0 == 0u) g[2 * u] += __uint_as_float(wv[u] << 16);
+            if (b1 == 0u) g[2 * u + 1] += __uint_as_float(wv[u] & 0xffff0000u);
+          }
+        }
+      }
+    }
+    uint4 ov;
+    ov.x = pack2(g[0], g[1]); ov.y = pack2(g[2], g[3]); ov.z = pack2(g[4], g[5]); ov.w = pack2(g[6], g[7]);
+    *reinterpret_cast<uint4*>(o) = ov;
+  }
+}
+
 }  // namespace
+
+extern "C" int svit_skip_maxpool_fwd_idx(const void* x, void* y, void* idx, int B, int C, int T, int H, int W, int O,
+                                         int stride_hw, int dtype, void* stream) {
+  if (!x || !y || !idx || stride_hw < 2 || B < 0 || O < 1) return SVIT_EINVAL;
+  if (dtype != SVIT_BF16 || C % 8 ||
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) || (reinterpret_cast<uintptr_t>(idx) & 7))
+    return SVIT_ENOTSUP;
+  const int Ho = (H - 1) / stride_hw + 1, Wo = (W - 1) / stride_hw + 1;
+  const int64_t total = (int64_t)B * (1 + (int64_t)T * Ho * Wo + O) * (C / 8);
+  if (total == 0) return 0;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)svit_num_sms() * 32) blocks = (int64_t)svit_num_sms() * 32;
+  skip_maxpool_bf16_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, (uint8_t*)idx, B, C,
+                                                                                   T, H, W, Ho, Wo, O, stride_hw);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int svit_skip_maxpool_bwd_idx(const void* idx, const void* dy, void* dx, int B, int C, int T, int H, int W, int O,
+                                         int stride_hw, int dtype, void* stream) {
+  if (!idx || !dy || !dx || stride_hw < 2 || B < 0 || O < 1) return SVIT_EINVAL;
+  if (dtype != SVIT_BF16 || C % 8 ||
+      ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) || (reinterpret_cast<uintptr_t>(idx) & 7))
+    return SVIT_ENOTSUP;
+  const int Ho = (H - 1) / stride_hw + 1, Wo = (W - 1) / stride_hw + 1;
+  const int64_t total = (int64_t)B * (1 + (int64_t)T * H * W + O) * (C / 8);
+  if (total == 0) return 0;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)svit_num_sms() * 32) blocks = (int64_t)svit_num_sms() * 32;
+  skip_maxpool_bwd_idx_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)idx, (const bf16*)dy, (bf16*)dx, B,
+                                                                                C, T, H, W, Ho, Wo, O, stride_hw);
+  SVIT_CHECK_LAUNCH();
+  return 0;
+}
 
 int svit_skip_maxpool_fwd_bf16(const void* x, void* y, int B, int C, int T, int H, int W, int Ho, int Wo, int O, int s,
                                cudaStream_t st) {
@@ -232,7 +333,7 @@ int svit_skip_maxpool_fwd_bf16(const void* x, void* y, int B, int C, int T, int 
   const int64_t total = (int64_t)B * (1 + (int64_t)T * Ho * Wo + O) * (C / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)svit_num_sms() * 32) blocks = (int64_t)svit_num_sms() * 32;
-  skip_maxpool_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>((const bf16*)x, (bf16*)y, B, C, T, H, W, Ho, Wo, O, s);
+  skip_maxpool_bf16_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)x, (bf16*)y, nullptr, B, C, T, H, W, Ho, Wo, O, s);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : 1000 + (int)e;
 }

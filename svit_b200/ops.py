@@ -95,7 +95,7 @@ def cast_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 _FAMILY = {"svit_gemm": "gemm", "svit_attn_fwd": "attention", "svit_attn_bwd": "attention_bwd",
            "svit_pool_ln_fwd": "pool_ln", "svit_pool_ln_fwd_save": "pool_ln", "svit_pool_ln_bwd": "pool_ln_bwd",
            "svit_pool_ln_bwd_saved": "pool_ln_bwd", "svit_layernorm_fwd": "layernorm", "svit_row_stats": "layernorm",
-           "svit_layernorm_bwd": "layernorm_bwd", "svit_skip_maxpool_fwd": "skip_pool", "svit_im2col3d": "im2col", "svit_s2d_clip": "im2col",
+           "svit_layernorm_bwd": "layernorm_bwd", "svit_skip_maxpool_fwd": "skip_pool", "svit_skip_maxpool_fwd_idx": "skip_pool", "svit_im2col3d": "im2col", "svit_s2d_clip": "im2col",
            "svit_patch_embed_s2d": "gemm", "svit_mlp_fused": "gemm"}
 _prof = None
 
@@ -630,18 +630,34 @@ class _SkipPool(torch.autograd.Function):
         T, H, W = thw
         Ho, Wo = pooled_hw(H, s), pooled_hw(W, s)
         y = torch.empty(B, 1 + T * Ho * Wo + O, Cn, dtype=x.dtype, device=x.device)
+        ctx.geom = (B, Cn, T, H, W, O, s)
+        ctx.in_shape = x.shape
+        if x.dtype == torch.bfloat16 and Cn % 8 == 0 and ctx.needs_input_grad[0]:
+            # training: record the winning window position per output element (1 byte): the backward then needs neither
+            # x nor a re-scan of the windows
+            idx = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+            _call("svit_skip_maxpool_fwd_idx", x.data_ptr(), y.data_ptr(), idx.data_ptr(), B, Cn, T, H, W, O, s, _dt(x),
+                  _stream())
+            ctx.save_for_backward(idx)
+            ctx.by_index = True
+            return y
         _call("svit_skip_maxpool_fwd", x.data_ptr(), y.data_ptr(), B, Cn, T, H, W, O, s, _dt(x), _stream())
         ctx.save_for_backward(x)
-        ctx.geom = (B, Cn, T, H, W, O, s)
+        ctx.by_index = False
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
+        (saved,) = ctx.saved_tensors
         B, Cn, T, H, W, O, s = ctx.geom
         dy = dy.contiguous()
-        dx = torch.empty_like(x)
-        _call("svit_skip_maxpool_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), B, Cn, T, H, W, O, s, _dt(x), _stream())
+        dx = torch.empty(ctx.in_shape, dtype=dy.dtype, device=dy.device)
+        if ctx.by_index:
+            _call("svit_skip_maxpool_bwd_idx", saved.data_ptr(), dy.data_ptr(), dx.data_ptr(), B, Cn, T, H, W, O, s, _dt(dy),
+                  _stream())
+        else:
+            _call("svit_skip_maxpool_bwd", saved.data_ptr(), dy.data_ptr(), dx.data_ptr(), B, Cn, T, H, W, O, s, _dt(dy),
+                  _stream())
         return dx, None, None, None
 
 
