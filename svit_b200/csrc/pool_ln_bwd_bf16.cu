@@ -166,6 +166,92 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_kernel(const bf16* __restric
   }
 }
 
+// LayerNorm backward on the SAVED pre-LayerNorm rows (svit_pool_ln_fwd_save): pure streaming, 16 lanes per output token
+// (12 active, 8 channels each, 16-byte accesses), two tokens per warp instruction, reductions over 16 lanes.
+__device__ __forceinline__ float group16_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+  return v;
+}
+__device__ __forceinline__ void unpack8p(const uint4 v, float f[8]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+__global__ void __launch_bounds__(256) pool_bwd_pre_saved_kernel(const bf16* __restrict__ pre, const float* __restrict__ gamma,
+                                                                 const bf16* __restrict__ dout, bf16* __restrict__ dpre,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                 int64_t rows, float eps) {
+  __shared__ float sred[2 * PD];
+  for (int i = threadIdx.x; i < 2 * PD; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int sub = threadIdx.x & 15;
+  const bool act = sub < PD / 8;
+  const int c0 = act ? sub * 8 : 0;
+  float gm[8];
+  {
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), gb = *reinterpret_cast<const float4*>(gamma + c0 + 4);
+    gm[0] = ga.x; gm[1] = ga.y; gm[2] = ga.z; gm[3] = ga.w; gm[4] = gb.x; gm[5] = gb.y; gm[6] = gb.z; gm[7] = gb.w;
+  }
+  float ag[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = 0.f;
+  const int64_t gpb = blockDim.x >> 4;  // token groups per CTA
+  const int64_t iters = (rows + gridDim.x * gpb - 1) / (gridDim.x * gpb);  // uniform trip count: full-mask shuffles
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t i = (it * gridDim.x + blockIdx.x) * gpb + (threadIdx.x >> 4);
+    const bool ok = act && i < rows;
+    float v[8], dy[8];
+    unpack8p(ok ? __ldg(reinterpret_cast<const uint4*>(pre + i * PD + c0)) : make_uint4(0, 0, 0, 0), v);
+    unpack8p(ok ? __ldg(reinterpret_cast<const uint4*>(dout + i * PD + c0)) : make_uint4(0, 0, 0, 0), dy);
+    float sm = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm += v[j];
+    const float mean = group16_sum(sm) * (1.f / PD);
+    float xh[8], q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xh[j] = act ? v[j] - mean : 0.f;
+      q = fmaf(xh[j], xh[j], q);
+    }
+    const float rstd = rsqrtf(group16_sum(q) * (1.f / PD) + eps);
+    float gy[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xh[j] *= rstd;
+      gy[j] = dy[j] * gm[j];
+      s1 += gy[j];
+      s2 = fmaf(gy[j], xh[j], s2);
+      ag[j] = fmaf(dy[j], xh[j], ag[j]);
+      ab[j] += dy[j];
+    }
+    s1 = group16_sum(s1) * (1.f / PD);
+    s2 = group16_sum(s2) * (1.f / PD);
+    if (ok) {
+      float dp[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dp[j] = rstd * (gy[j] - s1 - xh[j] * s2);
+      uint4 o;
+      o.x = pack4(dp).x; o.y = pack4(dp).y; o.z = pack4(dp + 4).x; o.w = pack4(dp + 4).y;
+      *reinterpret_cast<uint4*>(dpre + i * PD + c0) = o;
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sred[c0 + j], ag[j]);
+      atomicAdd(&sred[PD + c0 + j], ab[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < PD; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sred[c]);
+    atomicAdd(&dbeta[c], sred[PD + c]);
+  }
+}
+
 // block = 288 threads: quad = tid % 24 (channels 4 quad .. 4 quad + 3, 8-byte accesses), tg = (tid / 24) % 3 (temporal tap
 // plane), part = tid / 72 (token index mod 4 inside the chunk).  grid = (chunks, B * h).
 __global__ void __launch_bounds__(288, 3) pool_bwd_dw_kernel(const bf16* __restrict__ in, Geom g,
@@ -273,41 +359,67 @@ __global__ void __launch_bounds__(288, 3) pool_bwd_dw_kernel(const bf16* __restr
   for (int i = threadIdx.x; i < PD * TAPS; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
 }
 
-template <int LS>  // log2(stride) for power-of-two strides, -1 = generic
+__device__ __forceinline__ void unpack8w(const uint4 v, float f[8]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+// 16 lanes per INPUT token, 12 of them active with 8 channels each (16-byte accesses; two tokens per warp instruction).
+// V8 = false keeps the 8-byte form (24 lanes x 4 channels) for slices that are only 8-byte aligned.
+template <int LS, bool V8>  // LS = log2(stride) for power-of-two strides, -1 = generic
 __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict__ dpre, Geom g,
                                                           const float* __restrict__ w, const float* __restrict__ frac,
                                                           bf16* __restrict__ dz) {
   __shared__ __align__(16) float sw[TAPS * PD];
   __shared__ __align__(16) float sweff[PD];
   load_weights(w, frac, sw, sweff);
-  const int lane = threadIdx.x & 31;
-  if (lane >= 24) return;
-  const int c0 = lane * 4;
+  constexpr int LPT = V8 ? 16 : 32;       // lanes per token
+  constexpr int NCH = V8 ? 8 : 4;         // channels per lane
+  const int sub = threadIdx.x & (LPT - 1);
+  if (sub >= PD / NCH) return;
+  const int c0 = sub * NCH;
   const int Lo = g.T * g.Ho * g.Wo, L = g.T * g.H * g.W;
   const int Nout = 1 + Lo + g.O, Nin = 1 + L + g.O;
-  const int wpb = blockDim.x >> 5;
+  const int tpb = blockDim.x / LPT;       // tokens per CTA pass
   const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
   const bf16* dp = dpre + (int64_t)bh * Nout * PD + c0;
   bf16* dzb = dz + b * g.in_bs + head * g.in_hs + c0;
   const int smask = (1 << (LS >= 0 ? LS : 0)) - 1;  // unused by the generic (LS < 0) instantiation
-  const int step = gridDim.x * wpb;
+  const int step = gridDim.x * tpb;
   const int step_w = step % g.W, step_h = (step / g.W) % g.H, step_t = step / (g.W * g.H);
   int ww, hh, t;
   {
-    const int tok0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const int tok0 = blockIdx.x * tpb + threadIdx.x / LPT;
     const unsigned p = (tok0 < 1 ? tok0 + step : tok0) - 1;
     const unsigned pr = p / (unsigned)g.W;
     ww = (int)(p - pr * g.W); t = (int)(pr / (unsigned)g.H); hh = (int)(pr - t * g.H);
   }
-  for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < Nin; tok += step) {
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+  auto load = [&](const bf16* src, float f[NCH]) {
+    if (V8) {
+      float t8[8];
+      unpack8w(__ldg(reinterpret_cast<const uint4*>(src)), t8);
+#pragma unroll
+      for (int e = 0; e < NCH; ++e) f[e] = t8[e];
+    } else {
+      float t4[4];
+      unpack4(__ldg(reinterpret_cast<const uint2*>(src)), t4);
+#pragma unroll
+      for (int e = 0; e < NCH; ++e) f[e] = t4[e];
+    }
+  };
+  for (int tok = blockIdx.x * tpb + threadIdx.x / LPT; tok < Nin; tok += step) {
+    float v[NCH];
+#pragma unroll
+    for (int e = 0; e < NCH; ++e) v[e] = 0.f;
     if (tok == 0) {
-      unpack4(__ldg(reinterpret_cast<const uint2*>(dp)), v);
+      load(dp, v);
     } else if (tok > L) {
-      float z[4];
-      unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (tok - L + Lo) * PD)), z);
-      const float4 we = *reinterpret_cast<const float4*>(sweff + c0);
-      v[0] = z[0] * we.x; v[1] = z[1] * we.y; v[2] = z[2] * we.z; v[3] = z[3] * we.w;
+      float z[NCH];
+      load(dp + (tok - L + Lo) * PD, z);
+#pragma unroll
+      for (int e = 0; e < NCH; ++e) v[e] = z[e] * sweff[c0 + e];
     } else {
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
@@ -325,16 +437,26 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
             if (numw < 0 || (LS >= 0 ? (numw & smask) != 0 : numw % g.s != 0)) continue;
             const int wo = LS >= 0 ? numw >> LS : numw / g.s;
             if (wo >= g.Wo) continue;
-            float z[4];
-            unpack4(__ldg(reinterpret_cast<const uint2*>(dp + (1 + (to * g.Ho + ho) * g.Wo + wo) * PD)), z);
-            const float4 wr = *reinterpret_cast<const float4*>(sw + (kt * 9 + kh * 3 + kw) * PD + c0);
-            v[0] = fmaf(z[0], wr.x, v[0]); v[1] = fmaf(z[1], wr.y, v[1]);
-            v[2] = fmaf(z[2], wr.z, v[2]); v[3] = fmaf(z[3], wr.w, v[3]);
+            float z[NCH];
+            load(dp + (1 + (to * g.Ho + ho) * g.Wo + wo) * PD, z);
+            const float* wr = sw + (kt * 9 + kh * 3 + kw) * PD + c0;
+#pragma unroll
+            for (int e = 0; e < NCH; e += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wr + e);
+              v[e] = fmaf(z[e], w4.x, v[e]); v[e + 1] = fmaf(z[e + 1], w4.y, v[e + 1]);
+              v[e + 2] = fmaf(z[e + 2], w4.z, v[e + 2]); v[e + 3] = fmaf(z[e + 3], w4.w, v[e + 3]);
+            }
           }
         }
       }
     }
-    *reinterpret_cast<uint2*>(dzb + tok * g.its) = pack4(v);
+    if (V8) {
+      uint4 o;
+      o.x = pack4(v).x; o.y = pack4(v).y; o.z = pack4(v + 4).x; o.w = pack4(v + 4).y;
+      *reinterpret_cast<uint4*>(dzb + tok * g.its) = o;
+    } else {
+      *reinterpret_cast<uint2*>(dzb + tok * g.its) = pack4(v);
+    }
     if (tok >= 1) {
       ww += step_w;
       if (ww >= g.W) { ww -= g.W; ++hh; }
@@ -367,15 +489,24 @@ int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   const int64_t Nout = 1 + (int64_t)T * g.Ho * g.Wo + O, Nin = 1 + (int64_t)T * H * W + O;
   const int64_t tok_out = (int64_t)B * h * Nout, tok_in = (int64_t)B * h * Nin;
   if (B * h > 65535 || Nin * in_ts >= (1ll << 31) || Nin * PD >= (1ll << 31)) return SVIT_ENOTSUP;  // 32-bit offsets
-  (void)tok_out; (void)tok_in;
+  (void)tok_in;
   const unsigned BH = (unsigned)(B * h);
   auto gx = [&](int64_t n) {  // CTAs along x so that x * BH is about 8 CTAs per SM, 8 tokens per CTA pass
     int64_t want = ceil_div64((int64_t)svit_num_sms() * 8, BH), need = ceil_div64(n, 8);
     return (unsigned)(need < want ? need : want);
   };
-  pool_bwd_pre_kernel<<<dim3(gx(Nout), BH), 256, 0, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma,
-                                                                (const bf16*)dout, (bf16*)dpre, dgamma, dbeta, eps,
-                                                                (const bf16*)pre);
+  if (pre && ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dpre)) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(gamma) & 15) == 0) {
+    int64_t ctas = ceil_div64(tok_out, 16);
+    const int64_t cap = (int64_t)svit_num_sms() * 8;
+    if (ctas > cap) ctas = cap;
+    pool_bwd_pre_saved_kernel<<<(unsigned)ctas, 256, 0, st>>>((const bf16*)pre, gamma, (const bf16*)dout, (bf16*)dpre, dgamma,
+                                                             dbeta, tok_out, eps);
+  } else {
+    pool_bwd_pre_kernel<<<dim3(gx(Nout), BH), 256, 0, st>>>((const bf16*)in, g, conv_w, tap_frac, gamma,
+                                                                  (const bf16*)dout, (bf16*)dpre, dgamma, dbeta, eps,
+                                                                  (const bf16*)pre);
+  }
   SVIT_CHECK_LAUNCH();
   int64_t chunk = ceil_div64(tok_out, (int64_t)svit_num_sms() * 8);  // ~8 CTAs (72 warps) per SM: latency-bound loop
   if (chunk < 32) chunk = 32;
@@ -383,14 +514,24 @@ int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   pool_bwd_dw_kernel<<<dim3((unsigned)ceil_div64(Nout, chunk), (unsigned)(B * h)), 288, 0, st>>>(
       (const bf16*)in, g, tap_frac, (const bf16*)dpre, dw, (int)chunk);
   SVIT_CHECK_LAUNCH();
-  const dim3 gin(gx(Nin), BH);
+  // 16-byte form when the packed qkv slice and the scratch rows are 16-byte aligned (always for the model's layouts)
+  const bool v8 = in_bs % 8 == 0 && in_ts % 8 == 0 && in_hs % 8 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(dpre) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0;
+  auto gin_x = [&](int64_t n, int tpb) {
+    int64_t want = ceil_div64((int64_t)svit_num_sms() * 8, BH), need = ceil_div64(n, tpb);
+    return (unsigned)(need < want ? need : want);
+  };
+#define IN_LAUNCH(LS)                                                                                                         \
+  if (v8) pool_bwd_in_kernel<LS, true><<<dim3(gin_x(Nin, 16), BH), 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); \
+  else pool_bwd_in_kernel<LS, false><<<dim3(gin_x(Nin, 8), BH), 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz);
   switch (s) {
-    case 1: pool_bwd_in_kernel<0><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
-    case 2: pool_bwd_in_kernel<1><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
-    case 4: pool_bwd_in_kernel<2><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
-    case 8: pool_bwd_in_kernel<3><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
-    default: pool_bwd_in_kernel<-1><<<gin, 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); break;
+    case 1: IN_LAUNCH(0) break;
+    case 2: IN_LAUNCH(1) break;
+    case 4: IN_LAUNCH(2) break;
+    case 8: IN_LAUNCH(3) break;
+    default: IN_LAUNCH(-1) break;
   }
+#undef IN_LAUNCH
   SVIT_CHECK_LAUNCH();
   return 0;
 }
