@@ -94,7 +94,7 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
@@ -121,7 +121,7 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;

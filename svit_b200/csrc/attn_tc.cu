@@ -143,7 +143,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int tl_n = 0;
       TL(0, 9000);
       tc::mbar_arrive_expect_tx(&bars[BAR_Q_FULL], 32768);
@@ -186,7 +186,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc_e = tc::idesc_bf16(BM, TP, 0, 0);
       constexpr uint32_t idesc_s = tc::idesc_bf16(BM, BN, 0, 0);
       constexpr uint32_t idesc_o = tc::idesc_bf16(BM, HD, 0, 1);  // N = 96: the zero-padded half atom of V is not multiplied

@@ -156,7 +156,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int tl_n = 0;
       TL(0, 9000);
       tc::mbar_arrive_expect_tx(&bars[BAR_Q_FULL], 16384 + 8192);
@@ -207,7 +207,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc_e = tc::idesc_bf16(BM, TP, 0, 0);
       constexpr uint32_t idesc_s = tc::idesc_bf16(BM, BN, 0, 0);
       constexpr uint32_t idesc_o = tc::idesc_bf16(BM, HD, 0, 1);
@@ -237,6 +237,10 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
       for (int j = 0; j <= p.n_tiles; ++j) {
         if (j < p.n_tiles) {
           const int ks = j & 1;
+#ifdef SVIT_TIMELINE
+          TL(1, 800 + j);
+          TL(1, tc::mbar_try_wait(&bars[BAR_K_FULL0 + ks], (j >> 1) & 1) ? 9901 : 9900);
+#endif
           tc::mbar_wait(&bars[BAR_K_FULL0 + ks], (j >> 1) & 1);
           tc::fence_after_sync();
           TL(1, 100 + j);
@@ -253,8 +257,10 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
           for (int k = 0; k < 2; ++k)
             tc::umma_bf16_ss(d, smem_desc_sw64(se + k * 32), smem_desc_sw64(sk + SEL_OFF + k * 32), idesc_s, 1u);
           if (X16) tc::umma_bf16_ss(d, smem_desc_sw32(se2), smem_desc_sw32(sk + SEL2_OFF), idesc_s, 1u);
+          TL(1, 600 + j);
           tc::umma_commit(&bars[BAR_K_EMPTY0 + ks]);
           tc::umma_commit(&bars[BAR_S_FULL0 + (j & 1)]);
+          TL(1, 700 + j);
         }
         if (j >= 1) {
           const int i = j - 1;
@@ -269,8 +275,10 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q0, const __grid_co
             const uint64_t db = tc::smem_desc_sw128(sv + k * 2048, 8192, 1024);
             tc::umma_bf16_ts(tmem_base + COL_O, tmem_base + COL_S0 + (i & 1) * BN + k * 8, db, idesc_o, (i | k) != 0);
           }
+          TL(1, 400 + i);
           tc::umma_commit(&bars[BAR_V_EMPTY0 + (i & 1)]);
           tc::umma_commit(&bars[BAR_O_DONE]);
+          TL(1, 500 + i);
           if (i == p.n_tiles - 1) tc::umma_commit(&bars[BAR_O_FINAL]);
         }
       }

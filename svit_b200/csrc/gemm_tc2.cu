@@ -225,7 +225,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int tl_n = 0;
@@ -258,7 +258,7 @@ gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && crank == 0) {
+    if (crank == 0 && tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_bf16(TM, BN, 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;

@@ -172,7 +172,7 @@ mlp_resident96_kernel(const __grid_constant__ CUtensorMap tmap_x64, const __grid
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_arrive_expect_tx(&bars[B_W_FULL], NC * (W1C_BYTES + W2C_BYTES));
       for (int c = 0; c < NC; ++c) {
         unsigned char* w1 = smem + OFF_W1 + c * W1C_BYTES;
@@ -195,7 +195,7 @@ mlp_resident96_kernel(const __grid_constant__ CUtensorMap tmap_x64, const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc1 = tc::idesc_bf16(BM, HC, 0, 0);
       constexpr uint32_t idesc2 = tc::idesc_bf16(BM, NOUT, 0, 0);
       const uint32_t xs = tc::smem_u32(smem + OFF_XS);
@@ -511,7 +511,7 @@ mlp_stream192_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 
   if (warp == 0) {
     // ===================== producer A: x tiles and the first-product weight ring =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       uint32_t g = 0;
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -536,7 +536,7 @@ mlp_stream192_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     }
   } else if (warp == 2 + 2 * TEAM_WARPS) {
     // ===================== producer B: the second-product weight ring =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       for (uint32_t g = 0; g < total; ++g) {
         const int slot = g % NW;
         tc::mbar_wait(&bars[B_W2_EMPTY0 + slot], ((g / NW) & 1) ^ 1);
@@ -546,7 +546,7 @@ mlp_stream192_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: two streams, whichever is ready =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc1 = tc::idesc_bf16(BM, HC, 0, 0);
       constexpr uint32_t idesc2 = tc::idesc_bf16(BM, NOUT, 0, 0);
       const uint32_t xs = tc::smem_u32(smem + OFF_XS);

@@ -110,7 +110,7 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // the whole weight matrix, once
       tc::mbar_arrive_expect_tx(w_full, (uint32_t)w_bytes);
       for (int c = 0; c < ntaps * p.chunks; ++c)
@@ -146,7 +146,7 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_bf16(128, E, 0, 0);
       tc::mbar_wait(w_full, 0);
       tc::fence_after_sync();
