@@ -370,8 +370,15 @@ def main():
     sampler = ClockSampler(local_rank)
     # The forward is captured once in a CUDA graph (svit_b200.GraphedForward) and replayed: one graph launch per step
     eager = model
+    model_u8 = None
     if not args.no_graph:
         model = svit_b200.GraphedForward(eager, dev_in[0], lanes=args.lanes)
+        if args.host_input == "uint8":
+            # the end-to-end leg's graph takes the decoded frames themselves: the colour normalisation is fused into the
+            # cell-layout kernel of the patch embed (svit_s2d_clip, in_kind uint8), no bf16 clip is ever materialised.
+            # Captured here, next to the first graph and before any collective of the timed legs.
+            model_u8 = svit_b200.GraphedForward(
+                eager, torch.zeros(B, 16, 224, 224, 3, dtype=torch.uint8, device=dev), lanes=args.lanes)
     # ---- device-resident throughput
     with torch.no_grad():
         for i in range(W):
@@ -393,17 +400,16 @@ def main():
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream()
         u8 = args.host_input == "uint8"
-        if u8:  # frames as the decoder leaves them: one normalise kernel (svit_normalize_u8) in front of the same graph
+        if u8:  # frames as the decoder leaves them (datasets/utils.py:287-303 runs on the device, inside the stem)
             host = [torch.randint(0, 256, (B, 16, 224, 224, 3), generator=gen, dtype=torch.uint8).pin_memory()
                     for _ in range(2)]
         staged = [torch.empty(host[0].shape, dtype=host[0].dtype, device=dev) for _ in range(2)]
         mean, std = cfg.DATA.MEAN, cfg.DATA.STD
 
         def model_e2e(inp):
-            x = inp[0] if args.no_graph else inp
-            if u8:
-                x = ops.normalize_u8(x, mean, std, torch.bfloat16)
-            return model([x]) if args.no_graph else model(x)
+            if args.no_graph:
+                return model([inp[0]])  # SViT.forward accepts uint8 [B, T, H, W, 3]
+            return model_u8(inp) if u8 else model(inp)
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
 
