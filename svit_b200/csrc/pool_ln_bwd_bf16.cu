@@ -359,6 +359,117 @@ __global__ void __launch_bounds__(288, 3) pool_bwd_dw_kernel(const bf16* __restr
   for (int i = threadIdx.x; i < PD * TAPS; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
 }
 
+// Strip form of the weight-gradient kernel (Wo % 7 == 0, stride 1 / 2 / 4): a thread (channel quad, temporal tap plane,
+// part) takes 7 consecutive output tokens of one output row at a time.  Their 7 dpre quads stay in registers and every
+// input token of the three rows under the strip is loaded ONCE and multiplied into all the outputs whose window covers
+// it (9 / 15 / 21 loads per row for 84 multiply-adds, where the token form issues 21 loads), with every tap index
+// resolved at compile time.  The loop of the token form was bound by its loads (10 per 36 FMAs).
+template <int S>
+__global__ void __launch_bounds__(288, 2) pool_bwd_dw_strip_kernel(const bf16* __restrict__ in, Geom g,
+                                                                   const float* __restrict__ frac,
+                                                                   const bf16* __restrict__ dpre, float* __restrict__ dw,
+                                                                   int strips_per_cta) {
+  constexpr int SW = 7, NI = (SW - 1) * S + 3;
+  __shared__ float sacc[3 * 72 * 36];
+  __shared__ float swe[4 * 24 * 4];
+  const int quad = threadIdx.x % 24, tg = (threadIdx.x / 24) % 3, part = threadIdx.x / 72;
+  const int Lo = g.T * g.Ho * g.Wo, L = g.T * g.H * g.W;
+  const int Nout = 1 + Lo + g.O;
+  const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
+  const bf16* zin = in + b * g.in_bs + head * g.in_hs + 4 * quad;
+  const bf16* dp_base = dpre + (int64_t)bh * Nout * PD + 4 * quad;
+  float acc[9][4], aweff[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+  const int spr = g.Wo / SW;  // strips per output row
+  const int nstrips = g.T * g.Ho * spr;
+  const int st0 = blockIdx.x * strips_per_cta;
+  const int st1 = st0 + strips_per_cta < nstrips ? st0 + strips_per_cta : nstrips;
+  for (int st = st0 + part; st < st1; st += 4) {
+    const int sx = st % spr, r = st / spr;
+    const int ho = r % g.Ho, to = r / g.Ho;
+    const int t = to - 1 + tg;
+    if (t < 0 || t >= g.T) continue;
+    const int wo0 = sx * SW;
+    float dp[SW][4];
+    {
+      const bf16* dps = dp_base + (1 + (to * g.Ho + ho) * g.Wo + wo0) * PD;
+#pragma unroll
+      for (int o = 0; o < SW; ++o) unpack4(__ldg(reinterpret_cast<const uint2*>(dps + o * PD)), dp[o]);
+    }
+    const int wbase = wo0 * S - 1;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hh = ho * S - 1 + kh;
+      if (hh < 0 || hh >= g.H) continue;
+      const bf16* zrow = zin + (1 + (t * g.H + hh) * g.W + wbase) * g.its;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if (i % S > 2 && S > 3) continue;  // stride 4: every fourth input column lies between the windows
+        const int ww = wbase + i;
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ww >= 0 && ww < g.W) unpack4(__ldg(reinterpret_cast<const uint2*>(zrow + i * g.its)), z);
+#pragma unroll
+        for (int o = 0; o < SW; ++o) {
+          const int kw = i - S * o;
+          if (kw >= 0 && kw <= 2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[kh * 3 + kw][e] = fmaf(dp[o][e], z[e], acc[kh * 3 + kw][e]);
+          }
+        }
+      }
+    }
+  }
+  // object tokens (no window: z * w_eff): the first CTA of the slice takes them
+  if (blockIdx.x == 0 && tg == 0) {
+    for (int tok = Lo + 1 + part; tok < Nout; tok += 4) {
+      float dpo[4], z[4];
+      unpack4(__ldg(reinterpret_cast<const uint2*>(dp_base + tok * PD)), dpo);
+      unpack4(__ldg(reinterpret_cast<const uint2*>(zin + (tok - Lo + L) * g.its)), z);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) aweff[e] = fmaf(dpo[e], z[e], aweff[e]);
+    }
+  }
+  if (tg == 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) swe[(part * 24 + quad) * 4 + e] = aweff[e];
+  }
+  if (part > 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[((part - 1) * 72 + tg * 24 + quad) * 36 + k * 4 + e] = acc[k][e];
+  }
+  __syncthreads();
+  if (part == 0) {
+    float e4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      e4[e] = swe[quad * 4 + e] + swe[(24 + quad) * 4 + e] + swe[(48 + quad) * 4 + e] + swe[(72 + quad) * 4 + e];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float f = frac[tg * 9 + k];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = fmaf(f, e4[e], acc[k][e]);
+#pragma unroll
+        for (int pp = 0; pp < 3; ++pp) v += sacc[(pp * 72 + tg * 24 + quad) * 36 + k * 4 + e];
+        acc[k][e] = v;
+      }
+    }
+  }
+  __syncthreads();
+  float* sdw = sacc;  // [96 * 27], laid out like dw: coalesced global atomics
+  if (part == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sdw[(4 * quad + e) * TAPS + tg * 9 + k] = acc[k][e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PD * TAPS; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+}
+
 __device__ __forceinline__ void unpack8w(const uint4 v, float f[8]) {
   f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
   f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
@@ -511,8 +622,19 @@ int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   int64_t chunk = ceil_div64(tok_out, (int64_t)svit_num_sms() * 8);  // ~8 CTAs (72 warps) per SM: latency-bound loop
   if (chunk < 32) chunk = 32;
   if (chunk > 2048) chunk = 2048;
-  pool_bwd_dw_kernel<<<dim3((unsigned)ceil_div64(Nout, chunk), (unsigned)(B * h)), 288, 0, st>>>(
-      (const bf16*)in, g, tap_frac, (const bf16*)dpre, dw, (int)chunk);
+  if (g.Wo % 7 == 0 && (s == 1 || s == 2 || s == 4)) {
+    const int64_t nstrips = (int64_t)T * g.Ho * (g.Wo / 7);
+    int64_t spc = ceil_div64(nstrips * BH, (int64_t)svit_num_sms() * 4);  // ~4 CTAs per SM over the whole launch
+    if (spc < 8) spc = 8;
+    if (spc > nstrips) spc = nstrips;
+    const dim3 gs((unsigned)ceil_div64(nstrips, spc), BH);
+    if (s == 1) pool_bwd_dw_strip_kernel<1><<<gs, 288, 0, st>>>((const bf16*)in, g, tap_frac, (const bf16*)dpre, dw, (int)spc);
+    else if (s == 2) pool_bwd_dw_strip_kernel<2><<<gs, 288, 0, st>>>((const bf16*)in, g, tap_frac, (const bf16*)dpre, dw, (int)spc);
+    else pool_bwd_dw_strip_kernel<4><<<gs, 288, 0, st>>>((const bf16*)in, g, tap_frac, (const bf16*)dpre, dw, (int)spc);
+  } else {
+    pool_bwd_dw_kernel<<<dim3((unsigned)ceil_div64(Nout, chunk), (unsigned)(B * h)), 288, 0, st>>>(
+        (const bf16*)in, g, tap_frac, (const bf16*)dpre, dw, (int)chunk);
+  }
   SVIT_CHECK_LAUNCH();
   // 16-byte form when the packed qkv slice and the scratch rows are 16-byte aligned (always for the model's layouts)
   const bool v8 = in_bs % 8 == 0 && in_ts % 8 == 0 && in_hs % 8 == 0 &&

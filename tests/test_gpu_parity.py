@@ -148,6 +148,47 @@ def test_pool_ln_tiled_bf16_vs_oracle(spec):
         assert max_rel_err(cpu(got[which]), want) < 1e-2
 
 
+@pytest.mark.parametrize("spec", [  # B, h, T, H, W, O, (sq, skv): strip form of the weight-gradient kernel (Wo % 7 == 0,
+    # strides 1 / 2 / 4) and the token form (everything else)
+    (2, 2, 4, 14, 14, 8, (1, 2)), (1, 1, 3, 28, 28, 4, (2, 4)), (1, 2, 2, 56, 56, 8, (1, 4)), (1, 4, 8, 7, 7, 64, (1, 1)),
+    (1, 2, 3, 20, 30, 8, (1, 2)), (1, 1, 2, 28, 28, 4, (1, 8)),
+])
+def test_pool_ln_bf16_backward_vs_oracle(spec):
+    """Backward of the bf16 conv-pool + LayerNorm (attention.py:13-65) on the packed qkv layout: gradients of the three
+    depthwise conv weights, the LayerNorm parameters and the qkv input against the oracle's autograd in fp32 on the same
+    bf16-rounded values; ||dg - dg_ref|| / ||dg_ref|| <= 2e-2 (dpre and dqkv are rounded to bf16 on the device)."""
+    B, h, T, H, W, Ot, (sq, skv) = spec
+    g = torch.Generator().manual_seed(H * 100 + W + sq)
+    N = 1 + T * H * W + Ot
+    qkv = torch.randn(B, N, 3 * h * 96, generator=g).bfloat16()
+    ws = [torch.randn(96, 1, 3, 3, 3, generator=g) * 0.3 for _ in range(3)]
+    gs = [1 + 0.2 * torch.randn(96, generator=g) for _ in range(3)]
+    bs = [0.2 * torch.randn(96, generator=g) for _ in range(3)]
+    leaf = lambda t: t.to(DEV).requires_grad_(True)
+    qd = leaf(qkv)
+    wd, gd, bd = [leaf(w) for w in ws], [leaf(x) for x in gs], [leaf(x) for x in bs]
+    got = ops.qkv_pool(qd, (T, H, W), Ot, sq, skv, wd[0], (gd[0], bd[0]), wd[1], (gd[1], bd[1]), wd[2], (gd[2], bd[2]))
+    qr = qkv.float().requires_grad_(True)
+    wr, gr, br = [w.clone().requires_grad_(True) for w in ws], [x.clone().requires_grad_(True) for x in gs], \
+        [x.clone().requires_grad_(True) for x in bs]
+    z = qr.reshape(B, N, 3, h, 96).permute(2, 0, 3, 1, 4)
+    loss_d, loss_r = 0, 0
+    for which, s in enumerate((sq, skv, skv)):
+        want, _ = O.pool_tokens(z[which], wr[which], (1, s, s), gr[which], br[which], [T, H, W])
+        gy = torch.randn(want.shape, generator=g).bfloat16()
+        loss_r = loss_r + (want * gy.float()).sum()
+        loss_d = loss_d + (got[which].float() * gy.to(DEV).float()).sum()
+    loss_r.backward()
+    loss_d.backward()
+    errs = {"dqkv": _norm_rel(cpu(qd.grad), qr.grad)}
+    for i, nm in enumerate("qkv"):
+        errs[f"dw_{nm}"] = _norm_rel(cpu(wd[i].grad), wr[i].grad)
+        errs[f"dgamma_{nm}"] = _norm_rel(cpu(gd[i].grad), gr[i].grad)
+        errs[f"dbeta_{nm}"] = _norm_rel(cpu(bd[i].grad), br[i].grad)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 2e-2, errs
+
+
 def test_attention_pool_skip_golden_exact(golden):
     for c in golden("attention_pool.pt")["skip"]:
         s = c["stride"]
