@@ -578,6 +578,119 @@ __global__ void __launch_bounds__(256) pool_bwd_in_kernel(const bf16* __restrict
   }
 }
 
+// Strip form of the input-gradient kernel (transposed depthwise conv): a lane group takes 7 (stride 1, 8 channels per
+// lane) or 14 (stride 2, 4 channels per lane) consecutive input tokens of one row.  Per (temporal, vertical) tap pair it
+// loads the 9 / 8 dpre tokens under the strip once and the 3 x NCH weights once, and every (input, tap) product is
+// resolved at compile time -- the token form issues one 16-byte load and two shared-memory weight loads per 8 FMAs.
+template <int S>
+__global__ void __launch_bounds__(256, 2) pool_bwd_in_strip_kernel(const bf16* __restrict__ dpre, Geom g,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ frac, bf16* __restrict__ dz) {
+  __shared__ __align__(16) float sw[TAPS * PD];
+  __shared__ __align__(16) float sweff[PD];
+  load_weights(w, frac, sw, sweff);
+  constexpr int NCH = S == 1 ? 8 : 4, SWI = S == 1 ? 7 : 14, LPT = S == 1 ? 16 : 32, NO = S == 1 ? 9 : 8;
+  constexpr int OFF = S == 1 ? 1 : 0;
+  const int sub = threadIdx.x & (LPT - 1);
+  if (sub >= PD / NCH) return;
+  const int c0 = sub * NCH;
+  const int Lo = g.T * g.Ho * g.Wo, L = g.T * g.H * g.W;
+  const int Nout = 1 + Lo + g.O;
+  const int bh = blockIdx.y, head = bh % g.h, b = bh / g.h;
+  const bf16* dp = dpre + (int64_t)bh * Nout * PD + c0;
+  bf16* dzb = dz + b * g.in_bs + head * g.in_hs + c0;
+  auto load = [&](const bf16* src, float f[NCH]) {
+    if (NCH == 8) {
+      float t8[8];
+      unpack8w(__ldg(reinterpret_cast<const uint4*>(src)), t8);
+#pragma unroll
+      for (int e = 0; e < NCH; ++e) f[e] = t8[e];
+    } else {
+      float t4[4];
+      unpack4(__ldg(reinterpret_cast<const uint2*>(src)), t4);
+#pragma unroll
+      for (int e = 0; e < NCH; ++e) f[e] = t4[e];
+    }
+  };
+  auto store = [&](bf16* dst, const float f[NCH]) {
+    if (NCH == 8) {
+      uint4 o;
+      o.x = pack4(f).x; o.y = pack4(f).y; o.z = pack4(f + 4).x; o.w = pack4(f + 4).y;
+      *reinterpret_cast<uint4*>(dst) = o;
+    } else {
+      *reinterpret_cast<uint2*>(dst) = pack4(f);
+    }
+  };
+  const int spr = g.W / SWI;
+  const int nstrips = g.T * g.H * spr;
+  const int spb = blockDim.x / LPT;
+  for (int st = blockIdx.x * spb + threadIdx.x / LPT; st < nstrips; st += gridDim.x * spb) {
+    const int sx = st % spr, r = st / spr;
+    const int hh = r % g.H, t = r / g.H;
+    const int ww0 = sx * SWI;
+    const int wo_base = S == 1 ? ww0 - 1 : ww0 >> 1;
+    float v[SWI][NCH];
+#pragma unroll
+    for (int j = 0; j < SWI; ++j)
+#pragma unroll
+      for (int e = 0; e < NCH; ++e) v[j][e] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+      const int to = t + 1 - kt;
+      if (to < 0 || to >= g.T) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int num = hh + 1 - kh;
+        if (num < 0 || (S == 2 && (num & 1))) continue;
+        const int ho = S == 2 ? num >> 1 : num;
+        if (ho >= g.Ho) continue;
+        const bf16* zr = dp + (1 + (to * g.Ho + ho) * g.Wo + wo_base) * PD;
+        float wk[3][NCH];
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int e = 0; e < NCH; e += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(sw + (kt * 9 + kh * 3 + kw) * PD + c0 + e);
+            wk[kw][e] = w4.x; wk[kw][e + 1] = w4.y; wk[kw][e + 2] = w4.z; wk[kw][e + 3] = w4.w;
+          }
+#pragma unroll
+        for (int i = 0; i < NO; ++i) {
+          const int wo = wo_base + i;
+          float z[NCH];
+#pragma unroll
+          for (int e = 0; e < NCH; ++e) z[e] = 0.f;
+          if (wo >= 0 && wo < g.Wo) load(zr + i * PD, z);
+#pragma unroll
+          for (int j = 0; j < SWI; ++j) {
+            const int kw = j + 1 + OFF - S * i;  // input ww0 + j reads output wo through tap kw = ww + 1 - S wo
+            if (kw >= 0 && kw <= 2) {
+#pragma unroll
+              for (int e = 0; e < NCH; ++e) v[j][e] = fmaf(z[e], wk[kw][e], v[j][e]);
+            }
+          }
+        }
+      }
+    }
+    bf16* dst = dzb + (1 + (t * g.H + hh) * g.W + ww0) * g.its;
+#pragma unroll
+    for (int j = 0; j < SWI; ++j) store(dst + j * g.its, v[j]);
+  }
+  if (blockIdx.x == 0) {  // cls row (pass-through) and the object rows (z * w_eff)
+    for (int n = threadIdx.x / LPT; n <= g.O; n += spb) {
+      float z[NCH];
+      if (n == 0) {
+        load(dp, z);
+        store(dzb, z);
+      } else {
+        load(dp + (Lo + n) * PD, z);
+#pragma unroll
+        for (int e = 0; e < NCH; ++e) z[e] *= sweff[c0 + e];
+        store(dzb + (L + n) * g.its, z);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 int svit_pool_ln_bwd_bf16_supported(const void* in, int64_t in_bs, int64_t in_ts, int64_t in_hs, const void* dout,
@@ -646,6 +759,22 @@ int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
 #define IN_LAUNCH(LS)                                                                                                         \
   if (v8) pool_bwd_in_kernel<LS, true><<<dim3(gin_x(Nin, 16), BH), 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz); \
   else pool_bwd_in_kernel<LS, false><<<dim3(gin_x(Nin, 8), BH), 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac, (bf16*)dz);
+  auto strip_grid = [&](int64_t nstrips, int per_pass) {
+    int64_t want = ceil_div64((int64_t)svit_num_sms() * 2, BH), need = ceil_div64(nstrips, per_pass);
+    return dim3((unsigned)(need < want ? need : want), BH);
+  };
+  if (s == 1 && v8 && W % 7 == 0) {
+    pool_bwd_in_strip_kernel<1><<<strip_grid((int64_t)T * H * (W / 7), 16), 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac,
+                                                                                      (bf16*)dz);
+    SVIT_CHECK_LAUNCH();
+    return 0;
+  }
+  if (s == 2 && W % 14 == 0) {
+    pool_bwd_in_strip_kernel<2><<<strip_grid((int64_t)T * H * (W / 14), 8), 256, 0, st>>>((const bf16*)dpre, g, conv_w, tap_frac,
+                                                                                      (bf16*)dz);
+    SVIT_CHECK_LAUNCH();
+    return 0;
+  }
   switch (s) {
     case 1: IN_LAUNCH(0) break;
     case 2: IN_LAUNCH(1) break;
