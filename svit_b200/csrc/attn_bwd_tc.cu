@@ -48,7 +48,11 @@ __device__ __forceinline__ void unpack8(const uint4 w, float f[8]) {
   f[6] = __uint_as_float(w.w << 16); f[7] = __uint_as_float(w.w & 0xffff0000u);
 }
 
-__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, int nep) {
+// etab != nullptr: the bias terms are rows of E_tab = q . T^T (fp32 [B h Nq, 96], one tcgen05 GEMM against the
+// un-gathered concatenated table, as in the forward kernel) picked through the integer index tables -- one 4-byte read
+// per (row, column) instead of a 96-long dot product against a gathered table row (12 x 16-byte loads + 24 shared-memory
+// reads each: the kernel was bound by them).
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, int nep, const float* __restrict__ etab) {
   __shared__ __align__(16) float sq[PQ][QP];
   const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
   const int64_t Nq = 1 + Lq + a.O;
@@ -98,6 +102,14 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, in
     if (c < ne && row >= 1 && row <= Lq) {
       const int64_t p = row - 1;
       const int j = (int)(p % a.qw), i = (int)((p / a.qw) % a.qh), t = (int)(p / ((int64_t)a.qw * a.qh));
+      if (etab) {
+        int gidx;
+        if (c < a.kh) gidx = __ldg(a.idx_h + i * a.kh + c);
+        else if (c < a.kh + a.kw) gidx = a.ntab_h + __ldg(a.idx_w + j * a.kw + (c - a.kh));
+        else gidx = a.ntab_h + a.ntab_w + __ldg(a.idx_t + t * a.kt + (c - a.kh - a.kw));
+        a.ws_e[((int64_t)bh * Nq + row) * nep + c] = __ldg(etab + ((int64_t)bh * Nq + row) * D + gidx);
+        continue;
+      }
       const uint4* R = reinterpret_cast<const uint4*>(rel_row(a, c, i, j, t));
       float acc2 = 0.f;
 #pragma unroll
@@ -273,10 +285,24 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
   const int64_t rows = (int64_t)BH * Nq;
   int rc;
 
-  attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep);
+  svit_gemm_args g;
+  // E_tab = q . T^T into the (still unused) fp32 dQ scratch when the concatenated table has at most 96 rows
+  const int ntab = a->ntab_h + a->ntab_w + a->ntab_t;
+  const float* etab = nullptr;
+  if (a->rel_tab && a->idx_h && a->idx_w && a->idx_t && ntab >= 8 && ntab <= D) {
+    gemm_defaults(g);
+    g.A = a->q; g.lda = D;
+    g.B = a->rel_tab; g.ldb = D; g.transB = 1;
+    g.C = a->ws_dq; g.ldc = D; g.out_dtype = SVIT_F32;
+    g.M = rows; g.N = ntab; g.K = D; g.batch = 1;
+    if (svit_gemm_tc_supported(&g)) {
+      if ((rc = svit_gemm_tc(&g, st))) return rc;
+      etab = a->ws_dq;
+    }
+  }
+  attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep, etab);
   SVIT_CHECK_LAUNCH();
 
-  svit_gemm_args g;
   if (!(a->ws_s && a->ws_dp) && svit_attn_bwd_sdp_supported(a)) {
     // S, dP, softmax and dS in one tcgen05 kernel: the fp32 matrices stay in TMEM (callers that pass the fp32 scratch
     // ask for the unfused path: key counts beyond the fused kernel's table, and the tests that compare the two)

@@ -708,6 +708,7 @@ class _Attention(torch.autograd.Function):
         if need:
             ctx.save_for_backward(q, k, v, Rh, Rw, Rt, out, lse)
         ctx.geom = (q_thw, k_thw, O, scale)
+        ctx.tc_tables = tc_tables if need else None  # the backward gets its bias terms from q . T^T (one GEMM) + the index tables
         return out
 
     @staticmethod
@@ -746,6 +747,10 @@ class _Attention(torch.autograd.Function):
             sel = key_select_table_bwd(tuple(k_thw), O, es, dev)
             a.ws_p, a.ws_ds, a.ws_dq = ws_p.data_ptr(), ws_ds.data_ptr(), ws_dq.data_ptr()
             a.sel_bwd, a.nep = sel.data_ptr(), es
+            if ctx.tc_tables is not None:
+                tab, ntabs, ih, iw, it = ctx.tc_tables[:5]
+                a.rel_tab, a.idx_h, a.idx_w, a.idx_t = tab.data_ptr(), ih.data_ptr(), iw.data_ptr(), it.data_ptr()
+                a.ntab_h, a.ntab_w, a.ntab_t = ntabs
         _call("svit_attn_bwd", C.byref(a), _stream(),
               tag=f"[B{B} h{h} Nq{Nq} Nk{Nk}]" if _prof is not None else None)
         return dq, dk, dv, dRh, dRw, dRt, None, None, None, None, None, None
