@@ -61,7 +61,10 @@ def interpolated_rel_pos(rel_pos: torch.Tensor, q_n: int, k_n: int) -> torch.Ten
 def gathered_rel_pos(rel_pos: torch.Tensor, q_n: int, k_n: int) -> torch.Tensor:
     """R[a, b, :] = get_rel_pos(rel_pos, 2*max(q,k)-1)[dist[a, b]]  (attention.py:116-119).
     Small torch glue (tables are <= 111 x 96) that keeps autograd to the parameter."""
-    return interpolated_rel_pos(rel_pos, q_n, k_n)[_index_on(rel_pos.device, q_n, k_n)]
+    idx = _index_on(rel_pos.device, q_n, k_n)
+    # index_select instead of advanced indexing: same values; its backward is one index_add_ (atomics) instead of ATen's
+    # sort-based index_put_ (a radix sort + 4 small kernels per table, 48 tables per training step)
+    return interpolated_rel_pos(rel_pos, q_n, k_n).index_select(0, idx.reshape(-1)).view(*idx.shape, -1)
 
 
 _keycol_cache = {}
