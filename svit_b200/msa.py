@@ -223,6 +223,41 @@ class MultiScaleAttention(nn.Module):
             trunc_normal_(self.rel_pos_w, std=0.02)
             trunc_normal_(self.rel_pos_t, std=0.02)
         self.residual_pooling = residual_pooling
+        self._rel_cache = {}
+
+    def _rel_tables(self, q_shape, k_shape, O, dtype, device):
+        """(Rh, Rw, Rt, tc_tables): the gathered tables R[a, b, :] (autograd path to the rel_pos parameters; the CUDA-core
+        kernels and the backward read them) and, in bf16, the un-gathered concatenated table + integer index tables of the
+        tensor-core kernels.  Without autograd the result only depends on the parameters: it is cached per (grid, dtype,
+        device, parameter versions), which takes 48 gathers, ~64 casts and 16 concatenations -- ~130 of the ~320 kernel
+        launches -- out of every inference forward."""
+        cache_key = None
+        if not torch.is_grad_enabled():
+            ps = (self.rel_pos_h, self.rel_pos_w, self.rel_pos_t)
+            cache_key = (tuple(q_shape), tuple(k_shape), O, dtype, str(device)) + tuple((p.data_ptr(), p._version) for p in ps)
+            hit = self._rel_cache.get(cache_key)
+            if hit is not None:
+                return hit
+        Rh = gathered_rel_pos(self.rel_pos_h, q_shape[1], k_shape[1])
+        Rw = gathered_rel_pos(self.rel_pos_w, q_shape[2], k_shape[2])
+        Rt = gathered_rel_pos(self.rel_pos_t, q_shape[0], k_shape[0])
+        tc_tables = None
+        if dtype == torch.bfloat16:
+            # tensor-core path: un-gathered tables + integer index tables (q.R becomes one MMA per query tile)
+            tabs = [interpolated_rel_pos(t.detach(), a, b) for t, a, b in
+                    ((self.rel_pos_h, q_shape[1], k_shape[1]), (self.rel_pos_w, q_shape[2], k_shape[2]),
+                     (self.rel_pos_t, q_shape[0], k_shape[0]))]
+            tc_tables = (torch.cat(tabs).to(torch.bfloat16).contiguous(), [t.shape[0] for t in tabs],
+                         _index32_on(device, q_shape[1], k_shape[1]), _index32_on(device, q_shape[2], k_shape[2]),
+                         _index32_on(device, q_shape[0], k_shape[0]), key_column_codes(k_shape, O, device),
+                         key_select_table(k_shape, O, device))
+        if cache_key is not None:
+            Rh, Rw, Rt = (r.to(dtype).contiguous() for r in (Rh, Rw, Rt))
+            # entries of older parameter versions go (a CUDA graph that captured them re-captures on a version change
+            # before it replays); the current version keeps one entry per grid (video / frame mode: a handful)
+            self._rel_cache = {k: v for k, v in self._rel_cache.items() if k[5:] == cache_key[5:]}
+            self._rel_cache[cache_key] = (Rh, Rw, Rt, tc_tables)
+        return Rh, Rw, Rt, tc_tables
 
     def forward(self, x, thw_shape, residual: Optional[torch.Tensor] = None,
                 sample_scale: Optional[torch.Tensor] = None, ln=None):
@@ -243,19 +278,7 @@ class MultiScaleAttention(nn.Module):
                                self.pool_v.weight, (self.norm_v.weight, self.norm_v.bias))
         q_shape = [T, ops.pooled_hw(H, self._sq), ops.pooled_hw(W, self._sq)]
         k_shape = [T, ops.pooled_hw(H, self._skv), ops.pooled_hw(W, self._skv)]
-        Rh = gathered_rel_pos(self.rel_pos_h, q_shape[1], k_shape[1])
-        Rw = gathered_rel_pos(self.rel_pos_w, q_shape[2], k_shape[2])
-        Rt = gathered_rel_pos(self.rel_pos_t, q_shape[0], k_shape[0])
-        tc_tables = None
-        if q.dtype == torch.bfloat16:
-            # tensor-core path: un-gathered tables + integer index tables (q.R becomes one MMA per query tile)
-            tabs = [interpolated_rel_pos(t.detach(), a, b) for t, a, b in
-                    ((self.rel_pos_h, q_shape[1], k_shape[1]), (self.rel_pos_w, q_shape[2], k_shape[2]),
-                     (self.rel_pos_t, q_shape[0], k_shape[0]))]
-            tc_tables = (torch.cat(tabs).to(torch.bfloat16).contiguous(), [t.shape[0] for t in tabs],
-                         _index32_on(x.device, q_shape[1], k_shape[1]), _index32_on(x.device, q_shape[2], k_shape[2]),
-                         _index32_on(x.device, q_shape[0], k_shape[0]), key_column_codes(k_shape, O, x.device),
-                         key_select_table(k_shape, O, x.device))
+        Rh, Rw, Rt, tc_tables = self._rel_tables(q_shape, k_shape, O, q.dtype, x.device)
         o = ops.attention(q, k, v, Rh, Rw, Rt, q_shape, k_shape, O, self.scale, tc_tables)
         y = ops.linear(o, self.proj.weight, self.proj.bias, residual=residual, sample_scale=sample_scale)
         return y, q_shape
