@@ -123,3 +123,54 @@ def test_graphed_forward_lanes_match_single_lane():
         assert p.shape == p1.shape and torch.equal(p, p1), lanes
         for k, v in e1.items():
             assert e[k].shape == v.shape and torch.equal(e[k], v), (lanes, k)
+
+
+def test_rel_pos_cache_follows_the_parameters():
+    """Without autograd every MultiScaleAttention caches its rel-pos tables (gathered R, concatenated bf16 table, index
+    tables) per (grid, dtype, device, parameter versions).  An in-place parameter update must invalidate the entry: the
+    eager forward and a GraphedForward (which re-captures on a version change) have to see the new tables, and the cached
+    forward must equal the forward with emptied caches bit for bit."""
+    cfg, m = _tiny()
+    m.eval()
+    clip = synth_input("relcache.clip", (2, 3, 4, 32, 32), 11).to(DEV).bfloat16()
+    with torch.no_grad():
+        a1 = m([clip])[1]["logits"].clone()   # fills the caches
+        a2 = m([clip])[1]["logits"].clone()   # served from them
+    attn = [mod for mod in m.modules() if isinstance(mod, svit_b200.MultiScaleAttention)]
+    assert torch.equal(a1, a2)
+    assert all(len(mod._rel_cache) == 1 for mod in attn)
+    g = svit_b200.GraphedForward(m, clip)
+    assert torch.equal(g(clip)[1]["logits"], a1)
+    with torch.no_grad():
+        for mod in attn:
+            mod.rel_pos_h.add_(0.5 * torch.randn_like(mod.rel_pos_h))
+            mod.rel_pos_t.mul_(-1.0)
+        b1 = m([clip])[1]["logits"].clone()
+        for mod in attn:
+            mod._rel_cache.clear()
+        ref2 = m([clip])[1]["logits"].clone()  # tables rebuilt from the parameters
+    assert not torch.equal(b1, a1), "the update of the tables must change the logits"
+    assert torch.equal(b1, ref2)
+    assert all(len(mod._rel_cache) == 1 for mod in attn), "stale entries are dropped"
+    assert torch.equal(g(clip)[1]["logits"], b1), "the graph re-captures on a parameter version change"
+
+
+def test_graphed_forward_on_uint8_frames_equals_eager():
+    """The end-to-end leg of bench.py replays a graph captured on the decoded uint8 frames [B, T, H, W, 3] (normalisation fused
+    into the stem's cell-layout kernel): same result as the eager uint8 forward and as the forward of the pre-normalised
+    bf16 clip."""
+    cfg, m = _tiny()
+    m.eval()
+    gen = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (2, 4, 32, 32, 3), generator=gen, dtype=torch.uint8).to(DEV)
+    with torch.no_grad():
+        eager = m([frames])[1]["logits"].clone()
+        clip = ops.normalize_u8(frames, cfg.DATA.MEAN, cfg.DATA.STD, torch.bfloat16)
+        from_clip = m([clip])[1]["logits"].clone()
+    g = svit_b200.GraphedForward(m, frames)
+    frames2 = torch.randint(0, 256, (2, 4, 32, 32, 3), generator=gen, dtype=torch.uint8).to(DEV)
+    g(frames2)
+    out = g(frames)[1]["logits"]
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+    assert torch.equal(eager, from_clip)
