@@ -14,6 +14,8 @@
 //   warps 2-9 epilogue, thread = query row: tcgen05.ld 32 columns of S and of dP, bias gathered from the row's E
 //             values (staged per warp in shared memory, key -> column codes built once per CTA), MUFU.EX2, pack to
 //             bf16, 16-byte stores of P and dS.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 #include "../../include/svit_b200.h"
 
@@ -25,10 +27,12 @@ constexpr int NUM_THREADS = 320, EPI_WARPS = 8;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_KEYS_PADDED = 4096;  // key -> column code table (4 B per key) lives in shared memory
+constexpr int OPITCH = 80;             // staging pitch of a 32-column bf16 row segment
 
 struct Params {
   int B, h, Nq, Nk, Nkp, Lq, Lk, kh, kw, kt, nep, pitch;
   int m_tiles, n_tiles;
+  int stage_out;  // 1: P / dS leave through a per-warp shared-memory transpose (coalesced row segments)
   float sc;  // scale * log2(e)
   const float* ws_e;
   const float* lse;
@@ -49,7 +53,10 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint32_t* codes = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES);         // [n_tiles * BN]
   float* es = reinterpret_cast<float*>(codes + p.n_tiles * BN);                       // [8 warps][32 rows][pitch]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(es + EPI_WARPS * 32 * p.pitch + 2);
+  // per epilogue warp two 32-row x 64-byte tiles (P, dS) at an 80-byte pitch: conflict-free 16-byte row writes
+  unsigned char* ostg = reinterpret_cast<unsigned char*>(es + EPI_WARPS * 32 * p.pitch);
+  ostg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ostg) + 15) & ~uintptr_t(15));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ostg + (p.stage_out ? EPI_WARPS * 2 * 32 * OPITCH : 0) + 8);
   full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(full_bar) + 7) & ~uintptr_t(7));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -210,7 +217,32 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           pk[j >> 1] = pack2(pv[0], pv[1]);
           dk[j >> 1] = pack2(ds[0], ds[1]);
         }
-        if (valid) {
+        if (p.stage_out) {
+          // thread = row in TMEM, but a row's 64 bytes per tensor are what is contiguous in memory: transpose through the
+          // warp's staging tiles so that one store instruction covers 8 rows x 64 B (16 full sectors) instead of 32 rows
+          // x 16 B (32 half sectors)
+          unsigned char* sp = ostg + (warp - 2) * (2 * 32 * OPITCH);
+          unsigned char* sd = sp + 32 * OPITCH;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            *reinterpret_cast<uint4*>(sp + lane * OPITCH + u * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            *reinterpret_cast<uint4*>(sd + lane * OPITCH + u * 16) = make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]);
+          }
+          __syncwarp();
+          const int piece = lane & 3;
+          const bool col_ok = cbase + 8 * piece < p.Nkp;
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 8) {
+            const int r = rr + (lane >> 2);
+            const int grow = m0 + q * 32 + r;
+            if (grow < p.Nq && col_ok) {
+              const int64_t off = ((int64_t)bh * p.Nq + grow) * p.Nkp + cbase + 8 * piece;
+              *reinterpret_cast<uint4*>(p.P + off) = *reinterpret_cast<const uint4*>(sp + r * OPITCH + piece * 16);
+              *reinterpret_cast<uint4*>(p.dS + off) = *reinterpret_cast<const uint4*>(sd + r * OPITCH + piece * 16);
+            }
+          }
+          __syncwarp();
+        } else if (valid) {
           bf16* prow = p.P + R * p.Nkp + cbase;
           bf16* drow = p.dS + R * p.Nkp + cbase;
 #pragma unroll
@@ -231,8 +263,9 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
-size_t smem_bytes(int n_tiles, int pitch) {
-  return (size_t)STAGES * STAGE_BYTES + (size_t)n_tiles * BN * 4 + (size_t)EPI_WARPS * 32 * pitch * 4 + 256 + 1024 + 64;
+size_t smem_bytes(int n_tiles, int pitch, int stage_out) {
+  return (size_t)STAGES * STAGE_BYTES + (size_t)n_tiles * BN * 4 + (size_t)EPI_WARPS * 32 * pitch * 4 + 256 + 1024 + 64 +
+         (stage_out ? (size_t)EPI_WARPS * 2 * 32 * OPITCH + 32 : 0);
 }
 
 }  // namespace
@@ -274,7 +307,9 @@ int svit_attn_bwd_sdp(const svit_attn_args* a, cudaStream_t st) {
   if ((rc = svit_make_tmap_4d(&tdo, a->dout, (uint64_t)a->B, (uint64_t)a->h, (uint64_t)p.Nq, HD, (uint64_t)a->h * HD, HD,
                               (uint64_t)p.Nq * a->h * HD, BM)))
     return rc;
-  const size_t smem = smem_bytes(p.n_tiles, p.pitch);
+  p.stage_out = smem_bytes(p.n_tiles, p.pitch, 1) <= 220 * 1024 ? 1 : 0;
+  if (getenv("SVIT_SDP_DIRECT_STORES")) p.stage_out = 0;  // A/B switch
+  const size_t smem = smem_bytes(p.n_tiles, p.pitch, p.stage_out);
   static SvitDevOnce configured;
   if (configured.need(smem)) {
     SVIT_CUDA(cudaFuncSetAttribute(attn_bwd_sdp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
