@@ -184,9 +184,7 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_saved_kernel(const bf16* __r
                                                                  const bf16* __restrict__ dout, bf16* __restrict__ dpre,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                  int64_t rows, float eps) {
-  __shared__ float sred[2 * PD];
-  for (int i = threadIdx.x; i < 2 * PD; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
+  __shared__ float sred[16][2 * PD + 1];  // one row of partial (dgamma | dbeta) per 16-lane token group: no shared atomics
   const int sub = threadIdx.x & 15;
   const bool act = sub < PD / 8;
   const int c0 = act ? sub * 8 : 0;
@@ -239,16 +237,19 @@ __global__ void __launch_bounds__(256) pool_bwd_pre_saved_kernel(const bf16* __r
     }
   }
   if (act) {
+    float* mine = sred[threadIdx.x >> 4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sred[c0 + j], ag[j]);
-      atomicAdd(&sred[PD + c0 + j], ab[j]);
+      mine[c0 + j] = ag[j];
+      mine[PD + c0 + j] = ab[j];
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < PD; c += blockDim.x) {
-    atomicAdd(&dgamma[c], sred[c]);
-    atomicAdd(&dbeta[c], sred[PD + c]);
+  for (int c = threadIdx.x; c < 2 * PD; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int gidx = 0; gidx < 16; ++gidx) t += sred[gidx][c];
+    atomicAdd(c < PD ? &dgamma[c] : &dbeta[c - PD], t);
   }
 }
 
@@ -721,8 +722,10 @@ int svit_pool_ln_bwd_bf16(const void* in, int64_t in_bs, int64_t in_ts, int64_t 
   };
   if (pre && ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dpre)) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(gamma) & 15) == 0) {
-    int64_t ctas = ceil_div64(tok_out, 16);
-    const int64_t cap = (int64_t)svit_num_sms() * 8;
+    // every CTA ends with 192 global atomics on the same two cache lines (~10 ns each, serialised in L2): at least four
+    // 16-token passes per CTA and at most 4 CTAs per SM keep that tail at a few microseconds
+    int64_t ctas = ceil_div64(tok_out, 64);
+    const int64_t cap = (int64_t)svit_num_sms() * 4;
     if (ctas > cap) ctas = cap;
     pool_bwd_pre_saved_kernel<<<(unsigned)ctas, 256, 0, st>>>((const bf16*)pre, gamma, (const bf16*)dout, (bf16*)dpre, dgamma,
                                                              dbeta, tok_out, eps);
