@@ -185,9 +185,12 @@ typedef struct svit_attn_args {
   const void* sel_tab;
   int32_t sel_cols;
   /* tensor-core backward (bf16, attn_bwd_tc.cu), optional: all six present -> the five contractions of the backward
-   * run as batched tcgen05 GEMMs.  Nkp = Nk rounded up to 8; nep = kh+kw+kt rounded up to 8 (<= 64); with these,
-   * ws_e and ws_de are [B,h,Nq,nep].  sel_bwd [Nk, nep] (activation dtype): row n = key n with ones in columns
-   * i'(n), kh + j'(n), kh + kw + t'(n) for patch keys, zero rows for cls / object keys. */
+   * run as batched tcgen05 GEMMs.  Nkp = Nk rounded up to 8; nep = kh+kw+kt rounded up to 8 (<= 64) -- to 16 for the
+   * fused S / dP / softmax kernel (ws_s / ws_dp NULL), which takes the bias terms as extra K columns of its score
+   * product and keeps them in the ws_e bytes as bf16 [B,h,Nq, hi (nep) | lo (nep)]; with these, ws_e and ws_de are
+   * [B,h,Nq,nep].  sel_bwd [Nk, nep] (activation dtype): row n = key n with ones in columns i'(n), kh + j'(n),
+   * kh + kw + t'(n) for patch keys, zero rows for cls / object keys.  rel_tab / idx_* / ntab_* (above), when present
+   * and ntab_h + ntab_w + ntab_t <= 96, let the backward compute the bias terms as one GEMM q . rel_tab^T. */
   float* ws_s;      /* scratch fp32 [B,h,Nq,Nkp]: q k^T; ws_s / ws_dp may be NULL when Nk <= 4096 (fused kernel) */
   float* ws_dp;     /* scratch fp32 [B,h,Nq,Nkp]: dO v^T */
   void* ws_p;       /* scratch bf16 [B,h,Nq,Nkp]: softmax probabilities */

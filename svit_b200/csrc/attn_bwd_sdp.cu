@@ -1,19 +1,23 @@
 // Attention backward, first half, fused on the tensor cores:  for every 128 x 128 (query x key) tile
-//     S  = q k^T   and   dP = dO v^T          two tcgen05 accumulations side by side in TMEM (K = 96 each)
-//     P  = exp(scale S + bias - lse)           bias = E[row, i'] + E[row, kh + j'] + E[row, kh + kw + t']
+//     S  = [q | E'] [k | Sel]^T   and   dP = dO v^T     two tcgen05 accumulations side by side in TMEM
+//     P  = exp(scale S - lse)                  the rel-pos bias E[row, i'] + E[row, kh + j'] + E[row, kh + kw + t'] is part
+//                                              of the score product, as in the forward kernel (attn_tc3.cu): E' = E / scale
+//                                              as a bf16 hi + lo pair (written by the prep kernel: fp32-accurate, the
+//                                              backward differentiates the exact bias), Sel the 0/1 key-selection matrix.  The
+//                                              epilogue used to gather the three terms per element from shared memory
+//                                              (ncu: 31 instructions per element, half of the kernel's issue slots).
 //     dS = P (dP - delta)
 // and only the bf16 operands of the second round of GEMMs (P for dV, dS for dK / dQ / dE) go to HBM -- the fp32 score
 // and dP matrices never exist in memory (attention.py:429-459 differentiated; see attn_bwd_tc.cu for the whole plan).
 //
 // Persistent, warp-specialised, one CTA per SM (320 threads), same skeleton as gemm_tc.cu:
-//   warp 0    TMA producer: 4-stage ring of {A 128 x 64, B 128 x 64} bf16 tiles (128-byte swizzle); per tile four
-//             stage loads: (q, k) columns 0..63 and 64..95, then (dO, v) likewise.  dO is read in place from the
+//   warp 0    TMA producer: 4-stage ring of {A 128 x 64, B 128 x 64} bf16 tiles (128-byte swizzle); per tile six
+//             stage loads: (q, k) columns 0..63 and 64..95, (E'hi, Sel), (E'lo, Sel), then (dO, v) columns 0..63 and 64..95.  dO is read in place from the
 //             head-merged [B, Nq, h, 96] gradient through a 4-D tensor map (sample, head) coordinate.
-//   warp 1    MMA issuer: 6 + 6 tcgen05.mma 128 x 128 x 16 per tile; accumulators S | dP (2 x 128 columns), double
+//   warp 1    MMA issuer: 6 + 2 nep/16 + 6 tcgen05.mma 128 x 128 x 16 per tile; accumulators S | dP (2 x 128 columns), double
 //             buffered (512 TMEM columns) so the MMAs of tile i+1 overlap the epilogue of tile i
-//   warps 2-9 epilogue, thread = query row: tcgen05.ld 32 columns of S and of dP, bias gathered from the row's E
-//             values (staged per warp in shared memory, key -> column codes built once per CTA), MUFU.EX2, pack to
-//             bf16, 16-byte stores of P and dS.
+//   warps 2-9 epilogue, thread = query row: tcgen05.ld 32 columns of S and of dP, MUFU.EX2, pack to bf16, P and dS
+//             rows leave through a per-warp shared-memory transpose.
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -30,11 +34,10 @@ constexpr int MAX_KEYS_PADDED = 4096;  // key -> column code table (4 B per key)
 constexpr int OPITCH = 80;             // staging pitch of a 32-column bf16 row segment
 
 struct Params {
-  int B, h, Nq, Nk, Nkp, Lq, Lk, kh, kw, kt, nep, pitch;
+  int B, h, Nq, Nk, Nkp, Lq, Lk, kh, kw, kt, nep;
   int m_tiles, n_tiles;
   int stage_out;  // 1: P / dS leave through a per-warp shared-memory transpose (coalesced row segments)
   float sc;  // scale * log2(e)
-  const float* ws_e;
   const float* lse;
   const float* ws_delta;
   bf16* P;
@@ -48,14 +51,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_do, const __grid_constant__ CUtensorMap tmap_v, Params p) {
+                    const __grid_constant__ CUtensorMap tmap_do, const __grid_constant__ CUtensorMap tmap_v,
+                    const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_sel, Params p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint32_t* codes = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES);         // [n_tiles * BN]
-  float* es = reinterpret_cast<float*>(codes + p.n_tiles * BN);                       // [8 warps][32 rows][pitch]
   // per epilogue warp two 32-row x 64-byte tiles (P, dS) at an 80-byte pitch: conflict-free 16-byte row writes
-  unsigned char* ostg = reinterpret_cast<unsigned char*>(es + EPI_WARPS * 32 * p.pitch);
-  ostg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ostg) + 15) & ~uintptr_t(15));
+  unsigned char* ostg = smem + STAGES * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ostg + (p.stage_out ? EPI_WARPS * 2 * 32 * OPITCH : 0) + 8);
   full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(full_bar) + 7) & ~uintptr_t(7));
   uint64_t* empty_bar = full_bar + STAGES;
@@ -72,6 +73,8 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tc::prefetch_tmap(&tmap_k);
     tc::prefetch_tmap(&tmap_do);
     tc::prefetch_tmap(&tmap_v);
+    tc::prefetch_tmap(&tmap_e);
+    tc::prefetch_tmap(&tmap_sel);
     for (int i = 0; i < STAGES; ++i) {
       tc::mbar_init(&full_bar[i], 1);
       tc::mbar_init(&empty_bar[i], 1);
@@ -83,17 +86,6 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, TMEM_COLS);
-  // key -> E-column codes (slot nep = the always-zero entry of cls / object / padding keys)
-  for (int n = threadIdx.x; n < p.n_tiles * BN; n += blockDim.x) {
-    uint32_t code = (uint32_t)p.nep * 0x010101u;
-    if (n >= 1 && n <= p.Lk) {
-      const unsigned q = n - 1;
-      const unsigned r = q / (unsigned)p.kw;
-      const unsigned jj = q - r * p.kw, tt = r / (unsigned)p.kh, ii = r - tt * p.kh;
-      code = ii | ((p.kh + jj) << 8) | ((p.kh + p.kw + tt) << 16);
-    }
-    codes[n] = code;
-  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -109,18 +101,20 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
         const int b = bh / p.h, head = bh - b * p.h;
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
+        for (int kb = 0; kb < 6; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * STAGE_BYTES;
           unsigned char* sb = sa + A_BYTES;
           tc::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          const int kc = (kb & 1) * BK;
           if (kb < 2) {
-            tc::tma_load_4d(sa, &tmap_q, &full_bar[stage], kc, m0, 0, bh);
-            tc::tma_load_4d(sb, &tmap_k, &full_bar[stage], kc, n0, 0, bh);
+            tc::tma_load_4d(sa, &tmap_q, &full_bar[stage], kb * BK, m0, 0, bh);
+            tc::tma_load_4d(sb, &tmap_k, &full_bar[stage], kb * BK, n0, 0, bh);
+          } else if (kb < 4) {  // bias operands: E' hi / lo rows of this (b, head), Sel rows of the keys (shared by all)
+            tc::tma_load_4d(sa, &tmap_e, &full_bar[stage], (kb - 2) * p.nep, m0, 0, bh);
+            tc::tma_load_4d(sb, &tmap_sel, &full_bar[stage], 0, n0, 0, 0);
           } else {
-            tc::tma_load_4d(sa, &tmap_do, &full_bar[stage], kc, m0, head, b);
-            tc::tma_load_4d(sb, &tmap_v, &full_bar[stage], kc, n0, 0, bh);
+            tc::tma_load_4d(sa, &tmap_do, &full_bar[stage], (kb - 4) * BK, m0, head, b);
+            tc::tma_load_4d(sb, &tmap_v, &full_bar[stage], (kb - 4) * BK, n0, 0, bh);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -137,21 +131,23 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int as = it & 1;
         tc::mbar_wait_hot(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
         tc::fence_after_sync();
+        const int esteps = p.nep >> 4;  // bias entries, 16 per MMA (nep is a multiple of 16 on this path)
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
+        for (int kb = 0; kb < 6; ++kb) {
           tc::mbar_wait_hot(&full_bar[stage], phase);
           tc::fence_after_sync();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BN + (kb >> 1) * BN);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BN + (kb >= 4 ? BN : 0));
           const uint32_t sa = tc::smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
-          const int ksteps = (kb & 1) ? (HD - BK) / 16 : BK / 16;  // columns 64..95 only in the second block
+          // columns 64..95 only in the second block of q / k and of dO / v
+          const int ksteps = (kb == 2 || kb == 3) ? esteps : ((kb == 1 || kb == 5) ? (HD - BK) / 16 : BK / 16);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             if (k < ksteps)
               tc::umma_bf16_ss(d_tmem, tc::smem_desc_sw128(sa + k * 32, 16, 1024), tc::smem_desc_sw128(sb + k * 32, 16, 1024),
-                               idesc, ((kb & 1) || k != 0) ? 1u : 0u);
+                               idesc, ((kb != 0 && kb != 4) || k != 0) ? 1u : 0u);
           tc::umma_commit(&empty_bar[stage]);
-          if (kb == 3) tc::umma_commit(&tmem_full[as]);
+          if (kb == 5) tc::umma_commit(&tmem_full[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -160,7 +156,6 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // ===================== epilogue warps =====================
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    float* e = es + ((warp - 2) * 32 + lane) * p.pitch;
     const float kLog2e = 1.4426950408889634f;
     int it = 0;
     for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++it) {
@@ -168,22 +163,9 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
       const int row = m0 + q * 32 + lane;
       const bool valid = row < p.Nq;
-      const bool qpatch = valid && row >= 1 && row <= p.Lq;
       const int64_t R = (int64_t)bh * p.Nq + (valid ? row : 0);
-      __syncwarp();
-      if (qpatch) {
-        const float4* src = reinterpret_cast<const float4*>(p.ws_e + R * p.nep);
-        for (int c = 0; c < p.nep; c += 4) {
-          const float4 v4 = __ldg(src + (c >> 2));
-          e[c] = v4.x * kLog2e; e[c + 1] = v4.y * kLog2e; e[c + 2] = v4.z * kLog2e; e[c + 3] = v4.w * kLog2e;
-        }
-      } else {
-        for (int c = 0; c < p.nep; ++c) e[c] = 0.f;
-      }
-      e[p.nep] = 0.f;
       const float nlse = valid ? -p.lse[R] * kLog2e : 0.f;
       const float delta = valid ? p.ws_delta[R] : 0.f;
-      __syncwarp();
       const int as = it & 1;
       tc::mbar_wait_hot(&tmem_full[as], (it >> 1) & 1);
       tc::fence_after_sync();
@@ -207,9 +189,7 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           float pv[2], ds[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const uint32_t code = codes[cbase + j + u];
-            const float bias = e[code & 255u] + e[(code >> 8) & 255u] + e[code >> 16];
-            float x = tc::ex2_approx(fmaf(sv[j + u], p.sc, bias + nlse));
+            float x = tc::ex2_approx(fmaf(sv[j + u], p.sc, nlse));
             if (cbase + j + u >= p.Nk) x = 0.f;
             pv[u] = x;
             ds[u] = x * (dv[j + u] - delta);
@@ -263,17 +243,16 @@ attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
-size_t smem_bytes(int n_tiles, int pitch, int stage_out) {
-  return (size_t)STAGES * STAGE_BYTES + (size_t)n_tiles * BN * 4 + (size_t)EPI_WARPS * 32 * pitch * 4 + 256 + 1024 + 64 +
-         (stage_out ? (size_t)EPI_WARPS * 2 * 32 * OPITCH + 32 : 0);
+size_t smem_bytes(int stage_out) {
+  return (size_t)STAGES * STAGE_BYTES + 256 + 1024 + 64 + (stage_out ? (size_t)EPI_WARPS * 2 * 32 * OPITCH + 32 : 0);
 }
 
 }  // namespace
 
 int svit_attn_bwd_sdp_supported(const svit_attn_args* a) {
-  if (a->dtype != SVIT_BF16 || !a->ws_p || !a->ws_ds || !a->ws_e || !a->ws_delta || !a->lse) return 0;
+  if (a->dtype != SVIT_BF16 || !a->ws_p || !a->ws_ds || !a->ws_e || !a->ws_delta || !a->lse || !a->sel_bwd) return 0;
   const int ne = a->kh + a->kw + a->kt;
-  if (a->nep < ne || a->nep % 8 || a->nep > 64) return 0;
+  if (a->nep < ne || a->nep % 16 || a->nep > 64) return 0;  // hi | lo halves of E' are whole 16-column MMA steps
   const int64_t Nk = 1 + (int64_t)a->kt * a->kh * a->kw + a->O;
   const int64_t Nq = 1 + (int64_t)a->qt * a->qh * a->qw + a->O;
   if (Nk > MAX_KEYS_PADDED || Nq >= (1ll << 30)) return 0;
@@ -281,7 +260,7 @@ int svit_attn_bwd_sdp_supported(const svit_attn_args* a) {
   if (tiles >= (1ll << 31)) return 0;
   if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
        reinterpret_cast<uintptr_t>(a->dout) | reinterpret_cast<uintptr_t>(a->ws_p) | reinterpret_cast<uintptr_t>(a->ws_ds) |
-       reinterpret_cast<uintptr_t>(a->ws_e)) & 15)
+       reinterpret_cast<uintptr_t>(a->ws_e) | reinterpret_cast<uintptr_t>(a->sel_bwd)) & 15)
     return 0;
   return 1;
 }
@@ -293,13 +272,12 @@ int svit_attn_bwd_sdp(const svit_attn_args* a, cudaStream_t st) {
   p.Nq = 1 + p.Lq + a->O; p.Nk = 1 + p.Lk + a->O;
   p.Nkp = (p.Nk + 7) / 8 * 8;
   p.kh = a->kh; p.kw = a->kw; p.kt = a->kt; p.nep = a->nep;
-  p.pitch = (a->nep + 1) | 1;  // odd pitch: the 32 rows of a warp fall in different banks
   p.m_tiles = (p.Nq + BM - 1) / BM; p.n_tiles = (p.Nk + BN - 1) / BN;
   p.sc = a->scale * 1.4426950408889634f;
-  p.ws_e = a->ws_e; p.lse = a->lse; p.ws_delta = a->ws_delta;
+  p.lse = a->lse; p.ws_delta = a->ws_delta;
   p.P = (bf16*)a->ws_p; p.dS = (bf16*)a->ws_ds;
   const uint64_t BH = (uint64_t)a->B * a->h;
-  CUtensorMap tq, tk, tdo, tv;
+  CUtensorMap tq, tk, tdo, tv, te, tsel;
   int rc;
   if ((rc = svit_make_tmap_4d(&tq, a->q, BH, 1, (uint64_t)p.Nq, HD, HD, 0, (uint64_t)p.Nq * HD, BM))) return rc;
   if ((rc = svit_make_tmap_4d(&tk, a->k, BH, 1, (uint64_t)p.Nk, HD, HD, 0, (uint64_t)p.Nk * HD, BN))) return rc;
@@ -307,9 +285,16 @@ int svit_attn_bwd_sdp(const svit_attn_args* a, cudaStream_t st) {
   if ((rc = svit_make_tmap_4d(&tdo, a->dout, (uint64_t)a->B, (uint64_t)a->h, (uint64_t)p.Nq, HD, (uint64_t)a->h * HD, HD,
                               (uint64_t)p.Nq * a->h * HD, BM)))
     return rc;
-  p.stage_out = smem_bytes(p.n_tiles, p.pitch, 1) <= 220 * 1024 ? 1 : 0;
-  if (getenv("SVIT_SDP_DIRECT_STORES")) p.stage_out = 0;  // A/B switch
-  const size_t smem = smem_bytes(p.n_tiles, p.pitch, p.stage_out);
+  // E' = E / scale as bf16 [B h, Nq, hi (nep) | lo (nep)] in the ws_e scratch (the bytes of its fp32 rows;
+  // attn_bwd_prep_kernel, e16 mode); Sel = sel_bwd [Nk, nep]
+  if ((rc = svit_make_tmap_4d(&te, a->ws_e, BH, 1, (uint64_t)p.Nq, (uint64_t)2 * p.nep, (uint64_t)2 * p.nep, 0,
+                              (uint64_t)p.Nq * 2 * p.nep, BM)))
+    return rc;
+  if ((rc = svit_make_tmap_4d(&tsel, a->sel_bwd, 1, 1, (uint64_t)p.Nk, (uint64_t)p.nep, (uint64_t)p.nep, 0,
+                              (uint64_t)p.Nk * p.nep, BN)))
+    return rc;
+  p.stage_out = getenv("SVIT_SDP_DIRECT_STORES") ? 0 : 1;  // A/B switch
+  const size_t smem = smem_bytes(p.stage_out);
   static SvitDevOnce configured;
   if (configured.need(smem)) {
     SVIT_CUDA(cudaFuncSetAttribute(attn_bwd_sdp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -317,7 +302,7 @@ int svit_attn_bwd_sdp(const svit_attn_args* a, cudaStream_t st) {
   }
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles * BH;
   const int grid = (int)(tiles < svit_num_sms() ? tiles : svit_num_sms());
-  attn_bwd_sdp_kernel<<<grid, NUM_THREADS, smem, st>>>(tq, tk, tdo, tv, p);
+  attn_bwd_sdp_kernel<<<grid, NUM_THREADS, smem, st>>>(tq, tk, tdo, tv, te, tsel, p);
   SVIT_CHECK_LAUNCH();
   return 0;
 }

@@ -52,7 +52,11 @@ __device__ __forceinline__ void unpack8(const uint4 w, float f[8]) {
 // un-gathered concatenated table, as in the forward kernel) picked through the integer index tables -- one 4-byte read
 // per (row, column) instead of a 96-long dot product against a gathered table row (12 x 16-byte loads + 24 shared-memory
 // reads each: the kernel was bound by them).
-__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, int nep, const float* __restrict__ etab) {
+// e16: the bias terms are written as E / scale split into a bf16 hi + lo pair (the A-operand columns of the fused
+// kernel's score product; hi + lo carries 16 mantissa bits, so the backward keeps differentiating the exact bias) into
+// the ws_e scratch viewed as bf16 [B h Nq, hi (nep) | lo (nep)] -- the same bytes as its fp32 rows; else fp32 E.
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, int nep, const float* __restrict__ etab,
+                                                            int e16) {
   __shared__ __align__(16) float sq[PQ][QP];
   const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
   const int64_t Nq = 1 + Lq + a.O;
@@ -107,9 +111,8 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, in
         if (c < a.kh) gidx = __ldg(a.idx_h + i * a.kh + c);
         else if (c < a.kh + a.kw) gidx = a.ntab_h + __ldg(a.idx_w + j * a.kw + (c - a.kh));
         else gidx = a.ntab_h + a.ntab_w + __ldg(a.idx_t + t * a.kt + (c - a.kh - a.kw));
-        a.ws_e[((int64_t)bh * Nq + row) * nep + c] = __ldg(etab + ((int64_t)bh * Nq + row) * D + gidx);
-        continue;
-      }
+        acc = __ldg(etab + ((int64_t)bh * Nq + row) * D + gidx);
+      } else {
       const uint4* R = reinterpret_cast<const uint4*>(rel_row(a, c, i, j, t));
       float acc2 = 0.f;
 #pragma unroll
@@ -124,8 +127,17 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, in
         acc = fmaf(qb.z, f[6], acc); acc2 = fmaf(qb.w, f[7], acc2);
       }
       acc += acc2;
+      }
     }
-    a.ws_e[((int64_t)bh * Nq + row) * nep + c] = acc;
+    if (e16) {
+      const float x = acc / a.scale;
+      const bf16 hi = __float2bfloat16_rn(x);
+      bf16* dst = reinterpret_cast<bf16*>(a.ws_e) + ((int64_t)bh * Nq + row) * 2 * nep;
+      dst[c] = hi;
+      dst[nep + c] = __float2bfloat16_rn(x - __bfloat162float(hi));
+    } else {
+      a.ws_e[((int64_t)bh * Nq + row) * nep + c] = acc;
+    }
   }
 }
 
@@ -300,10 +312,11 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
       etab = a->ws_dq;
     }
   }
-  attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep, etab);
+  const bool fused = !(a->ws_s && a->ws_dp) && svit_attn_bwd_sdp_supported(a);
+  attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep, etab, fused ? 1 : 0);
   SVIT_CHECK_LAUNCH();
 
-  if (!(a->ws_s && a->ws_dp) && svit_attn_bwd_sdp_supported(a)) {
+  if (fused) {
     // S, dP, softmax and dS in one tcgen05 kernel: the fp32 matrices stay in TMEM (callers that pass the fp32 scratch
     // ask for the unfused path: key counts beyond the fused kernel's table, and the tests that compare the two)
     if ((rc = svit_attn_bwd_sdp(a, st))) return rc;

@@ -723,7 +723,8 @@ class _Attention(torch.autograd.Function):
         a = _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale)
         # bf16: the contractions run as batched tcgen05 GEMMs (attn_bwd_tc.cu); fp32 parity mode: CUDA-core kernels
         tc = q.dtype == torch.bfloat16 and _state["attn_impl"] != _lib.IMPL_SIMT and ne <= 64
-        es = (ne + 7) // 8 * 8 if tc else ne
+        # tensor-core path: whole 16-column MMA steps (the fused S / dP kernel takes the bias terms as extra K columns)
+        es = (ne + 15) // 16 * 16 if tc else ne
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         dR = torch.zeros(Rh.numel() + Rw.numel() + Rt.numel(), dtype=torch.float32, device=dev)  # one fill
         dRh = dR[:Rh.numel()].view(Rh.shape)
