@@ -59,6 +59,19 @@ def test_layernorm_fwd_bwd(dtype):
         assert max_rel_err(cpu(bd.grad), br.grad) < (1e-4 if dtype == torch.float32 else 2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_scale_rows_exact(dtype):
+    """y[m, :] = x[m, :] * scale[m // rows_per_sample] (DropPath backward, common.py:46-59): equal to the fp32 product
+    rounded once to the activation dtype, for the 16-byte bf16 kernel (C % 8 == 0) and the scalar one (C = 100)."""
+    g = torch.Generator().manual_seed(3)
+    for B, N, C in ((3, 37, 96), (2, 1633, 384), (5, 11, 100)):
+        x = torch.randn(B, N, C, generator=g).to(dtype).to(DEV)
+        s = (torch.rand(B, generator=g) * 2).to(DEV)
+        got = ops._scale_rows(x, s, N)
+        want = (x.float() * s.view(B, 1, 1)).to(dtype)
+        assert torch.equal(got, want), (B, N, C)
+
+
 def _gemm_ref(A, B, tA, tB):
     a = A.t() if tA else A
     b = B.t() if tB else B
