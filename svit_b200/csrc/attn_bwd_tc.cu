@@ -207,9 +207,50 @@ __global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(svit_attn_args a,
   }
 }
 
+// ---- G[row, g] = sum over the columns c with table row g(row, c) == g of dE[row, c]   (bf16 [B h Nq, 96]) -----------
+// The bias gradient in table-row space: with it the table term of dq is G . T and the table gradient G^T . q, two
+// GEMMs instead of a 96-long FMA chain per (row, column) against gathered table rows in two CUDA-core kernels.
+__global__ void __launch_bounds__(256) attn_bwd_gscatter_kernel(svit_attn_args a, int nep, bf16* __restrict__ G,
+                                                                int64_t total_rows) {
+  __shared__ float sg[16][D];
+  const int l = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
+  const int64_t Nq = 1 + Lq + a.O;
+  const int ne = a.kh + a.kw + a.kt;
+  const int64_t R = (int64_t)blockIdx.x * 16 + grp;
+  for (int i = l; i < D; i += 16) sg[grp][i] = 0.f;
+  __syncthreads();
+  if (R < total_rows) {
+    const int64_t row = R % Nq;
+    if (row >= 1 && row <= Lq) {
+      const int64_t p = row - 1;
+      const int jq = (int)(p % a.qw), iq = (int)((p / a.qw) % a.qh), tq = (int)(p / ((int64_t)a.qw * a.qh));
+      for (int c = l; c < ne; c += 16) {
+        int gidx;
+        if (c < a.kh) gidx = __ldg(a.idx_h + iq * a.kh + c);
+        else if (c < a.kh + a.kw) gidx = a.ntab_h + __ldg(a.idx_w + jq * a.kw + (c - a.kh));
+        else gidx = a.ntab_h + a.ntab_w + __ldg(a.idx_t + tq * a.kt + (c - a.kh - a.kw));
+        atomicAdd(&sg[grp][gidx], __ldg(a.ws_de + R * nep + c));  // two columns may share a table row
+      }
+    }
+  }
+  __syncthreads();
+  if (R < total_rows && l < D / 8) {
+    const float* s = &sg[grp][8 * l];
+    __nv_bfloat162 o0 = __floats2bfloat162_rn(s[0], s[1]), o1 = __floats2bfloat162_rn(s[2], s[3]);
+    __nv_bfloat162 o2 = __floats2bfloat162_rn(s[4], s[5]), o3 = __floats2bfloat162_rn(s[6], s[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&o0); o.y = *reinterpret_cast<uint32_t*>(&o1);
+    o.z = *reinterpret_cast<uint32_t*>(&o2); o.w = *reinterpret_cast<uint32_t*>(&o3);
+    *(reinterpret_cast<uint4*>(G + R * D) + l) = o;
+  }
+}
+
 // ---- dq = dq_part (already scaled) + sum_c dE[c] R_c + dO[rows >= 1] -------------------------------------------
+// dq_tab != nullptr: the table term arrives as a second fp32 [rows, 96] matrix (G . T), no gathers here
 __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(svit_attn_args a, const float* __restrict__ dq_part,
-                                                              int nep, int64_t total_rows) {
+                                                              int nep, int64_t total_rows,
+                                                              const float* __restrict__ dq_tab) {
   // 16 lanes per (b, head, query row), 12 of them active with 8 channels each (16-byte accesses); the row's bias
   // gradients dE[c] sit in registers of the group (lane l holds c = l, l + 16, ...) and are broadcast by shuffles
   const int l = threadIdx.x & 15;
@@ -228,7 +269,12 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(svit_attn_args a, 
     const float4 gb = __ldg(reinterpret_cast<const float4*>(dq_part + Rc * D + 8 * l + 4));
     g[0] = ga.x; g[1] = ga.y; g[2] = ga.z; g[3] = ga.w; g[4] = gb.x; g[5] = gb.y; g[6] = gb.z; g[7] = gb.w;
   }
-  const bool patch = row >= 1 && row <= Lq;  // uniform within the 16-lane group
+  const bool patch = row >= 1 && row <= Lq && !dq_tab;  // uniform within the 16-lane group
+  if (dq_tab && act) {
+    const float4 ta = __ldg(reinterpret_cast<const float4*>(dq_tab + Rc * D + 8 * l));
+    const float4 tb = __ldg(reinterpret_cast<const float4*>(dq_tab + Rc * D + 8 * l + 4));
+    g[0] += ta.x; g[1] += ta.y; g[2] += ta.z; g[3] += ta.w; g[4] += tb.x; g[5] += tb.y; g[6] += tb.z; g[7] += tb.w;
+  }
   float dreg[MAXE / 16];
 #pragma unroll
   for (int k = 0; k < MAXE / 16; ++k) dreg[k] = (patch && l + 16 * k < ne) ? __ldg(a.ws_de + Rc * nep + l + 16 * k) : 0.f;
@@ -312,6 +358,7 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
       etab = a->ws_dq;
     }
   }
+  if (a->d_rel_tab && !(etab && Nkp >= 2 * D)) return SVIT_ENOTSUP;  // the caller would read an unwritten gradient
   const bool fused = !(a->ws_s && a->ws_dp) && svit_attn_bwd_sdp_supported(a);
   attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep, etab, fused ? 1 : 0);
   SVIT_CHECK_LAUNCH();
@@ -381,7 +428,30 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
   g.M = rows; g.N = nep; g.K = Nk; g.batch = 1;
   if ((rc = run_gemm(g, st))) return rc;
 
-  attn_bwd_finish_kernel<<<(unsigned)ceil_div64(rows, 16), 256, 0, st>>>(*a, a->ws_dq, nep, rows);
+  if (a->d_rel_tab && etab && Nkp >= 2 * D) {
+    // table-row space: G (bf16 [rows, 96]) takes the place of dS, dq_tab = G . T (fp32 [rows, 96]) that of P -- both
+    // scratch matrices have been consumed by the GEMMs above and a row of either holds at least 96 fp32 values
+    bf16* G = (bf16*)a->ws_ds;
+    float* dq_tab = (float*)a->ws_p;
+    attn_bwd_gscatter_kernel<<<(unsigned)ceil_div64(rows, 16), 256, 0, st>>>(*a, nep, G, rows);
+    SVIT_CHECK_LAUNCH();
+    gemm_defaults(g);
+    g.A = G; g.lda = D;
+    g.B = a->rel_tab; g.ldb = D; g.transB = 0;  // T stored [K = table rows, N = 96]
+    g.C = dq_tab; g.ldc = D; g.out_dtype = SVIT_F32;
+    g.M = rows; g.N = D; g.K = ntab; g.batch = 1;
+    if ((rc = run_gemm(g, st))) return rc;
+    attn_bwd_finish_kernel<<<(unsigned)ceil_div64(rows, 16), 256, 0, st>>>(*a, a->ws_dq, nep, rows, dq_tab);
+    SVIT_CHECK_LAUNCH();
+    // d_rel_tab = G^T . q  (split-K over the rows; the GEMM zeroes its output)
+    gemm_defaults(g);
+    g.A = G; g.lda = D; g.transA = 1;
+    g.B = a->q; g.ldb = D; g.transB = 0;
+    g.C = a->d_rel_tab; g.ldc = D; g.out_dtype = SVIT_F32;
+    g.M = ntab; g.N = D; g.K = rows; g.batch = 1;
+    return run_gemm(g, st);
+  }
+  attn_bwd_finish_kernel<<<(unsigned)ceil_div64(rows, 16), 256, 0, st>>>(*a, a->ws_dq, nep, rows, nullptr);
   SVIT_CHECK_LAUNCH();
   return svit_attn_bwd_drel(a, nep, st);
 }

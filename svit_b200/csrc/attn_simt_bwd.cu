@@ -412,6 +412,7 @@ extern "C" int svit_attn_bwd(const svit_attn_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a->impl == 2) return svit_attn_bwd_tc_supported(a) ? svit_attn_bwd_tc(a, st) : SVIT_ENOTSUP;
   if (a->impl == 0 && svit_attn_bwd_tc_supported(a)) return svit_attn_bwd_tc(a, st);
+  if (a->d_rel_tab) return SVIT_ENOTSUP;  // the table-space gradient exists in the tensor-core path only
   if (a->dtype == SVIT_F32) return launch_bwd<float>(a, st);
   if (a->dtype == SVIT_BF16) return launch_bwd<bf16>(a, st);
   return SVIT_EINVAL;

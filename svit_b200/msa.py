@@ -226,7 +226,7 @@ class MultiScaleAttention(nn.Module):
         self._rel_cache = {}
 
     def _rel_tables(self, q_shape, k_shape, O, dtype, device):
-        """(Rh, Rw, Rt, tc_tables): the gathered tables R[a, b, :] (autograd path to the rel_pos parameters; the CUDA-core
+        """(Rh, Rw, Rt, tc_tables, tab): the gathered tables R[a, b, :] (autograd path to the rel_pos parameters; the CUDA-core
         kernels and the backward read them) and, in bf16, the un-gathered concatenated table + integer index tables of the
         tensor-core kernels.  Without autograd the result only depends on the parameters: it is cached per (grid, dtype,
         device, parameter versions), which takes 48 gathers, ~64 casts and 16 concatenations -- ~130 of the ~320 kernel
@@ -242,12 +242,17 @@ class MultiScaleAttention(nn.Module):
         Rw = gathered_rel_pos(self.rel_pos_w, q_shape[2], k_shape[2])
         Rt = gathered_rel_pos(self.rel_pos_t, q_shape[0], k_shape[0])
         tc_tables = None
+        tab = None
         if dtype == torch.bfloat16:
             # tensor-core path: un-gathered tables + integer index tables (q.R becomes one MMA per query tile)
-            tabs = [interpolated_rel_pos(t.detach(), a, b) for t, a, b in
+            with_grad = cache_key is None  # autograd on: the concatenated fp32 table keeps its history (see ops.attention)
+            tabs = [interpolated_rel_pos(t if with_grad else t.detach(), a, b) for t, a, b in
                     ((self.rel_pos_h, q_shape[1], k_shape[1]), (self.rel_pos_w, q_shape[2], k_shape[2]),
                      (self.rel_pos_t, q_shape[0], k_shape[0]))]
-            tc_tables = (torch.cat(tabs).to(torch.bfloat16).contiguous(), [t.shape[0] for t in tabs],
+            cat = torch.cat(tabs)
+            if with_grad and cat.requires_grad:
+                tab = cat
+            tc_tables = (cat.detach().to(torch.bfloat16).contiguous(), [t.shape[0] for t in tabs],
                          _index32_on(device, q_shape[1], k_shape[1]), _index32_on(device, q_shape[2], k_shape[2]),
                          _index32_on(device, q_shape[0], k_shape[0]), key_column_codes(k_shape, O, device),
                          key_select_table(k_shape, O, device))
@@ -256,8 +261,8 @@ class MultiScaleAttention(nn.Module):
             # entries of older parameter versions go (a CUDA graph that captured them re-captures on a version change
             # before it replays); the current version keeps one entry per grid (video / frame mode: a handful)
             self._rel_cache = {k: v for k, v in self._rel_cache.items() if k[5:] == cache_key[5:]}
-            self._rel_cache[cache_key] = (Rh, Rw, Rt, tc_tables)
-        return Rh, Rw, Rt, tc_tables
+            self._rel_cache[cache_key] = (Rh, Rw, Rt, tc_tables, None)
+        return Rh, Rw, Rt, tc_tables, tab
 
     def forward(self, x, thw_shape, residual: Optional[torch.Tensor] = None,
                 sample_scale: Optional[torch.Tensor] = None, ln=None):
@@ -278,8 +283,8 @@ class MultiScaleAttention(nn.Module):
                                self.pool_v.weight, (self.norm_v.weight, self.norm_v.bias))
         q_shape = [T, ops.pooled_hw(H, self._sq), ops.pooled_hw(W, self._sq)]
         k_shape = [T, ops.pooled_hw(H, self._skv), ops.pooled_hw(W, self._skv)]
-        Rh, Rw, Rt, tc_tables = self._rel_tables(q_shape, k_shape, O, q.dtype, x.device)
-        o = ops.attention(q, k, v, Rh, Rw, Rt, q_shape, k_shape, O, self.scale, tc_tables)
+        Rh, Rw, Rt, tc_tables, tab = self._rel_tables(q_shape, k_shape, O, q.dtype, x.device)
+        o = ops.attention(q, k, v, Rh, Rw, Rt, q_shape, k_shape, O, self.scale, tc_tables, tab)
         y = ops.linear(o, self.proj.weight, self.proj.bias, residual=residual, sample_scale=sample_scale)
         return y, q_shape
 

@@ -18,7 +18,9 @@ from ._lib import BF16, F32, IMPL_AUTO, IMPL_SIMT, IMPL_TC, AttnArgs, GemmArgs, 
 LN_EPS = 1e-6
 HEAD_DIM = 96
 
-_state = {"gemm_impl": IMPL_AUTO, "attn_impl": IMPL_AUTO, "launches": 0}
+_state = {"gemm_impl": IMPL_AUTO, "attn_impl": IMPL_AUTO, "launches": 0,
+          # rel-pos gradient of the tensor-core attention backward in table-row space (A / B switch for measurements)
+          "attn_tab_grad": os.environ.get("SVIT_ATTN_TAB_GRAD", "1") != "0"}
 
 
 def set_impl(gemm: Optional[int] = None, attn: Optional[int] = None):
@@ -685,7 +687,7 @@ def _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale):
 
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables, grad_mode):
+    def forward(ctx, q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables, grad_mode, tab=None):
         _chk(q, "attention")
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         Rh, Rw, Rt = (r.to(q.dtype).contiguous() for r in (Rh, Rw, Rt))
@@ -709,6 +711,10 @@ class _Attention(torch.autograd.Function):
             ctx.save_for_backward(q, k, v, Rh, Rw, Rt, out, lse)
         ctx.geom = (q_thw, k_thw, O, scale)
         ctx.tc_tables = tc_tables if need else None  # the backward gets its bias terms from q . T^T (one GEMM) + the index tables
+        # `tab` = the concatenated un-gathered fp32 table WITH autograd history: the backward then returns the rel-pos
+        # gradient in table-row space (two tcgen05 GEMMs) and nothing for the gathered tables
+        ctx.tab_grad = (need and tab is not None and tc_tables is not None and ctx.needs_input_grad[12]
+                        and _state.get("attn_tab_grad", True))
         return out
 
     @staticmethod
@@ -726,7 +732,12 @@ class _Attention(torch.autograd.Function):
         # tensor-core path: whole 16-column MMA steps (the fused S / dP kernel takes the bias terms as extra K columns)
         es = (ne + 15) // 16 * 16 if tc else ne
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        dR = torch.zeros(Rh.numel() + Rw.numel() + Rt.numel(), dtype=torch.float32, device=dev)  # one fill
+        d_tab = None
+        if tc and ctx.tab_grad and 8 <= sum(ctx.tc_tables[1]) <= d and (Nk + 7) // 8 * 8 >= 2 * d:
+            # table-row space (attn_bwd_tc.cu: G scatter + two GEMMs); d_rel_h / d_rel_w / d_rel_t are not written
+            d_tab = torch.empty(sum(ctx.tc_tables[1]), d, dtype=torch.float32, device=dev)
+        dR = (torch.zeros if d_tab is None else torch.empty)(Rh.numel() + Rw.numel() + Rt.numel(), dtype=torch.float32,
+                                                             device=dev)  # one fill
         dRh = dR[:Rh.numel()].view(Rh.shape)
         dRw = dR[Rh.numel():Rh.numel() + Rw.numel()].view(Rw.shape)
         dRt = dR[Rh.numel() + Rw.numel():].view(Rt.shape)
@@ -752,9 +763,13 @@ class _Attention(torch.autograd.Function):
                 tab, ntabs, ih, iw, it = ctx.tc_tables[:5]
                 a.rel_tab, a.idx_h, a.idx_w, a.idx_t = tab.data_ptr(), ih.data_ptr(), iw.data_ptr(), it.data_ptr()
                 a.ntab_h, a.ntab_w, a.ntab_t = ntabs
+                if d_tab is not None:
+                    a.d_rel_tab = d_tab.data_ptr()
         _call("svit_attn_bwd", C.byref(a), _stream(),
               tag=f"[B{B} h{h} Nq{Nq} Nk{Nk}]" if _prof is not None else None)
-        return dq, dk, dv, dRh, dRw, dRt, None, None, None, None, None, None
+        if d_tab is not None:
+            return dq, dk, dv, None, None, None, None, None, None, None, None, None, d_tab
+        return dq, dk, dv, dRh, dRw, dRt, None, None, None, None, None, None, None
 
 
 _sel_bwd_cache = {}
@@ -780,12 +795,13 @@ def key_select_table_bwd(k_thw, O, nep, device) -> torch.Tensor:
     return t
 
 
-def attention(q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables=None):
+def attention(q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables=None, tab=None):
     """softmax(scale q k^T + rel-pos bias) v + residual pooling -> [B, Nq, h*96] (attention.py:429-461).
     Rh/Rw/Rt: gathered tables (differentiable); tc_tables: (cat table bf16, [rows], idx_h, idx_w, idx_t, key codes)
-    for the tcgen05 kernel, or None."""
+    for the tcgen05 kernel, or None; tab: the concatenated fp32 table with autograd history (optional) -- where the
+    tensor-core backward supports it, the rel-pos gradient arrives through `tab` instead of Rh / Rw / Rt."""
     return _Attention.apply(q, k, v, Rh, Rw, Rt, tuple(q_thw), tuple(k_thw), O, float(scale), tc_tables,
-                            torch.is_grad_enabled())
+                            torch.is_grad_enabled(), tab)
 
 
 # --------------------------------------------------------------------------------------------

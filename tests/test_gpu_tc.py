@@ -293,6 +293,52 @@ def test_attention_backward_tc_matches_simt(shape, unfused):
         assert err < (5e-2 if name.startswith("dR") else 2e-2), (shape, name, err)
 
 
+TAB_SHAPES = [ATTN_SHAPES[i] for i in (8, 9, 10, 11, 12, 14)]  # the last one (Nk = 54) must fall back to the gathered path
+
+
+@pytest.mark.parametrize("shape", TAB_SHAPES)
+def test_attention_backward_table_space_gradient(shape):
+    """Rel-pos gradient in table-row space (attn_bwd_tc.cu: G scatter, dq += G . T and dT = G^T . q as tcgen05 GEMMs;
+    attention.py:116-119 is the gather it differentiates through) against the CUDA-core fp32 backward that goes through
+    the gathered tables, with the gradients compared ON THE PARAMETERS (the three un-gathered tables)."""
+    from svit_b200 import msa
+    B, h, q_thw, k_thw, O = shape
+    q, k, v, _, tc_tables = _attn_inputs(B, h, q_thw, k_thw, O, seed=53)
+    scale = 96 ** -0.5
+    pairs = ((q_thw[1], k_thw[1]), (q_thw[2], k_thw[2]), (q_thw[0], k_thw[0]))
+    gen = torch.Generator().manual_seed(7)
+    Nq, Nk = q.shape[2], k.shape[2]
+    dout = torch.randn(B, Nq, h * 96, generator=gen).to(torch.bfloat16).to(DEV)
+    base = [t.float() for t in torch.split(tc_tables[0], tc_tables[1])]  # bf16-representable table values
+
+    def run(dtype, impl, table_space):
+        ops.set_impl(attn=impl)
+        try:
+            ins = [t.detach().to(dtype).requires_grad_(True) for t in (q, k, v)]
+            rels = [t.detach().clone().requires_grad_(True) for t in base]
+            Rs = [msa.gathered_rel_pos(r, a, b) for r, (a, b) in zip(rels, pairs)]
+            tabs = tc_tables if dtype == torch.bfloat16 else None
+            out = ops.attention(ins[0], ins[1], ins[2], Rs[0], Rs[1], Rs[2], q_thw, k_thw, O, scale, tabs,
+                                torch.cat(rels) if table_space else None)
+            out.backward(dout.to(dtype))
+            torch.cuda.synchronize()
+            return [cpu(t.grad) for t in ins + rels]
+        finally:
+            ops.set_impl(attn=ops.IMPL_AUTO)
+
+    ref = run(torch.float32, ops.IMPL_SIMT, False)
+    gathered = run(torch.bfloat16, ops.IMPL_AUTO, False)
+    got = run(torch.bfloat16, ops.IMPL_AUTO, True)
+    for name, g, r, o in zip(("dq", "dk", "dv", "d_rel_h", "d_rel_w", "d_rel_t"), got, ref, gathered):
+        assert torch.isfinite(g).all(), name
+        err, err_g = max_rel_err(g, r), max_rel_err(o, r)
+        print(f"{shape} {name}: table-space {err:.2e}, gathered {err_g:.2e}")
+        # dq / dk / dv: 2e-2, or -- where the bf16 rounding of dS alone already costs the gathered path more than that
+        # (measured: 2.5e-2 on the 4 x 10 x 10 key grid with 128 object keys) -- no worse than the gathered path, 3e-2 at most
+        bound = 5e-2 if name.startswith("d_rel") else max(2e-2, min(3e-2, 1.05 * err_g))
+        assert err < bound, (shape, name, err, err_g)
+
+
 # ------------------------------------------------------------------------------------------------ folded LayerNorm
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_row_stats(dtype):
