@@ -198,12 +198,16 @@ typedef struct svit_attn_args {
   float* ws_dq;     /* scratch fp32 [B,h,Nq,96] */
   const void* sel_bwd;
   int32_t nep;
-  /* optional, tensor-core backward with rel_tab / idx_* present, ntab_h + ntab_w + ntab_t <= 96 and Nkp >= 192: the
+  /* optional, tensor-core backward with rel_tab / idx_* present, ntab = ntab_h + ntab_w + ntab_t rounded up to 8 at most
+   * min(Nkp, 512), Nkp >= 192 and (ntab <= 96 or ws_etab present), else SVIT_ENOTSUP: the
    * rel-pos gradient in TABLE space, fp32 [ntab_h + ntab_w + ntab_t, 96] (overwritten): row g = sum over query rows of
    * G[row, g] q[row] with G the scatter of dE into table-row space.  The table term of dq (G . rel_tab) and this
    * gradient (G^T . q) then run as two tcgen05 GEMMs and d_rel_h / d_rel_w / d_rel_t are NOT written (the caller maps
    * the table rows back through the index tables). */
   float* d_rel_tab;
+  /* optional scratch, tensor-core backward: fp32 [B,h,Nq, ntab rounded up to 8] for E_tab = q . rel_tab^T when the
+   * concatenated table has more than 96 rows (up to 96 rows the dQ scratch holds it) */
+  float* ws_etab;
 } svit_attn_args;
 int svit_attn_fwd(const svit_attn_args* args, void* stream);
 int svit_attn_bwd(const svit_attn_args* args, void* stream);

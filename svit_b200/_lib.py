@@ -48,7 +48,7 @@ class AttnArgs(C.Structure):
         ("ntab_h", i32), ("ntab_w", i32), ("ntab_t", i32),
         ("sel_tab", vp), ("sel_cols", i32),
         ("ws_s", vp), ("ws_dp", vp), ("ws_p", vp), ("ws_ds", vp), ("ws_dq", vp), ("sel_bwd", vp), ("nep", i32),
-        ("d_rel_tab", vp),
+        ("d_rel_tab", vp), ("ws_etab", vp),
     ]
 
 

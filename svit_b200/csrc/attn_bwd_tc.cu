@@ -48,7 +48,7 @@ __device__ __forceinline__ void unpack8(const uint4 w, float f[8]) {
   f[6] = __uint_as_float(w.w << 16); f[7] = __uint_as_float(w.w & 0xffff0000u);
 }
 
-// etab != nullptr: the bias terms are rows of E_tab = q . T^T (fp32 [B h Nq, 96], one tcgen05 GEMM against the
+// etab != nullptr: the bias terms are rows of E_tab = q . T^T (fp32 [B h Nq, ldt], one tcgen05 GEMM against the
 // un-gathered concatenated table, as in the forward kernel) picked through the integer index tables -- one 4-byte read
 // per (row, column) instead of a 96-long dot product against a gathered table row (12 x 16-byte loads + 24 shared-memory
 // reads each: the kernel was bound by them).
@@ -56,7 +56,7 @@ __device__ __forceinline__ void unpack8(const uint4 w, float f[8]) {
 // kernel's score product; hi + lo carries 16 mantissa bits, so the backward keeps differentiating the exact bias) into
 // the ws_e scratch viewed as bf16 [B h Nq, hi (nep) | lo (nep)] -- the same bytes as its fp32 rows; else fp32 E.
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, int nep, const float* __restrict__ etab,
-                                                            int e16) {
+                                                            int ldt, int e16) {
   __shared__ __align__(16) float sq[PQ][QP];
   const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
   const int64_t Nq = 1 + Lq + a.O;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, in
         if (c < a.kh) gidx = __ldg(a.idx_h + i * a.kh + c);
         else if (c < a.kh + a.kw) gidx = a.ntab_h + __ldg(a.idx_w + j * a.kw + (c - a.kh));
         else gidx = a.ntab_h + a.ntab_w + __ldg(a.idx_t + t * a.kt + (c - a.kh - a.kw));
-        acc = __ldg(etab + ((int64_t)bh * Nq + row) * D + gidx);
+        acc = __ldg(etab + ((int64_t)bh * Nq + row) * ldt + gidx);
       } else {
       const uint4* R = reinterpret_cast<const uint4*>(rel_row(a, c, i, j, t));
       float acc2 = 0.f;
@@ -207,18 +207,20 @@ __global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(svit_attn_args a,
   }
 }
 
-// ---- G[row, g] = sum over the columns c with table row g(row, c) == g of dE[row, c]   (bf16 [B h Nq, 96]) -----------
+// ---- G[row, g] = sum over the columns c with table row g(row, c) == g of dE[row, c]   (bf16 [B h Nq, ldg]) ----------
 // The bias gradient in table-row space: with it the table term of dq is G . T and the table gradient G^T . q, two
 // GEMMs instead of a 96-long FMA chain per (row, column) against gathered table rows in two CUDA-core kernels.
-__global__ void __launch_bounds__(256) attn_bwd_gscatter_kernel(svit_attn_args a, int nep, bf16* __restrict__ G,
+// ldg = table rows rounded up to 8 (pad columns are written as zeros); 16 rows per CTA, 16 lanes per row.
+__global__ void __launch_bounds__(256) attn_bwd_gscatter_kernel(svit_attn_args a, int nep, bf16* __restrict__ G, int ldg,
                                                                 int64_t total_rows) {
-  __shared__ float sg[16][D];
+  extern __shared__ float sg_all[];  // [16][ldg]
   const int l = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  float* sg = sg_all + grp * ldg;
   const int64_t Lq = (int64_t)a.qt * a.qh * a.qw;
   const int64_t Nq = 1 + Lq + a.O;
   const int ne = a.kh + a.kw + a.kt;
   const int64_t R = (int64_t)blockIdx.x * 16 + grp;
-  for (int i = l; i < D; i += 16) sg[grp][i] = 0.f;
+  for (int i = l; i < ldg; i += 16) sg[i] = 0.f;
   __syncthreads();
   if (R < total_rows) {
     const int64_t row = R % Nq;
@@ -230,19 +232,21 @@ __global__ void __launch_bounds__(256) attn_bwd_gscatter_kernel(svit_attn_args a
         if (c < a.kh) gidx = __ldg(a.idx_h + iq * a.kh + c);
         else if (c < a.kh + a.kw) gidx = a.ntab_h + __ldg(a.idx_w + jq * a.kw + (c - a.kh));
         else gidx = a.ntab_h + a.ntab_w + __ldg(a.idx_t + tq * a.kt + (c - a.kh - a.kw));
-        atomicAdd(&sg[grp][gidx], __ldg(a.ws_de + R * nep + c));  // two columns may share a table row
+        atomicAdd(&sg[gidx], __ldg(a.ws_de + R * nep + c));  // two columns may share a table row
       }
     }
   }
   __syncthreads();
-  if (R < total_rows && l < D / 8) {
-    const float* s = &sg[grp][8 * l];
-    __nv_bfloat162 o0 = __floats2bfloat162_rn(s[0], s[1]), o1 = __floats2bfloat162_rn(s[2], s[3]);
-    __nv_bfloat162 o2 = __floats2bfloat162_rn(s[4], s[5]), o3 = __floats2bfloat162_rn(s[6], s[7]);
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&o0); o.y = *reinterpret_cast<uint32_t*>(&o1);
-    o.z = *reinterpret_cast<uint32_t*>(&o2); o.w = *reinterpret_cast<uint32_t*>(&o3);
-    *(reinterpret_cast<uint4*>(G + R * D) + l) = o;
+  if (R < total_rows) {
+    for (int u = l; u < ldg / 8; u += 16) {
+      const float* s = &sg[8 * u];
+      __nv_bfloat162 o0 = __floats2bfloat162_rn(s[0], s[1]), o1 = __floats2bfloat162_rn(s[2], s[3]);
+      __nv_bfloat162 o2 = __floats2bfloat162_rn(s[4], s[5]), o3 = __floats2bfloat162_rn(s[6], s[7]);
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&o0); o.y = *reinterpret_cast<uint32_t*>(&o1);
+      o.z = *reinterpret_cast<uint32_t*>(&o2); o.w = *reinterpret_cast<uint32_t*>(&o3);
+      *(reinterpret_cast<uint4*>(G + R * ldg) + u) = o;
+    }
   }
 }
 
@@ -344,23 +348,30 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
   int rc;
 
   svit_gemm_args g;
-  // E_tab = q . T^T into the (still unused) fp32 dQ scratch when the concatenated table has at most 96 rows
+  // E_tab = q . T^T: into the (still unused) fp32 dQ scratch when the concatenated table has at most 96 rows, into the
+  // caller's ws_etab (row stride = table rows rounded up to 8) beyond that
   const int ntab = a->ntab_h + a->ntab_w + a->ntab_t;
+  const int ntabp = (ntab + 7) / 8 * 8;
   const float* etab = nullptr;
-  if (a->rel_tab && a->idx_h && a->idx_w && a->idx_t && ntab >= 8 && ntab <= D) {
+  int ldt = 0;
+  if (a->rel_tab && a->idx_h && a->idx_w && a->idx_t && ntab >= 8 && (ntab <= D || a->ws_etab)) {
+    float* dst = ntab <= D ? a->ws_dq : a->ws_etab;
+    ldt = ntab <= D ? D : ntabp;
     gemm_defaults(g);
     g.A = a->q; g.lda = D;
     g.B = a->rel_tab; g.ldb = D; g.transB = 1;
-    g.C = a->ws_dq; g.ldc = D; g.out_dtype = SVIT_F32;
+    g.C = dst; g.ldc = ldt; g.out_dtype = SVIT_F32;
     g.M = rows; g.N = ntab; g.K = D; g.batch = 1;
     if (svit_gemm_tc_supported(&g)) {
       if ((rc = svit_gemm_tc(&g, st))) return rc;
-      etab = a->ws_dq;
+      etab = dst;
     }
   }
-  if (a->d_rel_tab && !(etab && Nkp >= 2 * D)) return SVIT_ENOTSUP;  // the caller would read an unwritten gradient
+  // table-row space: G (bf16 [rows, ntabp]) takes the place of dS, dq_tab (fp32 [rows, 96]) that of P
+  const bool tab_space = a->d_rel_tab && etab && Nkp >= 2 * D && ntabp <= Nkp && ntabp <= 512;
+  if (a->d_rel_tab && !tab_space) return SVIT_ENOTSUP;  // the caller would read an unwritten gradient
   const bool fused = !(a->ws_s && a->ws_dp) && svit_attn_bwd_sdp_supported(a);
-  attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep, etab, fused ? 1 : 0);
+  attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep, etab, ldt, fused ? 1 : 0);
   SVIT_CHECK_LAUNCH();
 
   if (fused) {
@@ -428,15 +439,15 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
   g.M = rows; g.N = nep; g.K = Nk; g.batch = 1;
   if ((rc = run_gemm(g, st))) return rc;
 
-  if (a->d_rel_tab && etab && Nkp >= 2 * D) {
-    // table-row space: G (bf16 [rows, 96]) takes the place of dS, dq_tab = G . T (fp32 [rows, 96]) that of P -- both
-    // scratch matrices have been consumed by the GEMMs above and a row of either holds at least 96 fp32 values
+  if (tab_space) {
+    // both scratch matrices have been consumed by the GEMMs above; a row of dS holds ntabp bf16 values and a row of P
+    // 96 fp32 values (checked above)
     bf16* G = (bf16*)a->ws_ds;
     float* dq_tab = (float*)a->ws_p;
-    attn_bwd_gscatter_kernel<<<(unsigned)ceil_div64(rows, 16), 256, 0, st>>>(*a, nep, G, rows);
+    attn_bwd_gscatter_kernel<<<(unsigned)ceil_div64(rows, 16), 256, (size_t)16 * ntabp * 4, st>>>(*a, nep, G, ntabp, rows);
     SVIT_CHECK_LAUNCH();
     gemm_defaults(g);
-    g.A = G; g.lda = D;
+    g.A = G; g.lda = ntabp;
     g.B = a->rel_tab; g.ldb = D; g.transB = 0;  // T stored [K = table rows, N = 96]
     g.C = dq_tab; g.ldc = D; g.out_dtype = SVIT_F32;
     g.M = rows; g.N = D; g.K = ntab; g.batch = 1;
@@ -445,7 +456,7 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
     SVIT_CHECK_LAUNCH();
     // d_rel_tab = G^T . q  (split-K over the rows; the GEMM zeroes its output)
     gemm_defaults(g);
-    g.A = G; g.lda = D; g.transA = 1;
+    g.A = G; g.lda = ntabp; g.transA = 1;
     g.B = a->q; g.ldb = D; g.transB = 0;
     g.C = a->d_rel_tab; g.ldc = D; g.out_dtype = SVIT_F32;
     g.M = ntab; g.N = D; g.K = rows; g.batch = 1;

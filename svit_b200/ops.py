@@ -733,9 +733,11 @@ class _Attention(torch.autograd.Function):
         es = (ne + 15) // 16 * 16 if tc else ne
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         d_tab = None
-        if tc and ctx.tab_grad and 8 <= sum(ctx.tc_tables[1]) <= d and (Nk + 7) // 8 * 8 >= 2 * d:
+        ntab = sum(ctx.tc_tables[1]) if ctx.tc_tables is not None else 0
+        ntabp, Nkp = (ntab + 7) // 8 * 8, (Nk + 7) // 8 * 8
+        if tc and ctx.tab_grad and ntab >= 8 and ntabp <= min(Nkp, 512) and Nkp >= 2 * d:
             # table-row space (attn_bwd_tc.cu: G scatter + two GEMMs); d_rel_h / d_rel_w / d_rel_t are not written
-            d_tab = torch.empty(sum(ctx.tc_tables[1]), d, dtype=torch.float32, device=dev)
+            d_tab = torch.empty(ntab, d, dtype=torch.float32, device=dev)
         dR = (torch.zeros if d_tab is None else torch.empty)(Rh.numel() + Rw.numel() + Rt.numel(), dtype=torch.float32,
                                                              device=dev)  # one fill
         dRh = dR[:Rh.numel()].view(Rh.shape)
@@ -763,6 +765,9 @@ class _Attention(torch.autograd.Function):
                 tab, ntabs, ih, iw, it = ctx.tc_tables[:5]
                 a.rel_tab, a.idx_h, a.idx_w, a.idx_t = tab.data_ptr(), ih.data_ptr(), iw.data_ptr(), it.data_ptr()
                 a.ntab_h, a.ntab_w, a.ntab_t = ntabs
+                if ntab > d and ntabp <= 512:  # E_tab = q . T^T does not fit the dQ scratch
+                    ws_etab = torch.empty(B, h, Nq, ntabp, dtype=torch.float32, device=dev)
+                    a.ws_etab = ws_etab.data_ptr()
                 if d_tab is not None:
                     a.d_rel_tab = d_tab.data_ptr()
         _call("svit_attn_bwd", C.byref(a), _stream(),

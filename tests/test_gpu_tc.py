@@ -293,7 +293,7 @@ def test_attention_backward_tc_matches_simt(shape, unfused):
         assert err < (5e-2 if name.startswith("dR") else 2e-2), (shape, name, err)
 
 
-TAB_SHAPES = [ATTN_SHAPES[i] for i in (8, 9, 10, 11, 12, 14)]  # the last one (Nk = 54) must fall back to the gathered path
+TAB_SHAPES = [ATTN_SHAPES[i] for i in (5, 7, 8, 9, 10, 11, 12, 14)]  # 237 / 125 / 69 / 41 / 85 table rows; the last one (Nk = 54) falls back to the gathered path
 
 
 @pytest.mark.parametrize("shape", TAB_SHAPES)
@@ -335,7 +335,12 @@ def test_attention_backward_table_space_gradient(shape):
         print(f"{shape} {name}: table-space {err:.2e}, gathered {err_g:.2e}")
         # dq / dk / dv: 2e-2, or -- where the bf16 rounding of dS alone already costs the gathered path more than that
         # (measured: 2.5e-2 on the 4 x 10 x 10 key grid with 128 object keys) -- no worse than the gathered path, 3e-2 at most
-        bound = 5e-2 if name.startswith("d_rel") else max(2e-2, min(3e-2, 1.05 * err_g))
+        # table gradients: 5e-2 as in the gathered-path test, or no worse than the gathered path where that one is beyond
+        # it already (frame mode, kt = 1: ONE table row collects the heavily cancelling sum over every query row, 7.1e-2)
+        if name.startswith("d_rel"):
+            bound = max(5e-2, min(1e-1, 1.05 * err_g))
+        else:
+            bound = max(2e-2, min(3e-2, 1.05 * err_g))
         assert err < bound, (shape, name, err, err_g)
 
 
