@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "../../include/svit_b200.h"
 
+#include <cstdlib>
 #define D SVIT_HEAD_DIM
 
 int svit_gemm_tc(const svit_gemm_args* a, cudaStream_t st);  // gemm_tc.cu
@@ -141,6 +142,73 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(svit_attn_args a, in
   }
 }
 
+// ---- prep, E_tab form: no shared memory, no CTA barrier, 32-bit token arithmetic -------------------------------------
+// 16 lanes per (b, head, query row) over the flat row index (16 rows per CTA): delta from three 16-byte loads per lane
+// and a 16-lane butterfly; the row's bias terms are 4-byte picks from its E_tab row through the integer index tables,
+// written as column pairs (bf16x2 hi / lo for the fused score product, or fp32).
+__global__ void __launch_bounds__(256) attn_bwd_prep_tab_kernel(svit_attn_args a, int nep, const float* __restrict__ etab,
+                                                                int ldt, int e16, int64_t total_rows) {
+  const int l = threadIdx.x & 15;
+  const int64_t R = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4);
+  const bool live = R < total_rows;
+  const int64_t Rc = live ? R : 0;
+  const int Lq = a.qt * a.qh * a.qw;
+  const int Nq = 1 + Lq + a.O;
+  const int ne = a.kh + a.kw + a.kt;
+  const int bh = (int)(Rc / Nq), row = (int)(Rc - (int64_t)bh * Nq);
+  const int b = bh / a.h, head = bh - b * a.h;
+  float part = 0.f;
+  if (live && l < D / 8) {
+    const int64_t off = (((int64_t)b * Nq + row) * a.h + head) * D + 8 * l;
+    float o[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>((const bf16*)a.out + off)), o);
+    unpack8(__ldg(reinterpret_cast<const uint4*>((const bf16*)a.dout + off)), g);
+    if (row >= 1) {
+      float qv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>((const bf16*)a.q + Rc * D) + l), qv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] -= qv[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part = fmaf(o[e], g[e], part);
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o, 16);
+  if (!live) return;
+  if (l == 0) a.ws_delta[Rc] = part;
+  const bool patch = row >= 1 && row <= Lq;
+  const int p = row - 1;
+  const int j = p % a.qw, pi = p / a.qw, i = pi % a.qh, t = pi / a.qh;
+  const float* erow = etab + Rc * ldt;
+  for (int c2 = l; c2 < nep / 2; c2 += 16) {
+    float v[2] = {0.f, 0.f};
+    if (patch) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = 2 * c2 + u;
+        if (c < ne) {
+          int gidx;
+          if (c < a.kh) gidx = __ldg(a.idx_h + i * a.kh + c);
+          else if (c < a.kh + a.kw) gidx = a.ntab_h + __ldg(a.idx_w + j * a.kw + (c - a.kh));
+          else gidx = a.ntab_h + a.ntab_w + __ldg(a.idx_t + t * a.kt + (c - a.kh - a.kw));
+          v[u] = __ldg(erow + gidx);
+        }
+      }
+    }
+    if (e16) {
+      // the same arithmetic as the gathered form: x = E / scale by an IEEE division, hi = rn(x), lo = rn(x - hi)
+      const float x0 = v[0] / a.scale, x1 = v[1] / a.scale;
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(x0, x1);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 - __low2float(hi), x1 - __high2float(hi));
+      __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(a.ws_e) + Rc * 2 * nep);
+      dst[c2] = hi;
+      dst[nep / 2 + c2] = lo;
+    } else {
+      reinterpret_cast<float2*>(a.ws_e + Rc * nep)[c2] = make_float2(v[0], v[1]);
+    }
+  }
+}
+
 // ---- softmax recompute + dS ----------------------------------------------------------------------------------
 // One warp per (b, head, query row); lanes own 4 consecutive keys per 128-key step.  Key -> E-column codes are
 // built once per CTA in shared memory (slot 64 = the always-zero entry used by cls / object keys).
@@ -221,7 +289,7 @@ __global__ void __launch_bounds__(256) attn_bwd_gscatter_kernel(svit_attn_args a
   const int ne = a.kh + a.kw + a.kt;
   const int64_t R = (int64_t)blockIdx.x * 16 + grp;
   for (int i = l; i < ldg; i += 16) sg[i] = 0.f;
-  __syncthreads();
+  __syncwarp();  // a 16-lane group only touches its own row of sg, and lies within one warp
   if (R < total_rows) {
     const int64_t row = R % Nq;
     if (row >= 1 && row <= Lq) {
@@ -236,7 +304,7 @@ __global__ void __launch_bounds__(256) attn_bwd_gscatter_kernel(svit_attn_args a
       }
     }
   }
-  __syncthreads();
+  __syncwarp();  // a 16-lane group only touches its own row of sg, and lies within one warp
   if (R < total_rows) {
     for (int u = l; u < ldg / 8; u += 16) {
       const float* s = &sg[8 * u];
@@ -371,7 +439,11 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
   const bool tab_space = a->d_rel_tab && etab && Nkp >= 2 * D && ntabp <= Nkp && ntabp <= 512;
   if (a->d_rel_tab && !tab_space) return SVIT_ENOTSUP;  // the caller would read an unwritten gradient
   const bool fused = !(a->ws_s && a->ws_dp) && svit_attn_bwd_sdp_supported(a);
-  attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep, etab, ldt, fused ? 1 : 0);
+  static const bool prep_cta_form = getenv("SVIT_ATTN_BWD_PREP_CTA") != nullptr;  // A / B switch for measurements
+  if (etab && rows < (int64_t)1 << 31 && !prep_cta_form)
+    attn_bwd_prep_tab_kernel<<<(unsigned)ceil_div64(rows, 16), 256, 0, st>>>(*a, nep, etab, ldt, fused ? 1 : 0, rows);
+  else
+    attn_bwd_prep_kernel<<<dim3((unsigned)ceil_div64(Nq, PQ), BH), 256, 0, st>>>(*a, nep, etab, ldt, fused ? 1 : 0);
   SVIT_CHECK_LAUNCH();
 
   if (fused) {
