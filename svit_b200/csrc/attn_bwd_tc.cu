@@ -383,6 +383,33 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(svit_attn_args a, 
   *(reinterpret_cast<uint4*>((bf16*)a.dq + Rc * D) + l) = o;
 }
 
+// ---- finish, table-row-space form: dq = dq_part + dq_tab + dO[rows >= 1] -- a flat 8-channel-per-thread stream ----------
+__global__ void __launch_bounds__(256) attn_bwd_finish_tab_kernel(svit_attn_args a, const float* __restrict__ dq_part,
+                                                                  const float* __restrict__ dq_tab, uint32_t total_vecs) {
+  const uint32_t v = blockIdx.x * 256u + threadIdx.x;  // (flat row, 8-channel vector); total_vecs < 2^31
+  if (v >= total_vecs) return;
+  const uint32_t R = v / (D / 8), u = v - R * (D / 8);
+  const uint32_t Nq = 1u + (uint32_t)(a.qt * a.qh * a.qw) + (uint32_t)a.O;
+  const uint32_t bh = R / Nq, row = R - bh * Nq;
+  const uint32_t b = bh / (uint32_t)a.h, head = bh - b * (uint32_t)a.h;
+  const float4* pa = reinterpret_cast<const float4*>(dq_part + (int64_t)R * D) + 2 * u;
+  const float4* pt = reinterpret_cast<const float4*>(dq_tab + (int64_t)R * D) + 2 * u;
+  const float4 ga = __ldg(pa), gb = __ldg(pa + 1), ta = __ldg(pt), tb = __ldg(pt + 1);
+  float g[8] = {ga.x + ta.x, ga.y + ta.y, ga.z + ta.z, ga.w + ta.w, gb.x + tb.x, gb.y + tb.y, gb.z + tb.z, gb.w + tb.w};
+  if (row >= 1) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>((const bf16*)a.dout + (((int64_t)b * Nq + row) * a.h + head) * D) + u), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] += f[e];
+  }
+  __nv_bfloat162 o0 = __floats2bfloat162_rn(g[0], g[1]), o1 = __floats2bfloat162_rn(g[2], g[3]);
+  __nv_bfloat162 o2 = __floats2bfloat162_rn(g[4], g[5]), o3 = __floats2bfloat162_rn(g[6], g[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&o0); o.y = *reinterpret_cast<uint32_t*>(&o1);
+  o.z = *reinterpret_cast<uint32_t*>(&o2); o.w = *reinterpret_cast<uint32_t*>(&o3);
+  *(reinterpret_cast<uint4*>((bf16*)a.dq + (int64_t)R * D) + u) = o;
+}
+
 void gemm_defaults(svit_gemm_args& g) {
   g = svit_gemm_args{};
   g.dtype = SVIT_BF16;
@@ -524,7 +551,11 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
     g.C = dq_tab; g.ldc = D; g.out_dtype = SVIT_F32;
     g.M = rows; g.N = D; g.K = ntab; g.batch = 1;
     if ((rc = run_gemm(g, st))) return rc;
-    attn_bwd_finish_kernel<<<(unsigned)ceil_div64(rows, 16), 256, 0, st>>>(*a, a->ws_dq, nep, rows, dq_tab);
+    if (rows * (D / 8) < (int64_t)1 << 31)
+      attn_bwd_finish_tab_kernel<<<(unsigned)ceil_div64(rows * (D / 8), 256), 256, 0, st>>>(*a, a->ws_dq, dq_tab,
+                                                                                         (uint32_t)(rows * (D / 8)));
+    else
+      attn_bwd_finish_kernel<<<(unsigned)ceil_div64(rows, 16), 256, 0, st>>>(*a, a->ws_dq, nep, rows, dq_tab);
     SVIT_CHECK_LAUNCH();
     // d_rel_tab = G^T . q  (split-K over the rows; the GEMM zeroes its output)
     gemm_defaults(g);

@@ -7,6 +7,7 @@
 //
 // Used for: qkv / proj / skip-proj / fc1(+GELU) / fc2(+residual) (attention.py:345,462,561; common.py:27-34),
 // the patch-embed GEMM (stem_helper.py:317) and every dgrad / wgrad of those.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/svit_b200.h"
 
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restri
     const int c8 = c8_0 + tx;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (ty < rg && c8 < n8) {
-#pragma unroll 4
+#pragma unroll 8
       for (int64_t r = r0 + ty; r < r1; r += rg) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * ld + c8 * 8));
         const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
@@ -229,7 +230,8 @@ int svit_colsum(const void* x, float* out, int64_t M, int N, int64_t ld, int dty
     const int n8 = N / 8, tpr = n8 < 256 ? n8 : 256;
     const unsigned gx = (unsigned)((n8 + tpr - 1) / tpr);
     int64_t rows = ceil_div64(M, ceil_div64((int64_t)svit_num_sms() * 4, gx));  // ~4 CTAs per SM
-    if (rows < 64) rows = 64;
+    static const int min_rows = getenv("SVIT_COLSUM_MINROWS") ? atoi(getenv("SVIT_COLSUM_MINROWS")) : 64;  // A / B switch
+    if (rows < min_rows) rows = min_rows;
     dim3 grid8(gx, (unsigned)ceil_div64(M, rows));
     colsum_bf16x8_kernel<<<grid8, 256, 0, st>>>((const bf16*)x, out, M, N, ld, rows);
     SVIT_CHECK_LAUNCH();
