@@ -142,7 +142,9 @@ int svit_colsum(const void* x, float* out, int64_t M, int N, int64_t ld, int dty
  *   S = scale * q k^T ; S[patch q, patch k] += q . (Rh[i,i'] + Rw[j,j'] + Rt[t,t']) (un-scaled q)
  *   out = softmax(S) v ; out[rows >= 1] += q
  * q [B,h,Nq,96], k/v [B,h,Nk,96]; rel_* are the GATHERED tables R[a, b, :] (activation dtype), built on the host
- * side with the reference's exact fp32 index expression; out [B, Nq, h, 96] (heads merged). lse [B,h,Nq] or NULL. */
+ * side with the reference's exact fp32 index expression; out [B, Nq, h, 96] (heads merged). lse [B,h,Nq] or NULL.
+ * rel_* (and d_rel_*) may be NULL where only the tensor-core kernels run: the forward with rel_tab / idx_* present, the
+ * backward with d_rel_tab; a call that would need them on a CUDA-core path returns SVIT_EINVAL. */
 typedef struct svit_attn_args {
   const void* q;
   const void* k;

@@ -465,6 +465,7 @@ int svit_attn_bwd_tc(const svit_attn_args* a, cudaStream_t st) {
   // table-row space: G (bf16 [rows, ntabp]) takes the place of dS, dq_tab (fp32 [rows, 96]) that of P
   const bool tab_space = a->d_rel_tab && etab && Nkp >= 2 * D && ntabp <= Nkp && ntabp <= 512;
   if (a->d_rel_tab && !tab_space) return SVIT_ENOTSUP;  // the caller would read an unwritten gradient
+  if (!tab_space && !(a->rel_h && a->rel_w && a->rel_t && a->d_rel_h && a->d_rel_w && a->d_rel_t)) return SVIT_EINVAL;
   const bool fused = !(a->ws_s && a->ws_dp) && svit_attn_bwd_sdp_supported(a);
   static const bool prep_cta_form = getenv("SVIT_ATTN_BWD_PREP_CTA") != nullptr;  // A / B switch for measurements
   if (etab && rows < (int64_t)1 << 31 && !prep_cta_form)

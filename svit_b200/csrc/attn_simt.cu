@@ -166,7 +166,7 @@ int svit_attn_fwd_tc3(const svit_attn_args* a, cudaStream_t st);  // attn_tc3.cu
 int svit_attn_tc3_supported(const svit_attn_args* a);
 
 static int attn_check(const svit_attn_args* a) {
-  if (!a || !a->q || !a->k || !a->v || !a->out || !a->rel_h || !a->rel_w || !a->rel_t) return SVIT_EINVAL;
+  if (!a || !a->q || !a->k || !a->v || !a->out) return SVIT_EINVAL;  // the gathered tables: CUDA-core kernels only
   if (a->B < 0 || a->h < 1 || a->O < 1 || a->qt < 1 || a->qh < 1 || a->qw < 1 || a->kt < 1 || a->kh < 1 || a->kw < 1)
     return SVIT_EINVAL;
   return 0;
@@ -185,6 +185,7 @@ extern "C" int svit_attn_fwd(const svit_attn_args* a, void* stream) {
   if (a->impl == 0 && svit_attn_tc3_supported(a)) return svit_attn_fwd_tc3(a, st);
   if (a->impl == 0 && svit_attn_tc_supported(a)) return svit_attn_fwd_tc(a, st);
   if (a->kh + a->kw + a->kt > MAXE) return SVIT_ENOTSUP;
+  if (!a->rel_h || !a->rel_w || !a->rel_t) return SVIT_EINVAL;  // the CUDA-core kernel reads the gathered tables
   const int64_t Nq = 1 + (int64_t)a->qt * a->qh * a->qw + a->O;
   dim3 grid((unsigned)ceil_div64(Nq, AQ), (unsigned)(a->B * a->h));
   size_t smem = sizeof(AttnSmem);

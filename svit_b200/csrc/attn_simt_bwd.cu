@@ -404,15 +404,19 @@ int svit_attn_bwd_drel(const svit_attn_args* a, int estride, cudaStream_t st) {
 }
 
 extern "C" int svit_attn_bwd(const svit_attn_args* a, void* stream) {
-  if (!a || !a->q || !a->k || !a->v || !a->out || !a->lse || !a->dout || !a->dq || !a->dk || !a->dv || !a->d_rel_h ||
-      !a->d_rel_w || !a->d_rel_t || !a->ws_e || !a->ws_de || !a->ws_delta)
+  if (!a || !a->q || !a->k || !a->v || !a->out || !a->lse || !a->dout || !a->dq || !a->dk || !a->dv || !a->ws_e ||
+      !a->ws_de || !a->ws_delta)
     return SVIT_EINVAL;
+  // gathered tables and their gradients: required unless the gradient is asked for in table-row space (d_rel_tab)
+  const bool gathered = a->rel_h && a->rel_w && a->rel_t && a->d_rel_h && a->d_rel_w && a->d_rel_t;
+  if (!gathered && !a->d_rel_tab) return SVIT_EINVAL;
   if (a->kh + a->kw + a->kt > MAXE) return SVIT_ENOTSUP;
   if (a->B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (a->impl == 2) return svit_attn_bwd_tc_supported(a) ? svit_attn_bwd_tc(a, st) : SVIT_ENOTSUP;
   if (a->impl == 0 && svit_attn_bwd_tc_supported(a)) return svit_attn_bwd_tc(a, st);
   if (a->d_rel_tab) return SVIT_ENOTSUP;  // the table-space gradient exists in the tensor-core path only
+  if (!gathered) return SVIT_EINVAL;
   if (a->dtype == SVIT_F32) return launch_bwd<float>(a, st);
   if (a->dtype == SVIT_BF16) return launch_bwd<bf16>(a, st);
   return SVIT_EINVAL;

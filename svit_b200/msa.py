@@ -238,9 +238,6 @@ class MultiScaleAttention(nn.Module):
             hit = self._rel_cache.get(cache_key)
             if hit is not None:
                 return hit
-        Rh = gathered_rel_pos(self.rel_pos_h, q_shape[1], k_shape[1])
-        Rw = gathered_rel_pos(self.rel_pos_w, q_shape[2], k_shape[2])
-        Rt = gathered_rel_pos(self.rel_pos_t, q_shape[0], k_shape[0])
         tc_tables = None
         tab = None
         if dtype == torch.bfloat16:
@@ -256,6 +253,13 @@ class MultiScaleAttention(nn.Module):
                          _index32_on(device, q_shape[1], k_shape[1]), _index32_on(device, q_shape[2], k_shape[2]),
                          _index32_on(device, q_shape[0], k_shape[0]), key_column_codes(k_shape, O, device),
                          key_select_table(k_shape, O, device))
+        if tab is not None and ops.attention_tables_only(dtype, q_shape, k_shape, O, tab.shape[0]):
+            # training on the tensor-core kernels: neither direction reads the gathered tables (48 gathers + 48 casts per step)
+            Rh = Rw = Rt = None
+        else:
+            Rh = gathered_rel_pos(self.rel_pos_h, q_shape[1], k_shape[1])
+            Rw = gathered_rel_pos(self.rel_pos_w, q_shape[2], k_shape[2])
+            Rt = gathered_rel_pos(self.rel_pos_t, q_shape[0], k_shape[0])
         if cache_key is not None:
             Rh, Rw, Rt = (r.to(dtype).contiguous() for r in (Rh, Rw, Rt))
             # entries of older parameter versions go (a CUDA graph that captured them re-captures on a version change

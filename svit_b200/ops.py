@@ -676,7 +676,8 @@ def skip_pool(x, thw, O, stride_hw):
 def _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale):
     a = AttnArgs()
     a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
-    a.rel_h, a.rel_w, a.rel_t = Rh.data_ptr(), Rw.data_ptr(), Rt.data_ptr()
+    if Rh is not None:  # None: tensor-core kernels only (un-gathered table + index tables)
+        a.rel_h, a.rel_w, a.rel_t = Rh.data_ptr(), Rw.data_ptr(), Rt.data_ptr()
     a.out, a.lse = out.data_ptr(), _p(lse)
     a.B, a.h = q.shape[0], q.shape[1]
     a.qt, a.qh, a.qw = q_thw
@@ -685,12 +686,27 @@ def _attn_args(q, k, v, Rh, Rw, Rt, out, lse, q_thw, k_thw, O, scale):
     return a
 
 
+def attention_tables_only(dtype, q_thw, k_thw, O, ntab) -> bool:
+    """True where forward and backward of a bf16 attention run on the tensor-core kernels alone, with the rel-pos gradient
+    in table-row space: the caller then need not build the gathered tables R[a, b, :] (attention.py:116-119) at all.
+    Mirrors the conditions of svit_attn_bwd_tc (attn_bwd_tc.cu); a disagreement fails loudly there (SVIT_EINVAL)."""
+    if dtype != torch.bfloat16 or _state["attn_impl"] == _lib.IMPL_SIMT or not _state["attn_tab_grad"]:
+        return False
+    ne = k_thw[0] + k_thw[1] + k_thw[2]
+    Nk = 1 + k_thw[0] * k_thw[1] * k_thw[2] + O
+    ntabp, Nkp = (ntab + 7) // 8 * 8, (Nk + 7) // 8 * 8
+    return ne <= 64 and ntab >= 8 and ntabp <= min(Nkp, 512) and Nkp >= 2 * HEAD_DIM and Nk <= 32768
+
+
 class _Attention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, Rh, Rw, Rt, q_thw, k_thw, O, scale, tc_tables, grad_mode, tab=None):
         _chk(q, "attention")
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-        Rh, Rw, Rt = (r.to(q.dtype).contiguous() for r in (Rh, Rw, Rt))
+        if Rh is None:
+            assert tc_tables is not None, "attention without gathered rel-pos tables needs the tensor-core tables"
+        else:
+            Rh, Rw, Rt = (r.to(q.dtype).contiguous() for r in (Rh, Rw, Rt))
         B, h, Nq, d = q.shape
         assert d == HEAD_DIM, "svit_b200 attention kernels are specialised for head_dim 96"
         need = grad_mode and any(ctx.needs_input_grad[:6])
@@ -738,16 +754,20 @@ class _Attention(torch.autograd.Function):
         if tc and ctx.tab_grad and ntab >= 8 and ntabp <= min(Nkp, 512) and Nkp >= 2 * d:
             # table-row space (attn_bwd_tc.cu: G scatter + two GEMMs); d_rel_h / d_rel_w / d_rel_t are not written
             d_tab = torch.empty(ntab, d, dtype=torch.float32, device=dev)
-        dR = (torch.zeros if d_tab is None else torch.empty)(Rh.numel() + Rw.numel() + Rt.numel(), dtype=torch.float32,
-                                                             device=dev)  # one fill
-        dRh = dR[:Rh.numel()].view(Rh.shape)
-        dRw = dR[Rh.numel():Rh.numel() + Rw.numel()].view(Rw.shape)
-        dRt = dR[Rh.numel() + Rw.numel():].view(Rt.shape)
+        dRh = dRw = dRt = None
+        if d_tab is None:
+            if Rh is None:
+                raise RuntimeError("attention backward: no gathered rel-pos tables and no table-row-space path for this shape")
+            dR = torch.zeros(Rh.numel() + Rw.numel() + Rt.numel(), dtype=torch.float32, device=dev)  # one fill
+            dRh = dR[:Rh.numel()].view(Rh.shape)
+            dRw = dR[Rh.numel():Rh.numel() + Rw.numel()].view(Rw.shape)
+            dRt = dR[Rh.numel() + Rw.numel():].view(Rt.shape)
         ws_e = torch.empty(B, h, Nq, es, dtype=torch.float32, device=dev)
         ws_de = torch.empty(B, h, Nq, es, dtype=torch.float32, device=dev)
         ws_delta = torch.empty(B, h, Nq, dtype=torch.float32, device=dev)
         a.dout, a.dq, a.dk, a.dv = dout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
-        a.d_rel_h, a.d_rel_w, a.d_rel_t = dRh.data_ptr(), dRw.data_ptr(), dRt.data_ptr()
+        if dRh is not None:
+            a.d_rel_h, a.d_rel_w, a.d_rel_t = dRh.data_ptr(), dRw.data_ptr(), dRt.data_ptr()
         a.ws_e, a.ws_de, a.ws_delta = ws_e.data_ptr(), ws_de.data_ptr(), ws_delta.data_ptr()
         if tc:
             Nkp = (Nk + 7) // 8 * 8

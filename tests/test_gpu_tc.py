@@ -317,6 +317,8 @@ def test_attention_backward_table_space_gradient(shape):
             ins = [t.detach().to(dtype).requires_grad_(True) for t in (q, k, v)]
             rels = [t.detach().clone().requires_grad_(True) for t in base]
             Rs = [msa.gathered_rel_pos(r, a, b) for r, (a, b) in zip(rels, pairs)]
+            if table_space and ops.attention_tables_only(dtype, q_thw, k_thw, O, sum(tc_tables[1])):
+                Rs = [None, None, None]  # what MultiScaleAttention passes in training: no gathered tables at all
             tabs = tc_tables if dtype == torch.bfloat16 else None
             out = ops.attention(ins[0], ins[1], ins[2], Rs[0], Rs[1], Rs[2], q_thw, k_thw, O, scale, tabs,
                                 torch.cat(rels) if table_space else None)
