@@ -189,3 +189,27 @@ def test_lr_policy_matches_reference():
         for e in (0.0, 0.37, 4.99, 5.0, 12.5, 49.999):
             assert get_epoch_lr(e, c) == ref_opt.get_epoch_lr(e, c), (e, c.SOLVER.WARMUP_EPOCHS)
     assert get_epoch_lr(0.0, cfg)["lr"] == cfg.SOLVER.BASE_LR
+
+
+def test_attention_tables_only_predicate():
+    """ops.attention_tables_only mirrors the kernel-side conditions of the table-row-space backward (attn_bwd_tc.cu):
+    every ssv2.yaml block qualifies in bf16 (237 / 125 / 69 / 41 table rows, 457 keys), the frames pass (T = 1:
+    54 keys) and the fp32 parity mode keep the gathered tables R[a, b, :] of attention.py:116-119."""
+    O_tok = 64
+    grids = {56: (8, 56, 56), 28: (8, 28, 28), 14: (8, 14, 14), 7: (8, 7, 7)}
+    for q_thw in grids.values():
+        k_thw = (8, 7, 7)
+        ntab = sum(2 * max(a, b) - 1 for a, b in zip(q_thw, k_thw))
+        assert ops.attention_tables_only(torch.bfloat16, q_thw, k_thw, O_tok, ntab), q_thw
+        assert not ops.attention_tables_only(torch.float32, q_thw, k_thw, O_tok, ntab)
+    # frames pass: one frame, 1 + 49 + 4 keys -- fewer than the 192 the scratch reuse needs
+    assert not ops.attention_tables_only(torch.bfloat16, (1, 14, 14), (1, 7, 7), 4, 27 + 27 + 1)
+    # a table with more than 512 rows, or more table rows than keys
+    assert not ops.attention_tables_only(torch.bfloat16, (8, 300, 300), (8, 7, 7), 64, 599 + 599 + 15)
+    assert not ops.attention_tables_only(torch.bfloat16, (8, 56, 56), (2, 7, 7), 64, 111 + 111 + 15)
+    prev = ops._state["attn_tab_grad"]
+    try:
+        ops._state["attn_tab_grad"] = False
+        assert not ops.attention_tables_only(torch.bfloat16, (8, 14, 14), (8, 7, 7), 64, 69)
+    finally:
+        ops._state["attn_tab_grad"] = prev
