@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_tab_kernel(svit_attn_args a
   const int Lq = a.qt * a.qh * a.qw;
   const int Nq = 1 + Lq + a.O;
   const int ne = a.kh + a.kw + a.kt;
-  const int bh = (int)(Rc / Nq), row = (int)(Rc - (int64_t)bh * Nq);
+  const int bh = (int)((uint32_t)Rc / (uint32_t)Nq), row = (int)((uint32_t)Rc - (uint32_t)bh * (uint32_t)Nq);  // total_rows < 2^31
   const int b = bh / a.h, head = bh - b * a.h;
   float part = 0.f;
   if (live && l < D / 8) {
@@ -291,10 +291,12 @@ __global__ void __launch_bounds__(256) attn_bwd_gscatter_kernel(svit_attn_args a
   for (int i = l; i < ldg; i += 16) sg[i] = 0.f;
   __syncwarp();  // a 16-lane group only touches its own row of sg, and lies within one warp
   if (R < total_rows) {
-    const int64_t row = R % Nq;
-    if (row >= 1 && row <= Lq) {
-      const int64_t p = row - 1;
-      const int jq = (int)(p % a.qw), iq = (int)((p / a.qw) % a.qh), tq = (int)(p / ((int64_t)a.qw * a.qh));
+    // 32-bit index arithmetic where the flat row index fits (ncu: four 64-bit divisions per thread made the kernel
+    // issue-bound); p / (qw qh) == (p / qw) / qh for non-negative integers
+    const int row = total_rows <= 0x7fffffff ? (int)((uint32_t)R % (uint32_t)Nq) : (int)(R % Nq);
+    if (row >= 1 && row <= (int)Lq) {
+      const int p = row - 1;
+      const int jq = p % a.qw, pi = p / a.qw, iq = pi % a.qh, tq = pi / a.qh;
       for (int c = l; c < ne; c += 16) {
         int gidx;
         if (c < a.kh) gidx = __ldg(a.idx_h + iq * a.kh + c);
